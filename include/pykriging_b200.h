@@ -1,0 +1,128 @@
+/*
+ * pykriging_b200 -- C ABI of the B200-native pyKriging fit/predict hot path.
+ *
+ * This is the drop-in boundary for the reference's `matrixops` mixin
+ * (capaulson/pyKriging, pyKriging/matrixops.py) and for the per-candidate / per-point
+ * Python loops that drive it (pyKriging/krige.py, pyKriging/regressionkrige.py).
+ * Every entry point cites the reference interface it replaces.  The reference is pure
+ * Python, so the binding a maintainer adds is a ctypes stub.
+ *
+ * Conventions
+ *   - All arithmetic is FP64.  Matrices are row-major (C order), like the reference's
+ *     NumPy arrays.  Coordinates are in MODEL units (already min-max normalised, as
+ *     self.X / self.y are after normalizeData(), krige.py:117-133).
+ *   - Every data pointer may be a HOST pointer or a DEVICE pointer of the handle's GPU;
+ *     the library detects which.  Host buffers are copied in/out inside the call (the
+ *     call returns after outputs are valid); device buffers are used in place and the
+ *     call is stream-ordered (use pk_synchronize()).
+ *   - The caller owns every buffer it passes.  Nothing is retained past a call except
+ *     the copies made by pk_set_data().
+ *   - Return value: 0 = OK; non-zero = argument / CUDA error (fatal; text from
+ *     pk_last_error()).  NUMERICAL failure (Psi not positive definite) is NOT an error
+ *     status: it is reported per candidate in info[] with LAPACK's dpotrf convention
+ *     (0 ok, j>0 = order of the first non-positive pivot), and the Python glue maps it to
+ *     the reference's penalty 10000 (krige.py:447-450) or to its stale-U rule
+ *     (regressionkrige.py:167-172).
+ *   - One handle per (process, GPU).  A handle is not thread-safe.  There is no CPU
+ *     fallback: without a CUDA device pk_create() fails.
+ */
+#ifndef PYKRIGING_B200_H
+#define PYKRIGING_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pk_handle pk_handle;
+
+#define PK_MODE_INTERP 0     /* matrixops.updatePsi:    diag = 1 + np.spacing(1)  (matrixops.py:30) */
+#define PK_MODE_REGRESSION 1 /* matrixops.regupdatePsi: diag = 1 + Lambda         (matrixops.py:40) */
+
+#define PK_VERSION 100
+
+/* ABI version (PK_VERSION of the built library). */
+int pk_version(void);
+
+/* Last error text of a handle (or of the last failed pk_create when h == NULL). */
+const char *pk_last_error(const pk_handle *h);
+
+/* Replaces matrixops.__init__ (matrixops.py:7-16): creates the per-model device state on GPU
+ * `device` (workspaces are grown lazily).  Fails (non-zero) when no CUDA device is usable. */
+int pk_create(pk_handle **out, int device);
+int pk_destroy(pk_handle *h);
+
+/* Replaces matrixops.updateData (matrixops.py:18-22).  Uploads the n x k sample matrix X (model
+ * units, row-major) and the n observations y.  The reference's (n,n,k) `distance` tensor is never
+ * materialised; only O(n k) data is kept.  Also used after addPoint() (krige.py:135-156). */
+int pk_set_data(pk_handle *h, int n, int k, const double *X, const double *y);
+
+/* Replaces the candidate loop of kriging.fittingObjective (krige.py:429-452) and
+ * regression_kriging.fittingObjective (regressionkrige.py:428-452), i.e. per candidate
+ * updatePsi/regupdatePsi (matrixops.py:24-42) + neglikelihood/regneglikelihood (matrixops.py:45-66),
+ * for a whole GA/PSO population in one call.
+ *   theta, p : C x k (row-major);  lambda : C (mode REGRESSION) or NULL
+ *   outputs (each may be NULL): nll, mu, sigma2, lndet : C doubles; info : C int32.
+ * For info[c] != 0 the four doubles of candidate c are NaN. */
+int pk_nll_batch(pk_handle *h, int C, const double *theta, const double *p, const double *lambda, int mode,
+                 double *nll, double *mu, double *sigma2, double *lndet, int32_t *info);
+
+/* Replaces update()/updateModel() + neglikelihood() for ONE hyper-parameter set
+ * (krige.py:158-178, regressionkrige.py:151-172, matrixops.py:24-66) and caches what the predictors
+ * need: the Cholesky factor L (U = L^T), L^-1, a = L^-1 1, d = L^-1 y.
+ *   out4 (may be NULL) receives {NegLnLike, mu, SigmaSqr, LnDetPsi}; *info as in pk_nll_batch.
+ * When *info != 0 the previously cached factor is kept (the reference keeps its old self.U when
+ * np.linalg.cholesky raises, matrixops.py:31). */
+int pk_fit(pk_handle *h, const double *theta, const double *p, double lambda, int mode, double *out4,
+           int32_t *info);
+
+/* Replaces the per-point loops over predict_normalized (matrixops.py:68-77),
+ * predicterr_normalized (matrixops.py:79-95) and expimp / weightedexpimp (krige.py:201-234),
+ * i.e. infill_objective_mse / infill_objective_ei (krige.py:236-258) and the plot/snapshot grids.
+ *   Xq     : m x k query points in MODEL units (row-major)
+ *   theta,p: k values used for the psi vector (the reference uses the CURRENT self.theta/self.pl)
+ *   mu, sigma2 : the values the reference would have on self (they can be stale)
+ *   y_min  : min(self.y) (krige.py:208);  ei_weight < 0 -> expimp, in [0,1] -> weightedexpimp(w)
+ *   var_extra : 0 for predicterr_normalized; Lambda for regression_predicterr_normalized
+ *               (matrixops.py:97-110)
+ *   outputs (each may be NULL): yhat, s (= RMSE, sqrt|SigmaSqr*(1+extra-psi^T Psi^-1 psi)|), ei : m doubles.
+ * Uses the factor cached by the last successful pk_fit. */
+int pk_predict_batch(pk_handle *h, int64_t m, const double *Xq, const double *theta, const double *p, double mu,
+                     double sigma2, double y_min, double ei_weight, double var_extra, double *yhat, double *s,
+                     double *ei);
+
+/* self.Psi / self.U attribute access (matrixops.py:29-32): n x n row-major copies of the correlation
+ * matrix of the last pk_fit attempt and of the upper factor U = L^T of the last successful one. */
+int pk_get_psi(pk_handle *h, double *out);
+int pk_get_U(pk_handle *h, double *out);
+
+/* Stand-alone batched Psi construction (matrixops.py:28-30 for a whole population): writes the full
+ * symmetric n x n matrices of C candidates to `out` (C*n*n doubles).  Diagnostic / benchmark entry
+ * point for the Psi kernel; pk_nll_batch does not need it. */
+int pk_psi_batch(pk_handle *h, int C, const double *theta, const double *p, const double *lambda, int mode,
+                 double *out);
+
+/* Block until all work queued on the handle's stream has finished. */
+int pk_synchronize(pk_handle *h);
+
+/* The handle's CUDA stream (a cudaStream_t) so callers can time with events on the launching stream. */
+void *pk_stream(pk_handle *h);
+
+/* Number of kernel launches issued by the handle since creation (bench.py's gpu_launches). */
+int64_t pk_launch_count(const pk_handle *h);
+
+/* The factorisation declares "not positive definite" (info > 0) when a pivot is <= tol * (its diagonal
+ * entry of Psi).  tol = 0 is LAPACK's literal rule `ajj <= 0`; the default is a few ulps, calibrated so
+ * that numerically singular matrices (cond(Psi) > 1/eps), where the sign of the computed pivot is pure
+ * rounding noise and differs between BLAS builds, fail as often as they do under np.linalg.cholesky
+ * (DESIGN.md "failure parity"). */
+int pk_set_pivot_tolerance(pk_handle *h, double tol);
+
+/* Tuning knob: limit the device workspace (bytes) used for candidate chunks (0 = default). */
+int pk_set_workspace_limit(pk_handle *h, int64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYKRIGING_B200_H */

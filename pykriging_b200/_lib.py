@@ -1,0 +1,229 @@
+"""ctypes binding of libpykriging_b200.so -- the C ABI declared in include/pykriging_b200.h.
+
+There is deliberately no fallback: if the shared library has not been built, or no CUDA device
+is usable, this module raises.  Build with ``python -m pykriging_b200.build`` (or
+``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpykriging_b200.so")
+
+MODE_INTERP = 0
+MODE_REGRESSION = 1
+
+# every symbol include/pykriging_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "pk_version", "pk_last_error", "pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit",
+    "pk_predict_batch", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
+    "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance",
+]
+
+_lib = None
+
+
+class PkError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare the C signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PkError(
+            "libpykriging_b200.so is missing (%s). Build it with `python -m pykriging_b200.build`; "
+            "pykriging_b200 has no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c_dp = ctypes.c_void_p  # double* / int32_t* passed as raw addresses (host or device)
+    hp = ctypes.c_void_p
+    lib.pk_version.restype = ctypes.c_int
+    lib.pk_last_error.restype = ctypes.c_char_p
+    lib.pk_last_error.argtypes = [hp]
+    lib.pk_create.argtypes = [ctypes.POINTER(hp), ctypes.c_int]
+    lib.pk_destroy.argtypes = [hp]
+    lib.pk_set_data.argtypes = [hp, ctypes.c_int, ctypes.c_int, c_dp, c_dp]
+    lib.pk_nll_batch.argtypes = [hp, ctypes.c_int, c_dp, c_dp, c_dp, ctypes.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
+    lib.pk_fit.argtypes = [hp, c_dp, c_dp, ctypes.c_double, ctypes.c_int, c_dp, c_dp]
+    lib.pk_predict_batch.argtypes = [hp, ctypes.c_int64, c_dp, c_dp, c_dp, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_double, ctypes.c_double, ctypes.c_double, c_dp, c_dp, c_dp]
+    lib.pk_get_psi.argtypes = [hp, c_dp]
+    lib.pk_get_U.argtypes = [hp, c_dp]
+    lib.pk_psi_batch.argtypes = [hp, ctypes.c_int, c_dp, c_dp, c_dp, ctypes.c_int, c_dp]
+    lib.pk_synchronize.argtypes = [hp]
+    lib.pk_stream.restype = ctypes.c_void_p
+    lib.pk_stream.argtypes = [hp]
+    lib.pk_launch_count.restype = ctypes.c_int64
+    lib.pk_launch_count.argtypes = [hp]
+    lib.pk_set_workspace_limit.argtypes = [hp, ctypes.c_int64]
+    lib.pk_set_pivot_tolerance.argtypes = [hp, ctypes.c_double]
+    lib.pk_set_pivot_tolerance.restype = ctypes.c_int
+    for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
+                 "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_set_workspace_limit"):
+        getattr(lib, name).restype = ctypes.c_int
+    if hasattr(lib, "pk_opt_create"):
+        _declare_opt(lib)
+    _lib = lib
+    return lib
+
+
+def _declare_opt(lib):
+    hp = ctypes.c_void_p
+    c_dp = ctypes.c_void_p
+    lib.pk_opt_create.restype = ctypes.c_int
+    lib.pk_opt_create.argtypes = [hp, ctypes.POINTER(hp), ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, c_dp,
+                                  ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
+    lib.pk_opt_destroy.restype = ctypes.c_int
+    lib.pk_opt_destroy.argtypes = [hp]
+    lib.pk_opt_init.restype = ctypes.c_int
+    lib.pk_opt_init.argtypes = [hp]
+    lib.pk_opt_step.restype = ctypes.c_int
+    lib.pk_opt_step.argtypes = [hp, c_dp]
+    lib.pk_opt_get.restype = ctypes.c_int
+    lib.pk_opt_get.argtypes = [hp, ctypes.c_int, c_dp]
+    lib.pk_nll_population.restype = ctypes.c_int
+    lib.pk_nll_population.argtypes = [hp, hp, ctypes.c_int, c_dp, c_dp]
+
+
+def _addr(a):
+    """Raw address of a numpy array (host) or of anything with .data_ptr() (torch CUDA tensor)."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return ctypes.c_void_p(a.data_ptr())
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _f64(a):
+    if hasattr(a, "data_ptr"):
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Handle(object):
+    """Owner of one pk_handle (one per process and GPU; not thread-safe)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self._h = ctypes.c_void_p()
+        if self.lib.pk_create(ctypes.byref(self._h), int(device)) != 0:
+            raise PkError("pk_create failed: %s" % self.lib.pk_last_error(None).decode())
+        self.device = int(device)
+        self.n = 0
+        self.k = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.pk_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise PkError("%s failed: %s" % (what, self.lib.pk_last_error(self._h).decode()))
+
+    # -- data -----------------------------------------------------------------------------------
+    def set_data(self, X, y):
+        X = _f64(X)
+        y = _f64(y)
+        n, k = X.shape
+        self._check(self.lib.pk_set_data(self._h, n, k, _addr(X), _addr(y)), "pk_set_data")
+        self.n, self.k = int(n), int(k)
+
+    # -- likelihood -----------------------------------------------------------------------------
+    def nll_batch(self, theta, p, lam=None, mode=MODE_INTERP, want=("nll", "mu", "sigma2", "lndet", "info")):
+        """Host-array convenience wrapper: returns dict of numpy arrays."""
+        theta = _f64(theta)
+        p = _f64(p)
+        C = theta.shape[0]
+        lam_a = _f64(lam) if lam is not None else None
+        out = {}
+        for name in ("nll", "mu", "sigma2", "lndet"):
+            out[name] = np.empty(C, dtype=np.float64) if name in want else None
+        out["info"] = np.empty(C, dtype=np.int32) if "info" in want else None
+        self._check(self.lib.pk_nll_batch(self._h, C, _addr(theta), _addr(p), _addr(lam_a), int(mode),
+                                          _addr(out["nll"]), _addr(out["mu"]), _addr(out["sigma2"]),
+                                          _addr(out["lndet"]), _addr(out["info"])), "pk_nll_batch")
+        return out
+
+    def nll_batch_raw(self, C, theta, p, lam, mode, nll, mu=None, sigma2=None, lndet=None, info=None):
+        """Pointer-level call (host numpy arrays or CUDA tensors); no allocation, no implicit sync for
+        device buffers."""
+        self._check(self.lib.pk_nll_batch(self._h, int(C), _addr(theta), _addr(p), _addr(lam), int(mode), _addr(nll),
+                                          _addr(mu), _addr(sigma2), _addr(lndet), _addr(info)), "pk_nll_batch")
+
+    def fit(self, theta, p, lam=0.0, mode=MODE_INTERP):
+        theta = _f64(theta)
+        p = _f64(p)
+        out4 = np.empty(4, dtype=np.float64)
+        info = np.zeros(1, dtype=np.int32)
+        self._check(self.lib.pk_fit(self._h, _addr(theta), _addr(p), float(lam), int(mode), _addr(out4), _addr(info)),
+                    "pk_fit")
+        return out4, int(info[0])
+
+    # -- predictors -----------------------------------------------------------------------------
+    def predict_batch(self, Xq, theta, p, mu, sigma2, y_min=0.0, ei_weight=-1.0, var_extra=0.0,
+                      want=("yhat", "s", "ei")):
+        Xq = _f64(Xq)
+        m = Xq.shape[0]
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        out = {name: (np.empty(m, dtype=np.float64) if name in want else None) for name in ("yhat", "s", "ei")}
+        self._check(self.lib.pk_predict_batch(self._h, m, _addr(Xq), _addr(theta), _addr(p), float(mu), float(sigma2),
+                                              float(y_min), float(ei_weight), float(var_extra), _addr(out["yhat"]),
+                                              _addr(out["s"]), _addr(out["ei"])), "pk_predict_batch")
+        return out
+
+    def predict_batch_raw(self, m, Xq, theta, p, mu, sigma2, y_min, ei_weight, var_extra, yhat, s, ei):
+        self._check(self.lib.pk_predict_batch(self._h, int(m), _addr(Xq), _addr(theta), _addr(p), float(mu),
+                                              float(sigma2), float(y_min), float(ei_weight), float(var_extra),
+                                              _addr(yhat), _addr(s), _addr(ei)), "pk_predict_batch")
+
+    def get_psi(self):
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        self._check(self.lib.pk_get_psi(self._h, _addr(out)), "pk_get_psi")
+        return out
+
+    def get_U(self):
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        self._check(self.lib.pk_get_U(self._h, _addr(out)), "pk_get_U")
+        return out
+
+    def psi_batch(self, theta, p, lam=None, mode=MODE_INTERP, out=None):
+        theta = _f64(theta)
+        p = _f64(p)
+        C = theta.shape[0]
+        lam_a = _f64(lam) if lam is not None else None
+        if out is None:
+            out = np.empty((C, self.n, self.n), dtype=np.float64)
+        self._check(self.lib.pk_psi_batch(self._h, C, _addr(theta), _addr(p), _addr(lam_a), int(mode), _addr(out)),
+                    "pk_psi_batch")
+        return out
+
+    # -- misc -----------------------------------------------------------------------------------
+    def synchronize(self):
+        self._check(self.lib.pk_synchronize(self._h), "pk_synchronize")
+
+    @property
+    def stream(self):
+        return self.lib.pk_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pk_launch_count(self._h))
+
+    def set_pivot_tolerance(self, tol):
+        self._check(self.lib.pk_set_pivot_tolerance(self._h, float(tol)), "pk_set_pivot_tolerance")
+
+    def set_workspace_limit(self, nbytes):
+        self._check(self.lib.pk_set_workspace_limit(self._h, int(nbytes)), "pk_set_workspace_limit")

@@ -1,0 +1,419 @@
+// C ABI of libpykriging_b200.so (see include/pykriging_b200.h for the contract of every entry point).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "pk_internal.h"
+
+namespace pk {
+cudaError_t launch_extract_psi(pk_handle* h, const TiledShape& s, const double* M, double* out);
+}
+
+static std::string g_create_error;
+
+#define PK_FAIL(h, ...)                                  \
+    do {                                                 \
+        char buf_[512];                                  \
+        snprintf(buf_, sizeof(buf_), __VA_ARGS__);       \
+        (h)->err = buf_;                                 \
+        return 1;                                        \
+    } while (0)
+
+#define PK_CUDA(h, call)                                                                             \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) PK_FAIL(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+static cudaError_t regrow(T** ptr, size_t count) {
+    if (*ptr) {
+        cudaError_t e = cudaFree(*ptr);
+        *ptr = nullptr;
+        if (e != cudaSuccess) return e;
+    }
+    return cudaMalloc((void**)ptr, count * sizeof(T));
+}
+
+static int ensure_candidates(pk_handle* h, int C) {
+    if (C <= h->cap_C && h->k <= h->cap_k) return 0;
+    const int cap = C > h->cap_C ? C : h->cap_C;
+    const int ck = h->k > h->cap_k ? h->k : h->cap_k;
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    PK_CUDA(h, regrow(&h->d_theta, (size_t)cap * ck));
+    PK_CUDA(h, regrow(&h->d_p, (size_t)cap * ck));
+    PK_CUDA(h, regrow(&h->d_lambda, (size_t)cap));
+    PK_CUDA(h, regrow(&h->d_out, (size_t)cap * 4));
+    PK_CUDA(h, regrow(&h->d_info, (size_t)cap));
+    h->cap_C = cap;
+    h->cap_k = ck;
+    return 0;
+}
+
+// Return a device pointer holding `count` doubles of `src` (copying through `stage` when src is a host pointer).
+static int to_device(pk_handle* h, const double* src, double* stage, size_t count, const double** out) {
+    if (!src) {
+        *out = nullptr;
+        return 0;
+    }
+    if (is_device_ptr(src)) {
+        *out = src;
+        return 0;
+    }
+    PK_CUDA(h, cudaMemcpyAsync(stage, src, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    *out = stage;
+    return 0;
+}
+
+extern "C" {
+
+int pk_version(void) { return PK_VERSION; }
+
+const char* pk_last_error(const pk_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int pk_create(pk_handle** out, int device) {
+    if (!out) return 1;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                         " (pykriging_b200 has no CPU fallback)";
+        cudaGetLastError();
+        return 1;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device index out of range";
+        return 1;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    pk_handle* h = new (std::nothrow) pk_handle();
+    if (!h) return 1;
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete h;
+        return 1;
+    }
+    e = cudaMalloc((void**)&h->d_hp, sizeof(double) * 2 * PK_MAX_K);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+int pk_destroy(pk_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
+                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int pk_synchronize(pk_handle* h) {
+    if (!h) return 1;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+void* pk_stream(pk_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int64_t pk_launch_count(const pk_handle* h) { return h ? h->launches : 0; }
+
+int pk_set_pivot_tolerance(pk_handle* h, double tol) {
+    if (!h || !(tol >= 0.0)) return 1;
+    h->pivot_tol = tol;
+    return 0;
+}
+
+int pk_set_workspace_limit(pk_handle* h, int64_t bytes) {
+    if (!h || bytes < 0) return 1;
+    h->ws_limit = (size_t)bytes;
+    return 0;
+}
+
+int pk_set_data(pk_handle* h, int n, int k, const double* X, const double* y) {
+    if (!h) return 1;
+    if (n < 2 || k < 1 || k > PK_MAX_K || !X || !y) PK_FAIL(h, "pk_set_data: need n>=2, 1<=k<=%d, X, y", PK_MAX_K);
+    PK_CUDA(h, cudaSetDevice(h->device));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    PK_CUDA(h, regrow(&h->dX, (size_t)n * k));
+    PK_CUDA(h, regrow(&h->dy, (size_t)n));
+    PK_CUDA(h, cudaMemcpyAsync(h->dX, X, sizeof(double) * n * k, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(h->dy, y, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n = n;
+    h->k = k;
+    h->fit_valid = false;  // a cached factor belongs to the previous data set
+    h->w_valid = false;
+    return 0;
+}
+
+static int ensure_workspace(pk_handle* h, size_t per_matrix_bytes, int C, int* chunk_out) {
+    size_t limit = h->ws_limit;
+    if (limit == 0) {
+        size_t free_b = 0, total_b = 0;
+        PK_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+        limit = (size_t)((double)(free_b + h->ws_bytes) * 0.6);
+        const size_t cap = (size_t)64 << 30;
+        if (limit > cap) limit = cap;
+    }
+    size_t chunk = limit / per_matrix_bytes;
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)C) chunk = (size_t)C;
+    const size_t need = chunk * per_matrix_bytes;
+    if (need > h->ws_bytes) {
+        PK_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->d_ws) {
+            PK_CUDA(h, cudaFree(h->d_ws));
+            h->d_ws = nullptr;
+            h->ws_bytes = 0;
+        }
+        PK_CUDA(h, cudaMalloc((void**)&h->d_ws, need));
+        h->ws_bytes = need;
+    }
+    *chunk_out = (int)chunk;
+    return 0;
+}
+
+int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, const double* lambda, int mode,
+                 double* nll, double* mu, double* sigma2, double* lndet, int32_t* info) {
+    if (!h) return 1;
+    if (h->n == 0) PK_FAIL(h, "pk_nll_batch: pk_set_data has not been called");
+    if (C < 0 || !theta || !p) PK_FAIL(h, "pk_nll_batch: bad arguments");
+    if (mode == PK_MODE_REGRESSION && !lambda) PK_FAIL(h, "pk_nll_batch: regression mode needs lambda");
+    if (mode != PK_MODE_REGRESSION && mode != PK_MODE_INTERP) PK_FAIL(h, "pk_nll_batch: unknown mode %d", mode);
+    if (C == 0) return 0;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    if (ensure_candidates(h, C)) return 1;
+    const int k = h->k;
+    const double *d_theta, *d_p, *d_lambda;
+    if (to_device(h, theta, h->d_theta, (size_t)C * k, &d_theta)) return 1;
+    if (to_device(h, p, h->d_p, (size_t)C * k, &d_p)) return 1;
+    if (to_device(h, mode == PK_MODE_REGRESSION ? lambda : nullptr, h->d_lambda, (size_t)C, &d_lambda)) return 1;
+
+    if (h->n <= PK_SMALL_N_MAX) {
+        PK_CUDA(h, pk::launch_small_nll(h, C, d_theta, d_p, d_lambda, mode, h->d_out, h->d_info));
+    } else {
+        const pk::TiledShape s = pk::tiled_shape(h->n, false);
+        int chunk = 0;
+        if (ensure_workspace(h, s.elems() * sizeof(double), C, &chunk)) return 1;
+        for (int c0 = 0; c0 < C; c0 += chunk) {
+            const int cc = (C - c0 < chunk) ? (C - c0) : chunk;
+            PK_CUDA(h, pk::launch_psi_build(h, s, cc, d_theta + (size_t)c0 * k, d_p + (size_t)c0 * k,
+                                            d_lambda ? d_lambda + c0 : nullptr, mode, h->d_ws, h->d_info + c0));
+            PK_CUDA(h, pk::launch_cholesky(h, s, cc, h->d_ws, h->d_info + c0));
+            PK_CUDA(h, pk::launch_nll_epilogue(h, s, cc, h->d_ws, h->d_out + c0, h->cap_C, h->d_info + c0));
+        }
+    }
+    double* outs[4] = {nll, mu, sigma2, lndet};
+    bool host_out = false;
+    for (int i = 0; i < 4; ++i) {
+        if (!outs[i]) continue;
+        PK_CUDA(h, cudaMemcpyAsync(outs[i], h->d_out + (size_t)i * h->cap_C, sizeof(double) * C, cudaMemcpyDefault,
+                                   h->stream));
+        host_out |= !is_device_ptr(outs[i]);
+    }
+    if (info) {
+        PK_CUDA(h, cudaMemcpyAsync(info, h->d_info, sizeof(int32_t) * C, cudaMemcpyDefault, h->stream));
+        host_out |= !is_device_ptr(info);
+    }
+    if (host_out) PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int ensure_fit_buffers(pk_handle* h, const pk::TiledShape& s) {
+    const size_t bytes = s.elems() * sizeof(double);
+    if (h->fit_bytes >= bytes && h->fit_np == s.np) return 0;
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    PK_CUDA(h, regrow(&h->d_fit, s.elems()));
+    PK_CUDA(h, regrow(&h->d_try, s.elems()));
+    PK_CUDA(h, regrow(&h->d_psi, (size_t)s.np * s.np));
+    PK_CUDA(h, regrow(&h->d_linv, (size_t)s.np * s.np));
+    PK_CUDA(h, regrow(&h->d_ad, (size_t)2 * s.np));
+    PK_CUDA(h, regrow(&h->d_w, (size_t)s.np));
+    h->fit_bytes = bytes;
+    h->fit_np = s.np;
+    h->fit_valid = false;
+    h->w_valid = false;
+    return 0;
+}
+
+int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, int mode, double* out4,
+           int32_t* info) {
+    if (!h) return 1;
+    if (h->n == 0) PK_FAIL(h, "pk_fit: pk_set_data has not been called");
+    if (!theta || !p) PK_FAIL(h, "pk_fit: bad arguments");
+    if (mode != PK_MODE_REGRESSION && mode != PK_MODE_INTERP) PK_FAIL(h, "pk_fit: unknown mode %d", mode);
+    PK_CUDA(h, cudaSetDevice(h->device));
+    if (ensure_candidates(h, 1)) return 1;
+    const pk::TiledShape s = pk::tiled_shape(h->n, true);
+    if (ensure_fit_buffers(h, s)) return 1;
+    const int k = h->k;
+    const double *d_theta, *d_p;
+    if (to_device(h, theta, h->d_theta, (size_t)k, &d_theta)) return 1;
+    if (to_device(h, p, h->d_p, (size_t)k, &d_p)) return 1;
+    PK_CUDA(h, cudaMemcpyAsync(h->d_lambda, &lambda, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PK_CUDA(h, pk::launch_psi_build(h, s, 1, d_theta, d_p, h->d_lambda, mode, h->d_try, h->d_info));
+    PK_CUDA(h, pk::launch_extract_psi(h, s, h->d_try, h->d_psi));
+    PK_CUDA(h, pk::launch_cholesky(h, s, 1, h->d_try, h->d_info));
+    PK_CUDA(h, pk::launch_nll_epilogue(h, s, 1, h->d_try, h->d_out, h->cap_C, h->d_info));
+    double host4[4];
+    int32_t host_info = 0;
+    for (int i = 0; i < 4; ++i)
+        PK_CUDA(h, cudaMemcpyAsync(&host4[i], h->d_out + (size_t)i * h->cap_C, sizeof(double), cudaMemcpyDeviceToHost,
+                                   h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(&host_info, h->d_info, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (host_info == 0) {
+        double* t = h->d_fit;
+        h->d_fit = h->d_try;
+        h->d_try = t;
+        PK_CUDA(h, pk::launch_fit_finalize(h, s));
+        h->fit_valid = true;
+        h->fit_n = h->n;
+        h->w_valid = false;
+    }
+    if (out4) PK_CUDA(h, cudaMemcpy(out4, host4, sizeof(host4), cudaMemcpyDefault));
+    if (info) PK_CUDA(h, cudaMemcpy(info, &host_info, sizeof(int32_t), cudaMemcpyDefault));
+    return 0;
+}
+
+int pk_predict_batch(pk_handle* h, int64_t m, const double* Xq, const double* theta, const double* p, double mu,
+                     double sigma2, double y_min, double ei_weight, double var_extra, double* yhat, double* s,
+                     double* ei) {
+    if (!h) return 1;
+    if (!h->fit_valid || h->fit_n != h->n) PK_FAIL(h, "pk_predict_batch: no cached factor (call pk_fit first)");
+    if (m < 0 || !Xq || !theta || !p) PK_FAIL(h, "pk_predict_batch: bad arguments");
+    if (m == 0) return 0;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    const int k = h->k;
+    const pk::TiledShape sh = pk::tiled_shape(h->n, true);
+    if (sh.np > 2944) PK_FAIL(h, "pk_predict_batch: n=%d exceeds the fused predictor's limit (2944)", h->n);
+    PK_CUDA(h, cudaMemcpyAsync(h->d_hp, theta, sizeof(double) * k, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(h->d_hp + PK_MAX_K, p, sizeof(double) * k, cudaMemcpyDefault, h->stream));
+    if (!h->w_valid || !(h->w_mu == mu)) {
+        PK_CUDA(h, pk::launch_compute_w(h, sh, mu));
+        h->w_mu = mu;
+        h->w_valid = true;
+    }
+    const bool q_dev = is_device_ptr(Xq);
+    const bool out_dev = (!yhat || is_device_ptr(yhat)) && (!s || is_device_ptr(s)) && (!ei || is_device_ptr(ei));
+    if (q_dev && out_dev) {
+        PK_CUDA(h, pk::launch_predict(h, m, Xq, h->d_hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, s, ei));
+        return 0;
+    }
+    // host path: stream the queries through a device staging buffer in chunks
+    const int64_t chunk = m < ((int64_t)1 << 22) ? m : ((int64_t)1 << 22);
+    if (chunk * k > h->cap_q) {
+        PK_CUDA(h, cudaStreamSynchronize(h->stream));
+        PK_CUDA(h, regrow(&h->d_q, (size_t)chunk * k));
+        PK_CUDA(h, regrow(&h->d_qout, (size_t)chunk * 3));
+        h->cap_q = chunk * k;
+    }
+    for (int64_t q0 = 0; q0 < m; q0 += chunk) {
+        const int64_t mc = (m - q0 < chunk) ? (m - q0) : chunk;
+        const double* xq_d = Xq + q0 * k;
+        if (!q_dev) {
+            PK_CUDA(h, cudaMemcpyAsync(h->d_q, Xq + q0 * k, sizeof(double) * mc * k, cudaMemcpyDefault, h->stream));
+            xq_d = h->d_q;
+        }
+        double* o0 = yhat ? h->d_qout : nullptr;
+        double* o1 = s ? h->d_qout + chunk : nullptr;
+        double* o2 = ei ? h->d_qout + 2 * chunk : nullptr;
+        PK_CUDA(h, pk::launch_predict(h, mc, xq_d, h->d_hp, mu, sigma2, y_min, ei_weight, var_extra, o0, o1, o2));
+        if (yhat) PK_CUDA(h, cudaMemcpyAsync(yhat + q0, o0, sizeof(double) * mc, cudaMemcpyDefault, h->stream));
+        if (s) PK_CUDA(h, cudaMemcpyAsync(s + q0, o1, sizeof(double) * mc, cudaMemcpyDefault, h->stream));
+        if (ei) PK_CUDA(h, cudaMemcpyAsync(ei + q0, o2, sizeof(double) * mc, cudaMemcpyDefault, h->stream));
+    }
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pk_get_psi(pk_handle* h, double* out) {
+    if (!h || !out) return 1;
+    if (!h->d_psi || h->fit_np == 0) PK_FAIL(h, "pk_get_psi: pk_fit has not been called");
+    PK_CUDA(h, cudaSetDevice(h->device));
+    PK_CUDA(h, cudaMemcpyAsync(out, h->d_psi, sizeof(double) * h->n * h->n, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pk_get_U(pk_handle* h, double* out) {
+    if (!h || !out) return 1;
+    if (!h->fit_valid || h->fit_n != h->n) PK_FAIL(h, "pk_get_U: no successful pk_fit yet");
+    PK_CUDA(h, cudaSetDevice(h->device));
+    const pk::TiledShape s = pk::tiled_shape(h->n, true);
+    if (is_device_ptr(out)) {
+        PK_CUDA(h, pk::launch_extract_U(h, s, out));
+        return 0;
+    }
+    // d_try is scratch between fits: borrow its head for the n x n result
+    PK_CUDA(h, pk::launch_extract_U(h, s, h->d_try));
+    PK_CUDA(h, cudaMemcpyAsync(out, h->d_try, sizeof(double) * h->n * h->n, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pk_psi_batch(pk_handle* h, int C, const double* theta, const double* p, const double* lambda, int mode,
+                 double* out) {
+    if (!h) return 1;
+    if (h->n == 0) PK_FAIL(h, "pk_psi_batch: pk_set_data has not been called");
+    if (C < 0 || !theta || !p || !out) PK_FAIL(h, "pk_psi_batch: bad arguments");
+    if (mode == PK_MODE_REGRESSION && !lambda) PK_FAIL(h, "pk_psi_batch: regression mode needs lambda");
+    if (C == 0) return 0;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    if (ensure_candidates(h, C)) return 1;
+    const int k = h->k;
+    const double *d_theta, *d_p, *d_lambda;
+    if (to_device(h, theta, h->d_theta, (size_t)C * k, &d_theta)) return 1;
+    if (to_device(h, p, h->d_p, (size_t)C * k, &d_p)) return 1;
+    if (to_device(h, mode == PK_MODE_REGRESSION ? lambda : nullptr, h->d_lambda, (size_t)C, &d_lambda)) return 1;
+    const size_t per = (size_t)h->n * h->n;
+    if (is_device_ptr(out)) {
+        PK_CUDA(h, pk::launch_psi_full(h, C, d_theta, d_p, d_lambda, mode, out));
+        return 0;
+    }
+    int chunk = 0;
+    if (ensure_workspace(h, per * sizeof(double), C, &chunk)) return 1;
+    for (int c0 = 0; c0 < C; c0 += chunk) {
+        const int cc = (C - c0 < chunk) ? (C - c0) : chunk;
+        PK_CUDA(h, pk::launch_psi_full(h, cc, d_theta + (size_t)c0 * k, d_p + (size_t)c0 * k,
+                                       d_lambda ? d_lambda + c0 : nullptr, mode, h->d_ws));
+        PK_CUDA(h, cudaMemcpyAsync(out + (size_t)c0 * per, h->d_ws, sizeof(double) * per * cc, cudaMemcpyDefault,
+                                   h->stream));
+    }
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"

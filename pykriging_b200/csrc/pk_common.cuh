@@ -1,0 +1,98 @@
+// Shared device helpers for the pykriging_b200 kernels (sm_100a, FP64 throughout).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#define PK_MAX_K 64          // largest supported number of design variables
+#define PK_TILE 64           // tile edge of the blocked Cholesky (panel width nb)
+#define PK_AUG_ROWS 8        // augmented rows appended under Psi (row 0 = 1^T, row 1 = y^T, rest 0)
+#define PK_SMALL_N_MAX 128   // n <= this: one CTA per candidate, Psi never leaves shared memory
+
+// diag extra of the interpolating model: np.spacing(1) (matrixops.py:30)
+#define PK_EPS_DIAG 2.220446049250313e-16
+
+namespace pk {
+
+// ------------------------------------------------------------------------------------------------
+// Summation in NumPy's order.  The reference reduces theta*|d|^p over the contiguous last axis with
+// np.sum (matrixops.py:28,70): plain left-to-right for k < 8, otherwise NumPy's 8-accumulator
+// pairwise scheme (pairwise_sum, block <= 128).  Reproducing the order keeps the exponent of
+// exp(-S) identical to the reference whenever the individual terms are.
+// `term(d)` returns the d-th addend.
+// ------------------------------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ double sum_numpy_order(int k, F term) {
+    if (k < 8) {
+        double res = 0.0;
+        for (int d = 0; d < k; ++d) res += term(d);
+        return res;
+    }
+    double r0 = term(0), r1 = term(1), r2 = term(2), r3 = term(3);
+    double r4 = term(4), r5 = term(5), r6 = term(6), r7 = term(7);
+    int i = 8;
+    const int lim = k - (k % 8);
+    for (; i < lim; i += 8) {
+        r0 += term(i + 0); r1 += term(i + 1); r2 += term(i + 2); r3 += term(i + 3);
+        r4 += term(i + 4); r5 += term(i + 5); r6 += term(i + 6); r7 += term(i + 7);
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < k; ++i) res += term(i);
+    return res;
+}
+
+// |d|^p exactly as np.power would treat the special values the path can produce:
+// pow(0, p>0) = 0, pow(d, 1) = d, pow(d, 2) = d*d (correctly rounded).
+__device__ __forceinline__ double pow_abs(double d, double p) {
+    if (p == 2.0) return d * d;
+    if (p == 1.0) return d;
+    return pow(d, p);
+}
+
+// S(x, z) = sum_d theta_d |x_d - z_d|^p_d  (matrixops.py:28 / :70), NumPy summation order.
+__device__ __forceinline__ double corr_exponent(const double* __restrict__ x, const double* __restrict__ z,
+                                                const double* __restrict__ theta, const double* __restrict__ p,
+                                                int k) {
+    return sum_numpy_order(k, [&](int d) { return theta[d] * pow_abs(fabs(x[d] - z[d]), p[d]); });
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum (blockDim.x multiple of 32, <= 1024); `scratch` holds >= 32 doubles.
+// Every thread receives the result.  Deterministic (fixed tree).
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double t = (lane < nw) ? scratch[lane] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+
+}  // namespace pk

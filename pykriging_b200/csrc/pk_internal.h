@@ -1,0 +1,99 @@
+// Host-side internals shared by the translation units of libpykriging_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pykriging_b200.h"
+#include "pk_common.cuh"
+
+struct pk_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double pivot_tol = 2.0 * PK_EPS_DIAG;  // relative pivot threshold, 2 ulps (see pk_set_pivot_tolerance)
+
+    // model data (pk_set_data)
+    int n = 0, k = 0;
+    double* dX = nullptr;  // n x k, model units
+    double* dy = nullptr;  // n
+
+    // hyper-parameter / result staging for host callers
+    int cap_C = 0;
+    double* d_theta = nullptr;   // cap_C x k
+    double* d_p = nullptr;       // cap_C x k
+    double* d_lambda = nullptr;  // cap_C
+    double* d_out = nullptr;     // 4 x cap_C  (nll | mu | sigma2 | lndet)
+    int32_t* d_info = nullptr;   // cap_C
+    int cap_k = 0;
+
+    // workspace of the tiled path: chunk_C matrices of (rows x ld) doubles
+    double* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    size_t ws_limit = 0;
+
+    // cached fit (pk_fit) for the predictors
+    int fit_n = 0;            // n the cache was built for (0 = none)
+    int fit_np = 0;           // padded order (multiple of PK_TILE)
+    double* d_fit = nullptr;  // factorised augmented matrix of the last successful fit
+    double* d_try = nullptr;  // scratch for the attempt (swapped in on success)
+    double* d_psi = nullptr;  // n x n Psi of the last attempt (row-major, full symmetric)
+    double* d_linv = nullptr; // fit_np x fit_np row-major L^-1 (lower)
+    double* d_ad = nullptr;   // 2 x fit_np : a = L^-1 1, d = L^-1 y
+    double* d_w = nullptr;    // fit_np : w = L^-T (d - mu a)
+    double w_mu = 0.0;
+    bool w_valid = false;
+    bool fit_valid = false;
+    size_t fit_bytes = 0;
+
+    // staging for predict
+    double* d_q = nullptr;    // query chunk
+    double* d_qout = nullptr; // 3 x chunk
+    int64_t cap_q = 0;
+    double* d_hp = nullptr;   // 2 x PK_MAX_K (theta | p) for predict
+};
+
+namespace pk {
+
+// Layout of one augmented matrix of the tiled path (row-major, leading dimension ld = np):
+//   rows [0, n)            Psi (lower triangle used; the factor L overwrites it)
+//   rows [n, np)           identity padding up to a multiple of PK_TILE
+//   rows [np, np+8)        augmented rows: 1^T, y^T, 0...   -> become a^T = (L^-1 1)^T, d^T = (L^-1 y)^T
+//   rows [np+8, np+8+np)   (fit only) identity               -> becomes L^-T, i.e. (L^-1) transposed
+struct TiledShape {
+    int n, np, ld, rows;  // rows = total row count (multiple of 8)
+    bool with_inverse;
+    size_t elems() const { return (size_t)rows * (size_t)ld; }
+};
+inline TiledShape tiled_shape(int n, bool with_inverse) {
+    TiledShape s;
+    s.n = n;
+    s.np = ((n + PK_TILE - 1) / PK_TILE) * PK_TILE;
+    s.ld = s.np;
+    s.with_inverse = with_inverse;
+    s.rows = s.np + PK_AUG_ROWS + (with_inverse ? s.np : 0);
+    return s;
+}
+
+// ---- launchers (each returns cudaError_t of the launch) -------------------------------------------
+cudaError_t launch_small_nll(pk_handle* h, int C, const double* theta, const double* p, const double* lambda,
+                             int mode, double* out4, int32_t* info);
+
+cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
+                             const double* lambda, int mode, double* ws, int32_t* info);
+cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
+cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,
+                                int out_stride, int32_t* info);
+cudaError_t launch_psi_full(pk_handle* h, int C, const double* theta, const double* p, const double* lambda,
+                            int mode, double* out);
+cudaError_t launch_fit_finalize(pk_handle* h, const TiledShape& s);
+cudaError_t launch_compute_w(pk_handle* h, const TiledShape& s, double mu);
+cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
+                           double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
+                           double* ei);
+cudaError_t launch_extract_U(pk_handle* h, const TiledShape& s, double* out);
+
+}  // namespace pk

@@ -1,0 +1,301 @@
+// Prediction path: fused psi-vector / predictor / RMSE / expected-improvement kernel over large
+// query sets, plus the small helpers that turn a factorised augmented matrix into the cached
+// predictor state.
+//
+// Replaces the per-point Python loops over matrixops.predict_normalized (matrixops.py:68-77),
+// matrixops.predicterr_normalized (matrixops.py:79-95) and kriging.expimp / weightedexpimp
+// (krige.py:201-234): for every query point x
+//     psi_r = exp(-sum_d theta_d |X_rd - x_d|^p_d)            (never written to HBM)
+//     yhat  = mu + psi . w,           w = Psi^-1 (y - mu 1)   (query independent, cached)
+//     v     = L^-1 psi  (FP64 tensor-pipe GEMM against the cached L^-1),  q = |v|^2 = psi^T Psi^-1 psi
+//     s     = sqrt(|SigmaSqr (1 + extra - q)|),  EI(yhat, s, y_min)
+// HBM traffic per query: 8k bytes in, 8..24 bytes out; L^-1 (n^2/2 doubles) streams from L2.
+#include "pk_internal.h"
+
+namespace pk {
+
+// ---- fit helpers ---------------------------------------------------------------------------------
+// M = factorised augmented matrix with inverse rows (TiledShape with_inverse).
+__global__ void fit_finalize_kernel(int np, int ld, const double* __restrict__ M, double* __restrict__ linv,
+                                    double* __restrict__ ad) {
+    // linv[c][r] = M[(np + 8 + r) * ld + c]  (transpose of the inverse rows), tiled through smem
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;  // bx: c block, by: r block
+    const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
+    for (int i = ty; i < 32; i += 8) tile[i][tx] = M[(size_t)(np + PK_AUG_ROWS + by + i) * ld + bx + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = bx + i, r = by + tx;
+        linv[(size_t)c * np + r] = (r <= c) ? tile[tx][i] : 0.0;
+    }
+    if (blockIdx.y == 0 && ty == 0) {
+        ad[bx + tx] = M[(size_t)np * ld + bx + tx];
+        ad[np + bx + tx] = M[(size_t)(np + 1) * ld + bx + tx];
+    }
+}
+
+// w_r = sum_c R[r][c] (d_c - mu a_c), R = inverse rows of M (R = L^-T); one warp per row.
+__global__ void compute_w_kernel(int np, int ld, const double* __restrict__ M, const double* __restrict__ ad,
+                                 double mu, double* __restrict__ w) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= np) return;
+    const double* row = M + (size_t)(np + PK_AUG_ROWS + r) * ld;
+    double acc = 0.0;
+    for (int c = r - (r & 31) + lane; c < np; c += 32)  // R[r][c] == 0 for c < r
+        if (c >= r) acc += row[c] * (ad[np + c] - mu * ad[c]);
+    acc = warp_sum(acc);
+    if (lane == 0) w[r] = acc;
+}
+
+__global__ void extract_U_kernel(int n, int ld, const double* __restrict__ M, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < n) out[(size_t)r * n + c] = (c >= r) ? M[(size_t)c * ld + r] : 0.0;  // U = L^T
+}
+
+__global__ void extract_psi_kernel(int n, int ld, const double* __restrict__ M, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < n) out[(size_t)r * n + c] = (c <= r) ? M[(size_t)r * ld + c] : M[(size_t)c * ld + r];
+}
+
+// Full symmetric Psi for a population (diagnostic / K1 benchmark entry point pk_psi_batch).
+__global__ void __launch_bounds__(256)
+psi_full_kernel(int n, int k, const double* __restrict__ X, const double* __restrict__ theta,
+                const double* __restrict__ p, const double* __restrict__ lambda, int mode,
+                double* __restrict__ out) {
+    __shared__ double th[PK_MAX_K], pp[PK_MAX_K];
+    const int cand = blockIdx.z;
+    if (threadIdx.x < k) {
+        th[threadIdx.x] = theta[(size_t)cand * k + threadIdx.x];
+        pp[threadIdx.x] = p[(size_t)cand * k + threadIdx.x];
+    }
+    __syncthreads();
+    const double diag = 1.0 + (mode == PK_MODE_REGRESSION ? lambda[cand] : PK_EPS_DIAG);
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n) return;
+    double v;
+    if (c == r) v = diag;
+    else {
+        const int lo = min(r, c), hi = max(r, c);  // the reference evaluates |X[i]-X[j]| for i<j and mirrors
+        v = exp(-corr_exponent(X + (size_t)lo * k, X + (size_t)hi * k, th, pp, k));
+    }
+    out[((size_t)cand * n + r) * n + c] = v;
+}
+
+// ---- fused predictor -------------------------------------------------------------------------------
+constexpr int PKC = 16;           // K chunk of the L^-1 pipeline
+constexpr int PSLD = PKC + 4;     // 20
+constexpr int PSTAGES = 3;
+constexpr int PRED_THREADS = 256;
+
+// EI exactly as krige.py:207-217 / 227-233 (operation order kept).
+__device__ __forceinline__ double expected_improvement(double yhat, double S, double y_min, double w) {
+    if (S <= 0.0) return 0.0;
+    const double u = y_min - yhat;
+    const double one = u * (0.5 + 0.5 * erf((1.0 / sqrt(2.0)) * (u / S)));
+    const double two = (S * (1.0 / sqrt(2.0 * CUDART_PI))) * exp(-(1.0 / 2.0) * ((u * u) / (S * S)));
+    if (w < 0.0) return one + two;
+    return w * one + (1.0 - w) * two;
+}
+
+template <int QT>
+__global__ void __launch_bounds__(PRED_THREADS)
+predict_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X, const double* __restrict__ Xq,
+               const double* __restrict__ hp, const double* __restrict__ linv, const double* __restrict__ w,
+               double mu, double sigma2, double y_min, double ei_weight, double var_extra, int need_s,
+               double* __restrict__ yhat_out, double* __restrict__ s_out, double* __restrict__ ei_out) {
+    extern __shared__ __align__(16) double smem[];
+    const int psl = np + 4;                              // psi tile row stride (== 4 mod 16)
+    double* psi = smem;                                  // QT x psl
+    double* Bs = psi + QT * psl;                         // PSTAGES x 64 x PSLD
+    double* xq = Bs + PSTAGES * PK_TILE * PSLD;          // QT x k
+    double* th = xq + QT * k;                            // k
+    double* pp = th + k;                                 // k
+    double* ysum = pp + k;                               // QT
+    double* qsum = ysum + QT;                            // QT x 8 (per n-warp-group partials)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * QT;
+    const int qv = (int)min((int64_t)QT, m - q0);
+
+    for (int i = tid; i < QT * k; i += PRED_THREADS) {
+        const int q = i / k;
+        xq[i] = (q < qv) ? Xq[q0 * k + i] : 0.0;
+    }
+    if (tid < k) {
+        th[tid] = hp[tid];
+        pp[tid] = hp[PK_MAX_K + tid];
+    }
+    __syncthreads();
+
+    // ---- psi tile + yhat partials: warp `warp` handles queries warp, warp+8, ... ------------------
+    for (int q = warp; q < QT; q += PRED_THREADS / 32) {
+        double ys = 0.0;
+        for (int r = lane; r < np; r += 32) {
+            double v = 0.0;
+            if (r < n && q < qv) {
+                v = exp(-corr_exponent(X + (size_t)r * k, xq + q * k, th, pp, k));
+                ys += v * w[r];
+            }
+            psi[q * psl + r] = v;
+        }
+        ys = warp_sum(ys);
+        if (lane == 0) ysum[q] = ys;
+    }
+    __syncthreads();
+
+    double qpart[2] = {0.0, 0.0};
+    if (need_s) {
+        // ---- v = psi * Linv^T, column tile by column tile; accumulate |v|^2 per query ---------------
+        constexpr int MT = QT / 8;                       // m-subtiles (8 queries each)
+        constexpr int WM = (MT >= 2) ? 2 : 1;            // m-subtiles per warp
+        constexpr int MW = MT / WM;                      // warps along m
+        constexpr int NW = (PRED_THREADS / 32) / MW;     // warps along n
+        constexpr int WN = 8 / NW;                       // n-subtiles (8 cols) per warp
+        static_assert(MW * NW == PRED_THREADS / 32 && WN >= 1, "bad predict tiling");
+        const int wm = warp % MW, wn = warp / MW;
+        const int fr = lane >> 2, fc = lane & 3;
+        const int nct = np / PK_TILE;
+        for (int ct = 0; ct < nct; ++ct) {
+            double acc[WM][WN][2];
+#pragma unroll
+            for (int a = 0; a < WM; ++a)
+#pragma unroll
+                for (int b = 0; b < WN; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+            const double* Bg = linv + (size_t)(ct * PK_TILE) * np;
+            const int nk = (ct + 1) * PK_TILE / PKC;     // Linv[c][r] == 0 for r > c
+            auto load_stage = [&](int s, int k0) {
+                for (int i = tid; i < PK_TILE * 8; i += PRED_THREADS) {
+                    const int r = i >> 3, ch = i & 7;
+                    cp_async16(Bs + s * PK_TILE * PSLD + r * PSLD + ch * 2, Bg + (size_t)r * np + k0 + ch * 2);
+                }
+            };
+#pragma unroll
+            for (int s = 0; s < PSTAGES - 1; ++s) {
+                if (s < nk) load_stage(s, s * PKC);
+                cp_async_commit();
+            }
+            for (int it = 0; it < nk; ++it) {
+                cp_async_wait<PSTAGES - 2>();
+                __syncthreads();
+                const int nxt = it + PSTAGES - 1;
+                if (nxt < nk) load_stage(nxt % PSTAGES, nxt * PKC);
+                cp_async_commit();
+                const double* a_s = psi + (wm * WM * 8 + fr) * psl + it * PKC + fc;
+                const double* b_s = Bs + (it % PSTAGES) * PK_TILE * PSLD + (wn * WN * 8 + fr) * PSLD + fc;
+#pragma unroll
+                for (int kk = 0; kk < PKC; kk += 4) {
+                    double a[WM], b[WN];
+#pragma unroll
+                    for (int x = 0; x < WM; ++x) a[x] = a_s[x * 8 * psl + kk];
+#pragma unroll
+                    for (int x = 0; x < WN; ++x) b[x] = b_s[x * 8 * PSLD + kk];
+#pragma unroll
+                    for (int x = 0; x < WM; ++x)
+#pragma unroll
+                        for (int z = 0; z < WN; ++z) dmma884(acc[x][z][0], acc[x][z][1], a[x], b[z]);
+                }
+            }
+            cp_async_wait<0>();
+            __syncthreads();
+#pragma unroll
+            for (int x = 0; x < WM; ++x)
+#pragma unroll
+                for (int z = 0; z < WN; ++z) qpart[x] += acc[x][z][0] * acc[x][z][0] + acc[x][z][1] * acc[x][z][1];
+        }
+        // reduce over the 4 lanes sharing a row, then over the n-warps through smem
+#pragma unroll
+        for (int x = 0; x < WM; ++x) {
+            double v = qpart[x];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (fc == 0) qsum[(wm * WM * 8 + x * 8 + fr) * 8 + wn] = v;
+        }
+        static_assert(NW <= 8, "qsum holds 8 partials per query");
+        __syncthreads();
+        if (tid < QT) {
+            double v = 0.0;
+            for (int z = 0; z < NW; ++z) v += qsum[tid * 8 + z];
+            qsum[tid * 8] = v;
+        }
+        __syncthreads();
+    }
+
+    if (tid < qv) {
+        const double yhat = mu + ysum[tid];
+        if (yhat_out) yhat_out[q0 + tid] = yhat;
+        if (need_s) {
+            const double ssqr = sigma2 * (1.0 + var_extra - qsum[tid * 8]);
+            const double S = sqrt(fabs(ssqr));
+            if (s_out) s_out[q0 + tid] = S;
+            if (ei_out) ei_out[q0 + tid] = expected_improvement(yhat, S, y_min, ei_weight);
+        }
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+cudaError_t launch_fit_finalize(pk_handle* h, const TiledShape& s) {
+    dim3 grid(s.np / 32, s.np / 32), block(32, 8);
+    fit_finalize_kernel<<<grid, block, 0, h->stream>>>(s.np, s.ld, h->d_fit, h->d_linv, h->d_ad);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compute_w(pk_handle* h, const TiledShape& s, double mu) {
+    compute_w_kernel<<<(s.np + 7) / 8, 256, 0, h->stream>>>(s.np, s.ld, h->d_fit, h->d_ad, mu, h->d_w);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extract_U(pk_handle* h, const TiledShape& s, double* out) {
+    dim3 grid((s.n + 255) / 256, s.n);
+    extract_U_kernel<<<grid, 256, 0, h->stream>>>(s.n, s.ld, h->d_fit, out);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extract_psi(pk_handle* h, const TiledShape& s, const double* M, double* out) {
+    dim3 grid((s.n + 255) / 256, s.n);
+    extract_psi_kernel<<<grid, 256, 0, h->stream>>>(s.n, s.ld, M, out);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_psi_full(pk_handle* h, int C, const double* theta, const double* p, const double* lambda,
+                            int mode, double* out) {
+    dim3 grid((h->n + 255) / 256, h->n, C);
+    psi_full_kernel<<<grid, 256, 0, h->stream>>>(h->n, h->k, h->dX, theta, p, lambda, mode, out);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+template <int QT>
+static cudaError_t launch_predict_t(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu,
+                                    double sigma2, double y_min, double ei_weight, double var_extra,
+                                    double* yhat, double* sout, double* ei) {
+    const int np = h->fit_np, k = h->k;
+    const size_t smem = sizeof(double) * ((size_t)QT * (np + 4) + PSTAGES * PK_TILE * PSLD + (size_t)QT * k + 2 * k +
+                                          QT + QT * 8);
+    auto kern = predict_kernel<QT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int need_s = (sout != nullptr || ei != nullptr) ? 1 : 0;
+    const int64_t blocks = (m + QT - 1) / QT;
+    kern<<<(unsigned)blocks, PRED_THREADS, smem, h->stream>>>(h->n, np, k, m, h->dX, Xq, hp, h->d_linv, h->d_w, mu,
+                                                              sigma2, y_min, ei_weight, var_extra, need_s, yhat,
+                                                              sout, ei);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
+                           double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
+                           double* ei) {
+    const int np = h->fit_np;
+    if (np <= 512) return launch_predict_t<32>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+    if (np <= 1280) return launch_predict_t<16>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+    if (np <= 3072) return launch_predict_t<8>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace pk
