@@ -119,6 +119,19 @@ int64_t pk_launch_count(const pk_handle *h);
  * (DESIGN.md "failure parity"). */
 int pk_set_pivot_tolerance(pk_handle *h, double tol);
 
+/* Phase timing for roofline accounting (bench.py): when enabled, CUDA events are recorded on the
+ * handle's stream around the phases of every pk_nll_batch / pk_predict_batch call.
+ * pk_phase_times() synchronises, ADDS the elapsed milliseconds since the last call into
+ * ms[0..3] = {Psi construction, Cholesky (diag + panel kernels), likelihood epilogue, predictor} and
+ * resets the accumulation. */
+int pk_set_profiling(pk_handle *h, int enabled);
+int pk_phase_times(pk_handle *h, double *ms4);
+
+/* Measures this GPU's FP64 roofline denominators in place (MEASURED_PEAKS.json carries none):
+ * dense DMMA (mma.sync.m8n8k4.f64) and DFMA throughput in TFLOP/s, each the best of a few ~10 ms
+ * launches that fill every SM. */
+int pk_fp64_peak(pk_handle *h, double *dmma_tflops, double *dfma_tflops);
+
 /* Tuning knob: limit the device workspace (bytes) used for candidate chunks (0 = default). */
 int pk_set_workspace_limit(pk_handle *h, int64_t bytes);
 

@@ -19,7 +19,8 @@ MODE_REGRESSION = 1
 EXPORTS = [
     "pk_version", "pk_last_error", "pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit",
     "pk_predict_batch", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
-    "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance",
+    "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
+    "pk_fp64_peak",
 ]
 
 _lib = None
@@ -62,6 +63,12 @@ def load():
     lib.pk_set_workspace_limit.argtypes = [hp, ctypes.c_int64]
     lib.pk_set_pivot_tolerance.argtypes = [hp, ctypes.c_double]
     lib.pk_set_pivot_tolerance.restype = ctypes.c_int
+    lib.pk_set_profiling.argtypes = [hp, ctypes.c_int]
+    lib.pk_set_profiling.restype = ctypes.c_int
+    lib.pk_phase_times.argtypes = [hp, c_dp]
+    lib.pk_phase_times.restype = ctypes.c_int
+    lib.pk_fp64_peak.argtypes = [hp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.pk_fp64_peak.restype = ctypes.c_int
     for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
                  "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_set_workspace_limit"):
         getattr(lib, name).restype = ctypes.c_int
@@ -221,6 +228,20 @@ class Handle(object):
     @property
     def launch_count(self):
         return int(self.lib.pk_launch_count(self._h))
+
+    def set_profiling(self, enabled):
+        self._check(self.lib.pk_set_profiling(self._h, int(bool(enabled))), "pk_set_profiling")
+
+    def phase_times(self):
+        """ms spent since the last call in {psi, cholesky, epilogue, predict} (needs set_profiling(True))."""
+        ms = np.zeros(4, dtype=np.float64)
+        self._check(self.lib.pk_phase_times(self._h, _addr(ms)), "pk_phase_times")
+        return dict(zip(("psi", "cholesky", "epilogue", "predict"), ms.tolist()))
+
+    def fp64_peak(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._check(self.lib.pk_fp64_peak(self._h, ctypes.byref(a), ctypes.byref(b)), "pk_fp64_peak")
+        return {"dmma_tflops": a.value, "dfma_tflops": b.value}
 
     def set_pivot_tolerance(self, tol):
         self._check(self.lib.pk_set_pivot_tolerance(self._h, float(tol)), "pk_set_pivot_tolerance")

@@ -26,6 +26,27 @@ static std::string g_create_error;
         if (e_ != cudaSuccess) PK_FAIL(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+namespace pk {
+void phase_begin(pk_handle* h, int phase) {
+    if (!h->profiling) return;
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        h->ev_pool.push_back(a);
+        h->ev_pool.push_back(b);
+        h->ev_phase.push_back(phase);
+    }
+    h->ev_phase[h->ev_used / 2] = phase;
+    cudaEventRecord(h->ev_pool[h->ev_used], h->stream);
+}
+void phase_end(pk_handle* h) {
+    if (!h->profiling) return;
+    cudaEventRecord(h->ev_pool[h->ev_used + 1], h->stream);
+    h->ev_used += 2;
+}
+}  // namespace pk
+
 static bool is_device_ptr(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a;
@@ -133,6 +154,7 @@ int pk_destroy(pk_handle* h) {
                     h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -152,6 +174,33 @@ int64_t pk_launch_count(const pk_handle* h) { return h ? h->launches : 0; }
 int pk_set_pivot_tolerance(pk_handle* h, double tol) {
     if (!h || !(tol >= 0.0)) return 1;
     h->pivot_tol = tol;
+    return 0;
+}
+
+int pk_set_profiling(pk_handle* h, int enabled) {
+    if (!h) return 1;
+    h->profiling = enabled != 0;
+    return 0;
+}
+
+int pk_phase_times(pk_handle* h, double* ms4) {
+    if (!h || !ms4) return 1;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i + 1 < h->ev_used + 1 && i < h->ev_used; i += 2) {
+        float ms = 0.f;
+        PK_CUDA(h, cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+        const int ph = h->ev_phase[i / 2];
+        if (ph >= 0 && ph < 4) ms4[ph] += (double)ms;
+    }
+    h->ev_used = 0;
+    return 0;
+}
+
+int pk_fp64_peak(pk_handle* h, double* dmma_tflops, double* dfma_tflops) {
+    if (!h) return 1;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    PK_CUDA(h, pk::measure_fp64_peak(h, dmma_tflops, dfma_tflops));
     return 0;
 }
 
@@ -222,17 +271,25 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
     if (to_device(h, mode == PK_MODE_REGRESSION ? lambda : nullptr, h->d_lambda, (size_t)C, &d_lambda)) return 1;
 
     if (h->n <= PK_SMALL_N_MAX) {
+        pk::phase_begin(h, 1);
         PK_CUDA(h, pk::launch_small_nll(h, C, d_theta, d_p, d_lambda, mode, h->d_out, h->d_info));
+        pk::phase_end(h);
     } else {
         const pk::TiledShape s = pk::tiled_shape(h->n, false);
         int chunk = 0;
         if (ensure_workspace(h, s.elems() * sizeof(double), C, &chunk)) return 1;
         for (int c0 = 0; c0 < C; c0 += chunk) {
             const int cc = (C - c0 < chunk) ? (C - c0) : chunk;
+            pk::phase_begin(h, 0);
             PK_CUDA(h, pk::launch_psi_build(h, s, cc, d_theta + (size_t)c0 * k, d_p + (size_t)c0 * k,
                                             d_lambda ? d_lambda + c0 : nullptr, mode, h->d_ws, h->d_info + c0));
+            pk::phase_end(h);
+            pk::phase_begin(h, 1);
             PK_CUDA(h, pk::launch_cholesky(h, s, cc, h->d_ws, h->d_info + c0));
+            pk::phase_end(h);
+            pk::phase_begin(h, 2);
             PK_CUDA(h, pk::launch_nll_epilogue(h, s, cc, h->d_ws, h->d_out + c0, h->cap_C, h->d_info + c0));
+            pk::phase_end(h);
         }
     }
     double* outs[4] = {nll, mu, sigma2, lndet};
@@ -329,7 +386,9 @@ int pk_predict_batch(pk_handle* h, int64_t m, const double* Xq, const double* th
     const bool q_dev = is_device_ptr(Xq);
     const bool out_dev = (!yhat || is_device_ptr(yhat)) && (!s || is_device_ptr(s)) && (!ei || is_device_ptr(ei));
     if (q_dev && out_dev) {
+        pk::phase_begin(h, 3);
         PK_CUDA(h, pk::launch_predict(h, m, Xq, h->d_hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, s, ei));
+        pk::phase_end(h);
         return 0;
     }
     // host path: stream the queries through a device staging buffer in chunks
@@ -350,7 +409,9 @@ int pk_predict_batch(pk_handle* h, int64_t m, const double* Xq, const double* th
         double* o0 = yhat ? h->d_qout : nullptr;
         double* o1 = s ? h->d_qout + chunk : nullptr;
         double* o2 = ei ? h->d_qout + 2 * chunk : nullptr;
+        pk::phase_begin(h, 3);
         PK_CUDA(h, pk::launch_predict(h, mc, xq_d, h->d_hp, mu, sigma2, y_min, ei_weight, var_extra, o0, o1, o2));
+        pk::phase_end(h);
         if (yhat) PK_CUDA(h, cudaMemcpyAsync(yhat + q0, o0, sizeof(double) * mc, cudaMemcpyDefault, h->stream));
         if (s) PK_CUDA(h, cudaMemcpyAsync(s + q0, o1, sizeof(double) * mc, cudaMemcpyDefault, h->stream));
         if (ei) PK_CUDA(h, cudaMemcpyAsync(ei + q0, o2, sizeof(double) * mc, cudaMemcpyDefault, h->stream));

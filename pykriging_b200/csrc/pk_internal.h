@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/pykriging_b200.h"
 #include "pk_common.cuh"
@@ -14,6 +15,10 @@ struct pk_handle {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;   // recorded events, 2 per phase instance
+    std::vector<int> ev_phase;          // phase id of every event pair
+    size_t ev_used = 0;
     double pivot_tol = 2.0 * PK_EPS_DIAG;  // relative pivot threshold, 2 ulps (see pk_set_pivot_tolerance)
 
     // model data (pk_set_data)
@@ -95,5 +100,10 @@ cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const doub
                            double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
                            double* ei);
 cudaError_t launch_extract_U(pk_handle* h, const TiledShape& s, double* out);
+cudaError_t measure_fp64_peak(pk_handle* h, double* dmma, double* dfma);
+
+// phase timing helpers (no-ops unless h->profiling)
+void phase_begin(pk_handle* h, int phase);
+void phase_end(pk_handle* h);
 
 }  // namespace pk

@@ -1,0 +1,193 @@
+"""Drop-in replacement of ``pyKriging.matrixops.matrixops`` (reference: pyKriging/matrixops.py:1-110).
+
+Same class name, same method names, same attribute names -- ``kriging`` / ``regression_kriging``
+inherit from it exactly as they do in the reference (krige.py:22, regressionkrige.py:20) -- but every
+method is a thin call into the C ABI (``include/pykriging_b200.h``); no linear algebra happens in
+Python and there is no CPU fallback.
+
+State machine kept from the reference:
+  * ``updatePsi`` / ``regupdatePsi`` overwrite ``Psi`` always, ``U`` only when the factorisation
+    succeeds; on failure they raise ``numpy.linalg.LinAlgError`` like ``np.linalg.cholesky`` does.
+  * ``neglikelihood`` / ``regneglikelihood`` use whatever factor is current (possibly stale).
+  * the predictors use the CURRENT ``theta`` / ``pl`` for the psi vector and the CURRENT (possibly
+    stale) ``mu`` / ``SigmaSqr``.
+``Psi`` and ``U`` live on the device and are copied to host arrays only on attribute access.
+The reference's ``distance`` tensor (n x n x k, 84 MB at n=1024, k=10) is never materialised.
+"""
+import numpy as np
+
+from . import _lib
+
+
+class matrixops(object):
+    _pk_device = 0  # class-level default GPU; override per instance with `device=` or set_device()
+
+    def __init__(self):
+        self.LnDetPsi = None
+        self.psi = np.zeros((self.n, 1))
+        self.one = np.ones(self.n)
+        self.mu = None
+        self.SigmaSqr = None
+        self.Lambda = 1
+        self._pk_reset_factor()
+        self.updateData()
+
+    # -- device plumbing ------------------------------------------------------------------------
+    def _pk_handle(self):
+        h = self.__dict__.get("_pk")
+        if h is None:
+            h = _lib.Handle(self.__dict__.get("_pk_device", type(self)._pk_device))
+            self.__dict__["_pk"] = h
+        return h
+
+    def set_device(self, device):
+        """Move the model to another GPU of this process (drops device state)."""
+        old = self.__dict__.pop("_pk", None)
+        if old is not None:
+            old.close()
+        self.__dict__["_pk_device"] = int(device)
+        self._pk_reset_factor()
+        self.updateData()
+
+    def _pk_reset_factor(self):
+        self._has_U = False          # reference: self.U = None
+        self._fit_vals = None        # (NegLnLike, mu, SigmaSqr, LnDetPsi) of the current factor
+        self._psi_host = None
+        self._U_host = None
+        self._psi_ever = False
+        self._pending_factor = None  # (theta, pl, Lambda, mode): factor to restore lazily
+
+    def _pk_ensure_factor(self):
+        """After a batched fittingObjective the reference's self.U is the factor of the last
+        successfully evaluated candidate.  The batched call already recorded its scalars
+        (``_fit_vals``); the factor itself is re-created on the device only if somebody needs it
+        (U access or a prediction)."""
+        pend = self._pending_factor
+        if pend is not None:
+            self._pending_factor = None
+            th, pl, lam, mode = pend
+            self._pk_handle().fit(th, pl, lam, mode)
+            self._U_host = None
+            self._psi_host = None
+
+    def _pk_record_batch_state(self, last_ok_vals, last_ok_params, mode):
+        """Post-state of the reference's candidate loop."""
+        self._psi_ever = True
+        self._psi_host = None
+        if last_ok_vals is not None:
+            nll, mu, s2, lndet = last_ok_vals
+            self.LnDetPsi = np.float64(lndet)
+            self.mu = np.float64(mu)
+            self.SigmaSqr = np.float64(s2)
+            self.NegLnLike = np.float64(nll)
+            self._fit_vals = np.array([nll, mu, s2, lndet], dtype=float)
+            self._has_U = True
+            self._U_host = None
+            th, pl, lam = last_ok_params
+            self._pending_factor = (np.array(th, dtype=float), np.array(pl, dtype=float), float(lam), mode)
+
+    # -- reference attributes that live on the device ---------------------------------------------
+    @property
+    def Psi(self):
+        if not self._psi_ever:
+            return np.zeros((self.n, self.n), dtype=float)  # matrixops.py:9
+        if self._psi_host is None:
+            self._psi_host = self._pk_handle().get_psi()
+        return self._psi_host
+
+    @Psi.setter
+    def Psi(self, value):  # the reference assigns zeros in __init__/updatePsi; ignore
+        pass
+
+    @property
+    def U(self):
+        self._pk_ensure_factor()
+        if not self._has_U:
+            return None  # matrixops.py:13
+        if self._U_host is None:
+            self._U_host = self._pk_handle().get_U()
+        return self._U_host
+
+    @U.setter
+    def U(self, value):
+        if value is None:
+            self._has_U = False
+
+    # -- matrixops.py:18-22 -----------------------------------------------------------------------
+    def updateData(self):
+        """Upload X, y (O(nk) bytes); replaces the O(n^2 k) distance tensor build."""
+        self._pk_handle().set_data(np.ascontiguousarray(self.X, dtype=float),
+                                   np.ascontiguousarray(self.y, dtype=float))
+        self._pending_factor = None
+
+    # -- matrixops.py:24-32 / 34-42 ---------------------------------------------------------------
+    def _pk_factorise(self, mode):
+        self.one = np.ones(self.n)
+        self.psi = np.zeros((self.n, 1))
+        self._pending_factor = None
+        lam = float(self.Lambda) if mode == _lib.MODE_REGRESSION else 0.0
+        out4, info = self._pk_handle().fit(np.asarray(self.theta, dtype=float), np.asarray(self.pl, dtype=float),
+                                           lam, mode)
+        self._psi_host = None
+        self._psi_ever = True
+        if info != 0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        self._has_U = True
+        self._U_host = None
+        self._fit_vals = out4
+
+    def updatePsi(self):
+        self._pk_factorise(_lib.MODE_INTERP)
+
+    def regupdatePsi(self):
+        self._pk_factorise(_lib.MODE_REGRESSION)
+
+    # -- matrixops.py:45-56 / 58-66 ---------------------------------------------------------------
+    def neglikelihood(self):
+        if not self._has_U:
+            raise AttributeError("'NoneType' object has no attribute 'T'")  # self.U is None (matrixops.py:48)
+        nll, mu, s2, lndet = self._fit_vals
+        self.LnDetPsi = np.float64(lndet)
+        self.mu = np.float64(mu)
+        self.SigmaSqr = np.float64(s2)
+        self.NegLnLike = np.float64(nll)
+
+    def regneglikelihood(self):
+        self.neglikelihood()
+
+    # -- predictors: matrixops.py:68-110 -------------------------------------------------------------
+    def _pk_predict(self, X, want, y_min=0.0, ei_weight=-1.0, var_extra=0.0):
+        self._pk_ensure_factor()
+        if not self._has_U:
+            raise AttributeError("'NoneType' object has no attribute 'T'")
+        Xq = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=float)))
+        mu = float(self.mu)
+        s2 = float(self.SigmaSqr) if self.SigmaSqr is not None else float("nan")
+        return self._pk_handle().predict_batch(Xq, np.asarray(self.theta, dtype=float),
+                                               np.asarray(self.pl, dtype=float), mu, s2, y_min=y_min,
+                                               ei_weight=ei_weight, var_extra=var_extra, want=want)
+
+    def predict_normalized(self, x):
+        return np.float64(self._pk_predict(x, ("yhat",))["yhat"][0])
+
+    def predicterr_normalized(self, x):
+        return np.float64(self._pk_predict(x, ("s",))["s"][0])
+
+    def regression_predicterr_normalized(self, x):
+        return np.float64(self._pk_predict(x, ("s",), var_extra=float(self.Lambda))["s"][0])
+
+    # -- batched forms (what the per-point loops of the reference should call) -----------------------
+    def predict_normalized_batch(self, X):
+        return self._pk_predict(X, ("yhat",))["yhat"]
+
+    def predicterr_normalized_batch(self, X):
+        return self._pk_predict(X, ("s",))["s"]
+
+    def expimp_batch(self, X, w=None):
+        """expimp / weightedexpimp (krige.py:201-234) for many model-unit points at once."""
+        y_min = float(np.min(self.y))
+        return self._pk_predict(X, ("ei",), y_min=y_min, ei_weight=-1.0 if w is None else float(w))["ei"]
+
+    def predict_all_batch(self, X, w=None):
+        y_min = float(np.min(self.y))
+        return self._pk_predict(X, ("yhat", "s", "ei"), y_min=y_min, ei_weight=-1.0 if w is None else float(w))

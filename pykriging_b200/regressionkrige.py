@@ -1,0 +1,111 @@
+"""``regression_kriging`` -- the reference's nugget-regularised model class
+(pyKriging/regressionkrige.py:20-725) on top of the B200 ``matrixops`` mixin.
+
+It mirrors ``kriging`` 1:1 with one extra hyper-parameter ``Lambda`` (candidate layout
+``[theta_1..k, p_1..k, lambda]``), the reference's different bounds and population sizes, and its
+failure semantics: ``updateModel`` swallows a failed factorisation (regressionkrige.py:167-172), so
+``regneglikelihood`` is evaluated on the STALE factor of the last successful candidate and repeats
+that candidate's likelihood.
+"""
+import copy
+
+import numpy as np
+
+from . import _lib
+from .krige import kriging
+
+
+class regression_kriging(kriging):
+    _pk_mode = _lib.MODE_REGRESSION
+    _train_pop = {'pso': 150, 'ga': 50}  # regressionkrige.py:376, 391
+
+    def _init_bounds(self):
+        # regressionkrige.py:38-41
+        self.thetamin = 1e-4
+        self.thetamax = 100
+        self.pmin = 1.81231
+        self.pmax = 2
+
+    # regressionkrige.py:75-82: no k == 1 np.float64 special case
+    def normX(self, X):
+        X = copy.deepcopy(X)
+        for i in range(self.k):
+            X[i] = (X[i] - self.normRange[i][0]) / float(self.normRange[i][1] - self.normRange[i][0])
+        return X
+
+    def _bounds(self):
+        lowerBound = [self.thetamin] * self.k + [self.pmin] * self.k + [0]
+        upperBound = [self.thetamax] * self.k + [self.pmax] * self.k + [1]
+        return lowerBound, upperBound
+
+    def _set_hyper_all(self, values):
+        self._set_hyper(values)
+        self.Lambda = values[-1]
+
+    def update(self, values):
+        self._set_hyper(values)
+        self.Lambda = values[-1]
+        self.updateModel()
+
+    def updateModel(self):
+        try:
+            self.regupdatePsi()
+        except Exception:
+            pass  # regressionkrige.py:169-170
+
+    def predict(self, X, norm=True):
+        X = copy.deepcopy(X)
+        if norm:
+            X = self.normX(X)
+        return self.inversenormy(self.predict_normalized(X))
+
+    def predict_var(self, X, norm=True):
+        X = copy.deepcopy(X)
+        if norm:
+            X = self.normX(X)
+        return self.predicterr_normalized(X)
+
+    def _infill_result(self, newpoint):
+        return np.array(newpoint, dtype=float)  # regressionkrige.py:290 (no inversenormX)
+
+    def fittingObjective(self, candidates, args):
+        """NegLnLike of every candidate [theta, p, lambda] in ONE batched device call, followed by the
+        host post-pass that reproduces the reference's stale-factor semantics."""
+        cands = np.asarray(candidates, dtype=float)
+        if cands.size == 0:
+            return []
+        k = self.k
+        out = self._pk_handle().nll_batch(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
+                                          np.ascontiguousarray(cands[:, -1]), _lib.MODE_REGRESSION)
+        fitness = []
+        last_ok = -1
+        # factor present before this call? (then a failed candidate repeats ITS likelihood)
+        current = np.float64(self._fit_vals[0]) if self._has_U else None
+        for i in range(len(cands)):
+            if out["info"][i] == 0:
+                current = np.float64(out["nll"][i])
+                last_ok = i
+            fitness.append(10000 if current is None else current)
+        self._set_hyper(cands[-1])
+        self.Lambda = cands[-1][-1]
+        if last_ok >= 0:
+            vals = (out["nll"][last_ok], out["mu"][last_ok], out["sigma2"][last_ok], out["lndet"][last_ok])
+            self._pk_record_batch_state(vals, (cands[last_ok, :k], cands[last_ok, k:2 * k], cands[last_ok, -1]),
+                                        _lib.MODE_REGRESSION)
+        else:
+            self._pk_record_batch_state(None, None, _lib.MODE_REGRESSION)
+            if self._has_U:  # regneglikelihood re-evaluated on the stale factor refreshes these
+                self.neglikelihood()
+        return fitness
+
+    def fittingObjective_local(self, entry):
+        f = 10000
+        self._set_hyper(entry)
+        self.Lambda = entry[-1]
+        try:
+            self.updateModel()
+            self.regneglikelihood()
+            f = self.NegLnLike
+        except Exception:
+            f = 10000
+        return f

@@ -1,0 +1,217 @@
+"""GPU tests of the reference-facing classes (``kriging`` / ``regression_kriging`` on the CUDA
+``matrixops``) against the CPU oracle: batched fittingObjective incl. penalty / stale-U semantics and
+post-state, update/predict/expimp, addPoint, infill objectives, and a full ``train()`` under a fixed
+optimiser seed against the inspyred restatement driving the oracle likelihood."""
+from random import Random
+
+import numpy as np
+import pytest
+from scipy.optimize import minimize
+
+from oracle import inspyred_port as ip
+from oracle import oracle_np as onp
+from tests.golden_util import SMALL_CASES, fh, fha, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _classes():
+    from pykriging_b200.krige import kriging
+    from pykriging_b200.regressionkrige import regression_kriging
+
+    return kriging, regression_kriging
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_fitting_objective_sequence_and_poststate(name):
+    """Same list in -> same list out as the unmodified reference (golden), incl. the int 10000 penalty
+    (krige.py:447-450) and the regression stale-factor repeats (regressionkrige.py:167-172)."""
+    doc = load_case(name)
+    K, R = _classes()
+    m = (R if doc["regression"] else K)(doc["X_arr"], doc["y_arr"])
+    fo = doc["fittingObjective"]
+    cands = [list(fha(c)) for c in fo["candidates"]]
+    got = m.fittingObjective(cands, {})
+    want = [fh(v) for v in fo["fitness"]]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        if isinstance(w, int):
+            assert isinstance(g, int) and g == 10000
+        else:
+            assert not isinstance(g, int)
+            assert rel_err(g, w) < 1e-7  # some golden candidates have cond(Psi) up to 1e7
+    assert np.array_equal(m.theta, fha(fo["post_theta"]))
+    assert np.array_equal(m.pl, fha(fo["post_pl"]))
+    if fo["post_mu"] is not None:
+        assert rel_err(m.mu, fh(fo["post_mu"])) < 1e-7
+        assert rel_err(m.SigmaSqr, fh(fo["post_sigma2"])) < 1e-7
+        assert rel_err(m.NegLnLike, fh(fo["post_nll"])) < 1e-7
+    if doc["regression"]:
+        assert m.Lambda == fh(fo["post_Lambda"])
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_update_predict_expimp_match_golden(name):
+    doc = load_case(name)
+    K, R = _classes()
+    m = (R if doc["regression"] else K)(doc["X_arr"], doc["y_arr"])
+    assert m.U is None and m.Lambda == 1  # fresh-model state of the reference
+    for blk in doc["predictions"]:
+        c = fha(blk["candidate"])
+        m.update(c)
+        (m.regneglikelihood if doc["regression"] else m.neglikelihood)()
+        assert rel_err(m.mu, fh(blk["mu"])) < 1e-9
+        assert rel_err(m.SigmaSqr, fh(blk["sigma2"])) < 1e-9
+        assert rel_err(m.NegLnLike, fh(blk["nll"])) < 1e-9
+        pts = np.array([fha(p["x_model"]) for p in blk["points"]])
+        for p in blk["points"][:6]:
+            x = fha(p["x_model"])
+            xr = fha(p["x_real"])
+            assert rel_err(m.predict_normalized(x), fh(p["predict_normalized"])) < 1e-9
+            assert rel_err(m.predict(xr), fh(p["predict"])) < 1e-9
+            assert abs(m.predicterr_normalized(x) - fh(p["predicterr_normalized"])) < 1e-7
+            assert abs(m.predict_var(xr) - fh(p["predict_var"])) < 1e-7
+            assert abs(m.expimp(x) - fh(p["expimp"])) < 1e-7
+            assert abs(m.weightedexpimp(x, 0.3) - fh(p["weightedexpimp_0.3"])) < 1e-7
+        mse = m.infill_objective_mse(pts.tolist(), {})
+        ei = m.infill_objective_ei(pts.tolist(), {})
+        assert np.max(np.abs(np.array(mse) - fha(blk["infill_objective_mse"]))) < 1e-7
+        assert np.max(np.abs(np.array(ei) - fha(blk["infill_objective_ei"]))) < 1e-7
+        U = m.U
+        assert U.shape == (m.n, m.n) and np.allclose(U.T @ U, m.Psi, rtol=1e-12, atol=1e-13)
+
+
+def test_bad_params_raise_and_keep_state():
+    K, _ = _classes()
+    doc = load_case("c1_branin_n20_k2")
+    m = K(doc["X_arr"], doc["y_arr"])
+    m.update([10, 0.5, 1.5, 1.9])
+    m.neglikelihood()
+    U0, mu0 = m.U.copy(), m.mu
+    with pytest.raises(Exception, match="bad params"):
+        m.update([1e-5, 1e-5, 2, 2])
+    assert np.array_equal(m.U, U0) and m.mu == mu0
+    assert np.array_equal(m.theta, [1e-5, 1e-5])
+    assert m.fittingObjective_local([1e-5, 1e-5, 2, 2]) == 10000
+    f = m.fittingObjective_local([10, 0.5, 1.5, 1.9])
+    assert rel_err(f, -26.774947339276977) < 1e-9  # SURVEY section 4 known answer
+
+
+def test_addpoint_matches_oracle():
+    K, _ = _classes()
+    X = onp.rlh(30, 2, 3)
+    y = onp.f_branin(X)
+    m = K(X, y)
+    m.update([5.0, 3.0, 1.9, 1.7])
+    m.neglikelihood()
+    newx = np.array([0.31, 0.77])
+    newy = float(onp.f_branin(newx)[0])
+    m.addPoint(newx, newy)
+    assert m.n == 31
+    Xn = m.X
+    yn = m.y
+    ref = onp.predict_batch_fast(Xn, yn, m.theta, m.pl, onp.EPS_DIAG, np.array([[0.5, 0.5]]))
+    m.neglikelihood()
+    assert rel_err(m.mu, ref["mu"]) < 1e-9
+    assert rel_err(m.predict_normalized(np.array([0.5, 0.5])), ref["yhat"][0]) < 1e-9
+
+
+def _oracle_train(X, y, optimizer, seed, pop, regression=False):
+    """The reference's train() (krige.py:355-427) restated on the CPU oracle + inspyred port."""
+    ora = onp.OracleKriging(X, y, regression=regression)
+    k = ora.k
+    if regression:
+        lo = [1e-4] * k + [1.81231] * k + [0]
+        hi = [100] * k + [2] * k + [1]
+    else:
+        lo = [1e-5] * k + [1] * k
+        hi = [100] * k + [2] * k
+
+    def gen(random, args):
+        b = args["_ec"].bounder
+        return [random.uniform(l, h) for l, h in zip(b.lower_bound, b.upper_bound)]
+
+    def term(population, num_generations, num_evaluations, args):
+        mg = args.setdefault('max_generations', 10)
+        pb = args.setdefault('previous_best', None)
+        me = args.setdefault('max_evaluations', 30000)
+        cb = np.around(max(population).fitness, decimals=4)
+        if pb is None or pb != cb:
+            args['previous_best'] = cb
+            args['generation_count'] = 0
+            return False or (num_evaluations >= me)
+        if args['generation_count'] >= mg:
+            return True
+        args['generation_count'] += 1
+        return False or (num_evaluations >= me)
+
+    def evaluator(candidates, args):
+        return ora.fittingObjective(candidates)
+
+    if optimizer == 'pso':
+        ea = ip.PSO(Random(seed))
+        ea.terminator = term
+        final = ea.evolve(generator=gen, evaluator=evaluator, pop_size=pop, maximize=False,
+                          bounder=ip.Bounder(lo, hi), max_evaluations=30000, neighborhood_size=20, num_inputs=k)
+        final.sort(reverse=True)
+    else:
+        ea = ip.GA(Random(seed))
+        ea.terminator = term
+        final = ea.evolve(generator=gen, evaluator=evaluator, pop_size=pop, maximize=False,
+                          bounder=ip.Bounder(lo, hi), max_evaluations=30000, num_elites=10, mutation_rate=.05)
+    return ora, ea, final
+
+
+@pytest.mark.parametrize("optimizer,case,pop", [("ga", "c1_branin_n20_k2", 300), ("pso", "c2_squared_n40_k3", 256)])
+def test_train_selects_same_best_under_fixed_seed(optimizer, case, pop):
+    """BASELINE configs[0]/[1]: the global search must pick the same best theta/p as the CPU restatement
+    under a fixed optimiser seed (inspyred restatement: parity unpinned, see oracle/inspyred_port.py)."""
+    doc = load_case(case)
+    K, _ = _classes()
+    seed = 2024
+    ora, ea_ref, final_ref = _oracle_train(doc["X_arr"], doc["y_arr"], optimizer, seed, pop)
+    m = K(doc["X_arr"], doc["y_arr"])
+    m.train(optimizer=optimizer, seed=seed, pop_size=pop)
+    ea = m._last_ea
+    best_ref = final_ref[0]
+    best = max(ea.population)
+    # The search is chaotic in the last bits: once two candidates of near-equal fitness swap rank the
+    # trajectories may diverge.  Require identical generation count and best candidate when the traces
+    # agree, and always require the same best fitness to 1e-6 (4-decimal rounding drives termination).
+    assert rel_err(best.fitness, best_ref.fitness) < 1e-6
+    if ea.num_generations == ea_ref.num_generations:
+        assert np.allclose(best.candidate, best_ref.candidate, rtol=1e-9, atol=1e-12)
+    # SLSQP polish from the same start on the oracle objective
+    lo, hi = m._bounds()
+    res = minimize(lambda e: ora.fittingObjective([list(e)])[0], best_ref.candidate, method='SLSQP',
+                   bounds=list(zip(lo, hi)), options={'disp': False})
+    got = np.concatenate([m.theta, m.pl])
+    f_got = m.fittingObjective_local(got)
+    assert f_got <= res.fun + 1e-3 * abs(res.fun) + 1e-6
+
+
+def test_regression_train_runs_and_predicts():
+    _, R = _classes()
+    doc = load_case("reg_branin_noise_n20_k2")
+    m = R(doc["X_arr"], doc["y_arr"])
+    m.train(optimizer='ga', seed=5)
+    assert 0.0 <= m.Lambda <= 1.0
+    m.regneglikelihood()
+    v = m.predict(np.array(doc["X_arr"][3]))
+    assert np.isfinite(v)
+    assert m.predict_var(np.array(doc["X_arr"][3])) >= 0.0
+
+
+def test_infill_returns_points_in_bounds():
+    K, _ = _classes()
+    doc = load_case("c1_branin_n20_k2")
+    m = K(doc["X_arr"], doc["y_arr"])
+    m.update([1.38569, 0.29047, 1.97596, 2.0])
+    m.neglikelihood()
+    pts = m.infill(2, method='ei', addPoint=True, seed=3)
+    assert pts.shape == (2, 2) and m.n == 20
+    lo = np.array([r[0] for r in m.normRange])
+    hi = np.array([r[1] for r in m.normRange])
+    assert np.all(pts >= lo - 1e-12) and np.all(pts <= hi + 1e-12)
+    pts2 = m.infill(1, method='error', addPoint=False, seed=4)
+    assert pts2.shape == (1, 2)
