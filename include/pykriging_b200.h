@@ -132,6 +132,12 @@ int pk_phase_times(pk_handle *h, double *ms4);
  * launches that fill every SM. */
 int pk_fp64_peak(pk_handle *h, double *dmma_tflops, double *dfma_tflops);
 
+/* Diagnostic: evaluates the device building blocks of the Psi kernel on arrays of m doubles --
+ * out_pow[i] = |d[i]|^p[i] through the log2-split / table-driven 2^x path that replaces np.power
+ * (matrixops.py:28), out_expneg[i] = e^(-d[i]) through the table-driven exponential that replaces
+ * np.exp.  Tests use it to bound their error in ulps against a correctly rounded reference. */
+int pk_debug_math(pk_handle *h, int64_t m, const double *d, const double *p, double *out_pow, double *out_expneg);
+
 /* Tuning knob: limit the device workspace (bytes) used for candidate chunks (0 = default). */
 int pk_set_workspace_limit(pk_handle *h, int64_t bytes);
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "pk_version", "pk_last_error", "pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit",
     "pk_predict_batch", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
     "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
-    "pk_fp64_peak",
+    "pk_fp64_peak", "pk_debug_math",
 ]
 
 _lib = None
@@ -69,6 +69,8 @@ def load():
     lib.pk_phase_times.restype = ctypes.c_int
     lib.pk_fp64_peak.argtypes = [hp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.pk_fp64_peak.restype = ctypes.c_int
+    lib.pk_debug_math.argtypes = [hp, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp]
+    lib.pk_debug_math.restype = ctypes.c_int
     for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
                  "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_set_workspace_limit"):
         getattr(lib, name).restype = ctypes.c_int
@@ -242,6 +244,13 @@ class Handle(object):
         a, b = ctypes.c_double(), ctypes.c_double()
         self._check(self.lib.pk_fp64_peak(self._h, ctypes.byref(a), ctypes.byref(b)), "pk_fp64_peak")
         return {"dmma_tflops": a.value, "dfma_tflops": b.value}
+
+    def debug_math(self, d, p):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        a, b = np.empty_like(d), np.empty_like(d)
+        self._check(self.lib.pk_debug_math(self._h, d.size, _addr(d), _addr(p), _addr(a), _addr(b)), "pk_debug_math")
+        return a, b
 
     def set_pivot_tolerance(self, tol):
         self._check(self.lib.pk_set_pivot_tolerance(self._h, float(tol)), "pk_set_pivot_tolerance")

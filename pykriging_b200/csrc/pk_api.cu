@@ -7,7 +7,8 @@
 #include "pk_internal.h"
 
 namespace pk {
-cudaError_t launch_extract_psi(pk_handle* h, const TiledShape& s, const double* M, double* out);
+cudaError_t launch_debug_math(pk_handle* h, int64_t m, const double* d, const double* p, double* out_pow,
+                              double* out_expneg);
 }
 
 static std::string g_create_error;
@@ -177,6 +178,22 @@ int pk_set_pivot_tolerance(pk_handle* h, double tol) {
     return 0;
 }
 
+int pk_debug_math(pk_handle* h, int64_t m, const double* d, const double* p, double* out_pow, double* out_expneg) {
+    if (!h || m < 0 || !d || !p || !out_pow || !out_expneg) return 1;
+    if (m == 0) return 0;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    double* buf = nullptr;
+    PK_CUDA(h, cudaMalloc((void**)&buf, sizeof(double) * 4 * (size_t)m));
+    PK_CUDA(h, cudaMemcpyAsync(buf, d, sizeof(double) * m, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(buf + m, p, sizeof(double) * m, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, pk::launch_debug_math(h, m, buf, buf + m, buf + 2 * m, buf + 3 * m));
+    PK_CUDA(h, cudaMemcpyAsync(out_pow, buf + 2 * m, sizeof(double) * m, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(out_expneg, buf + 3 * m, sizeof(double) * m, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    PK_CUDA(h, cudaFree(buf));
+    return 0;
+}
+
 int pk_set_profiling(pk_handle* h, int enabled) {
     if (!h) return 1;
     h->profiling = enabled != 0;
@@ -228,13 +245,18 @@ int pk_set_data(pk_handle* h, int n, int k, const double* X, const double* y) {
 }
 
 static int ensure_workspace(pk_handle* h, size_t per_matrix_bytes, int C, int* chunk_out) {
+    // NB: cudaMemGetInfo serialises with in-flight work (tens of ms while kernels run), so the automatic
+    // limit is sampled once and cached, never on the per-generation path.
     size_t limit = h->ws_limit;
     if (limit == 0) {
-        size_t free_b = 0, total_b = 0;
-        PK_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
-        limit = (size_t)((double)(free_b + h->ws_bytes) * 0.6);
-        const size_t cap = (size_t)64 << 30;
-        if (limit > cap) limit = cap;
+        if (h->ws_limit_auto == 0) {
+            size_t free_b = 0, total_b = 0;
+            PK_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+            size_t lim = (size_t)((double)(free_b + h->ws_bytes) * 0.6);
+            const size_t cap = (size_t)64 << 30;
+            h->ws_limit_auto = lim > cap ? cap : lim;
+        }
+        limit = h->ws_limit_auto;
     }
     size_t chunk = limit / per_matrix_bytes;
     if (chunk < 1) chunk = 1;
@@ -341,7 +363,7 @@ int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, in
     if (to_device(h, p, h->d_p, (size_t)k, &d_p)) return 1;
     PK_CUDA(h, cudaMemcpyAsync(h->d_lambda, &lambda, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     PK_CUDA(h, pk::launch_psi_build(h, s, 1, d_theta, d_p, h->d_lambda, mode, h->d_try, h->d_info));
-    PK_CUDA(h, pk::launch_extract_psi(h, s, h->d_try, h->d_psi));
+    PK_CUDA(h, pk::launch_extract_psi(h, s, h->d_try, h->d_psi, 1));
     PK_CUDA(h, pk::launch_cholesky(h, s, 1, h->d_try, h->d_info));
     PK_CUDA(h, pk::launch_nll_epilogue(h, s, 1, h->d_try, h->d_out, h->cap_C, h->d_info));
     double host4[4];
@@ -459,21 +481,29 @@ int pk_psi_batch(pk_handle* h, int C, const double* theta, const double* p, cons
     if (to_device(h, theta, h->d_theta, (size_t)C * k, &d_theta)) return 1;
     if (to_device(h, p, h->d_p, (size_t)C * k, &d_p)) return 1;
     if (to_device(h, mode == PK_MODE_REGRESSION ? lambda : nullptr, h->d_lambda, (size_t)C, &d_lambda)) return 1;
+    // Psi is built by the same population kernel the likelihood path uses (lower-triangle tiles in the
+    // workspace), then mirrored into full symmetric matrices.
     const size_t per = (size_t)h->n * h->n;
-    if (is_device_ptr(out)) {
-        PK_CUDA(h, pk::launch_psi_full(h, C, d_theta, d_p, d_lambda, mode, out));
-        return 0;
-    }
+    const pk::TiledShape s = pk::tiled_shape(h->n, false);
+    const bool out_dev = is_device_ptr(out);
     int chunk = 0;
-    if (ensure_workspace(h, per * sizeof(double), C, &chunk)) return 1;
+    if (ensure_workspace(h, (s.elems() + (out_dev ? 0 : per)) * sizeof(double), C, &chunk)) return 1;
+    double* stage = h->d_ws + (size_t)chunk * s.elems();
     for (int c0 = 0; c0 < C; c0 += chunk) {
         const int cc = (C - c0 < chunk) ? (C - c0) : chunk;
-        PK_CUDA(h, pk::launch_psi_full(h, cc, d_theta + (size_t)c0 * k, d_p + (size_t)c0 * k,
-                                       d_lambda ? d_lambda + c0 : nullptr, mode, h->d_ws));
-        PK_CUDA(h, cudaMemcpyAsync(out + (size_t)c0 * per, h->d_ws, sizeof(double) * per * cc, cudaMemcpyDefault,
-                                   h->stream));
+        pk::phase_begin(h, 0);
+        PK_CUDA(h, pk::launch_psi_build(h, s, cc, d_theta + (size_t)c0 * k, d_p + (size_t)c0 * k,
+                                        d_lambda ? d_lambda + c0 : nullptr, mode, h->d_ws, h->d_info + c0));
+        pk::phase_end(h);
+        if (out_dev) {
+            PK_CUDA(h, pk::launch_extract_psi(h, s, h->d_ws, out + (size_t)c0 * per, cc));
+        } else {
+            PK_CUDA(h, pk::launch_extract_psi(h, s, h->d_ws, stage, cc));
+            PK_CUDA(h, cudaMemcpyAsync(out + (size_t)c0 * per, stage, sizeof(double) * per * cc, cudaMemcpyDefault,
+                                       h->stream));
+        }
     }
-    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!out_dev) PK_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 

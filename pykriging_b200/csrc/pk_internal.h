@@ -39,6 +39,7 @@ struct pk_handle {
     double* d_ws = nullptr;
     size_t ws_bytes = 0;
     size_t ws_limit = 0;
+    size_t ws_limit_auto = 0;  // cached default (60% of free memory at first use)
 
     // cached fit (pk_fit) for the predictors
     int fit_n = 0;            // n the cache was built for (0 = none)
@@ -92,8 +93,7 @@ cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const dou
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,
                                 int out_stride, int32_t* info);
-cudaError_t launch_psi_full(pk_handle* h, int C, const double* theta, const double* p, const double* lambda,
-                            int mode, double* out);
+cudaError_t launch_extract_psi(pk_handle* h, const TiledShape& s, const double* M, double* out, int C);
 cudaError_t launch_fit_finalize(pk_handle* h, const TiledShape& s);
 cudaError_t launch_compute_w(pk_handle* h, const TiledShape& s, double mu);
 cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,

@@ -53,34 +53,13 @@ __global__ void extract_U_kernel(int n, int ld, const double* __restrict__ M, do
     if (c < n) out[(size_t)r * n + c] = (c >= r) ? M[(size_t)c * ld + r] : 0.0;  // U = L^T
 }
 
-__global__ void extract_psi_kernel(int n, int ld, const double* __restrict__ M, double* __restrict__ out) {
+// full symmetric n x n Psi from the lower-triangle tiles of the tiled layout (blockIdx.z = candidate)
+__global__ void extract_psi_kernel(int n, int ld, size_t elems, const double* __restrict__ ws,
+                                   double* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c < n) out[(size_t)r * n + c] = (c <= r) ? M[(size_t)r * ld + c] : M[(size_t)c * ld + r];
-}
-
-// Full symmetric Psi for a population (diagnostic / K1 benchmark entry point pk_psi_batch).
-__global__ void __launch_bounds__(256)
-psi_full_kernel(int n, int k, const double* __restrict__ X, const double* __restrict__ theta,
-                const double* __restrict__ p, const double* __restrict__ lambda, int mode,
-                double* __restrict__ out) {
-    __shared__ double th[PK_MAX_K], pp[PK_MAX_K];
-    const int cand = blockIdx.z;
-    if (threadIdx.x < k) {
-        th[threadIdx.x] = theta[(size_t)cand * k + threadIdx.x];
-        pp[threadIdx.x] = p[(size_t)cand * k + threadIdx.x];
-    }
-    __syncthreads();
-    const double diag = 1.0 + (mode == PK_MODE_REGRESSION ? lambda[cand] : PK_EPS_DIAG);
-    const int r = blockIdx.y;
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= n) return;
-    double v;
-    if (c == r) v = diag;
-    else {
-        const int lo = min(r, c), hi = max(r, c);  // the reference evaluates |X[i]-X[j]| for i<j and mirrors
-        v = exp(-corr_exponent(X + (size_t)lo * k, X + (size_t)hi * k, th, pp, k));
-    }
-    out[((size_t)cand * n + r) * n + c] = v;
+    const double* M = ws + (size_t)blockIdx.z * elems;
+    double* o = out + (size_t)blockIdx.z * n * n;
+    if (c < n) o[(size_t)r * n + c] = (c <= r) ? M[(size_t)r * ld + c] : M[(size_t)c * ld + r];
 }
 
 // ---- fused predictor -------------------------------------------------------------------------------
@@ -254,17 +233,9 @@ cudaError_t launch_extract_U(pk_handle* h, const TiledShape& s, double* out) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_extract_psi(pk_handle* h, const TiledShape& s, const double* M, double* out) {
-    dim3 grid((s.n + 255) / 256, s.n);
-    extract_psi_kernel<<<grid, 256, 0, h->stream>>>(s.n, s.ld, M, out);
-    h->launches++;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_psi_full(pk_handle* h, int C, const double* theta, const double* p, const double* lambda,
-                            int mode, double* out) {
-    dim3 grid((h->n + 255) / 256, h->n, C);
-    psi_full_kernel<<<grid, 256, 0, h->stream>>>(h->n, h->k, h->dX, theta, p, lambda, mode, out);
+cudaError_t launch_extract_psi(pk_handle* h, const TiledShape& s, const double* M, double* out, int C) {
+    dim3 grid((s.n + 255) / 256, s.n, C);
+    extract_psi_kernel<<<grid, 256, 0, h->stream>>>(s.n, s.ld, s.elems(), M, out);
     h->launches++;
     return cudaGetLastError();
 }

@@ -1,0 +1,272 @@
+// Batched Psi construction for a whole GA/PSO population (the K1 kernel).
+//
+// Replaces the Psi part of matrixops.updatePsi / regupdatePsi (matrixops.py:28-30, 38-40):
+//     Psi_ij = exp(-sum_d theta_d |x_id - x_jd|^p_d)   (i != j),   Psi_ii = 1 + eps | 1 + lambda
+// for C candidates at once, written as the lower-triangle 64x64 tiles the blocked Cholesky consumes.
+//
+// Design (FP64-ALU bound, not HBM bound: k pow + 1 exp per 8 bytes written):
+//   * a CTA owns a (RB rows x 64 cols) block of sample PAIRS and loops over a group of candidates.
+//     The candidate-independent part of |d|^p = 2^(p log2 d) -- log2 d as an unevaluated sum
+//     lh + ll -- is computed ONCE per CTA and kept in registers, so the per-candidate cost of a
+//     (pair, dimension) is one table-driven 2^x (about 15 FP64 instructions) instead of a full pow().
+//   * sample coordinates of the block and the (theta, p) of the candidate group are staged in shared
+//     memory; every thread writes PPT consecutive doubles per candidate (coalesced 16/32-byte stores,
+//     a warp covers whole 128-byte lines).
+//   * p == 2 and p == 1 (what a bounded PSO clips to, krige.py:383) take the exact d*d / d path.
+//   * the sum over dimensions follows NumPy's reduction order (pk_common.cuh), the final exp(-S) is a
+//     Cody-Waite reduced table-driven exponential (< 1 ulp).
+#include "pk_exp2_table.h"
+#include "pk_internal.h"
+
+namespace pk {
+
+// 2^(j/64) as hi + lo (mpmath-generated, tools/gen_exp2_table.py) and the log2(1+z) series
+__constant__ double c_exp2_hi[64] = {PK_EXP2_HI_LIST};
+__constant__ double c_exp2_lo[64] = {PK_EXP2_LO_LIST};
+__constant__ double c_log2p1[9] = {PK_LOG2P1_LIST};
+
+// ---- table-driven 2^x and e^-S ----------------------------------------------------------------------
+// tab = shared copy of g_exp2_table replicated over the 16 eight-byte banks: tab[j * 16 + (lane & 15)]
+// is conflict free for any j pattern.
+constexpr double MAGIC64 = 6755399441055744.0 / 64.0;  // 1.5 * 2^52 / 64: rounds to multiples of 1/64
+constexpr double MAGIC1 = 6755399441055744.0;          // 1.5 * 2^52
+
+__device__ __forceinline__ double scale_pow2(double v, int n) {
+    // v in [1, 2): returns v * 2^n with flush-to-zero below the normal range and inf above it
+    if (n < -1021) return 0.0;
+    if (n > 1022) return CUDART_INF;
+    const long long bits = __double_as_longlong(v) + ((long long)n << 52);
+    return __longlong_as_double(bits);
+}
+
+// 2^(s + e) where s is a double and e a tiny correction (|e| << 1/64)
+__device__ __forceinline__ double exp2_table(double s, double e, const double* __restrict__ tab, int bank) {
+    const double kd = s + MAGIC64;
+    const int ki = __double2loint(kd);          // round(s * 64) in the low mantissa bits
+    const double kf = kd - MAGIC64;             // round(s * 64) / 64
+    const double r = (s - kf) + e;              // |r| <= 1/128 (+ e)
+    // 2^r - 1 = r (c1 + r (c2 + r (c3 + r (c4 + r c5)))), |r| <= 2^-7: truncation < 2^-56
+    double q = fma(r, 0x1.5d87fe78a6731p-10, 0x1.3b2ab6fba4e77p-7);  // ln2^5/120, ln2^4/24
+    q = fma(r, q, 0x1.c6b08d704a0c0p-5);                              // ln2^3/6
+    q = fma(r, q, 0x1.ebfbdff82c58fp-3);                              // ln2^2/2
+    q = fma(r, q, 0x1.62e42fefa39efp-1);                              // ln2
+    q = q * r;
+    const double T = tab[(ki & 63) * 16 + bank];
+    return scale_pow2(fma(T, q, T), ki >> 6);
+}
+
+// e^(-S), S >= 0 (also fine for negative S), Cody-Waite reduction with ln2/64 split in two
+__device__ __forceinline__ double expneg_table(double S, const double* __restrict__ tab, int bank) {
+    const double t = S * -0x1.71547652b82fep+6;  // -64 / ln 2
+    const double kd = t + MAGIC1;
+    const int ki = __double2loint(kd);
+    const double kf = kd - MAGIC1;              // k = round(-S * 64 / ln2)
+    // r = -S - k * ln2/64  (hi part has 21 trailing zero bits: k * hi is exact for |k| < 2^21)
+    double r = fma(kf, -0x1.62e42fee00000p-7, -S);   // fdlibm ln2HI / 64
+    r = fma(kf, -0x1.a39ef35793c76p-39, r);          // fdlibm ln2LO / 64
+    // e^r - 1 = r + r^2/2 + r^3/6 + r^4/24 + r^5/120, |r| <= ln2/128
+    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    q = fma(r, q, 1.6666666666666666e-01);
+    q = fma(r, q, 0.5);
+    q = fma(r, q, 1.0);
+    q = q * r;
+    const double T = tab[(ki & 63) * 16 + bank];
+    if (!(S < 1.0e6)) return (S != S) ? S : 0.0;  // NaN propagates, huge S underflows
+    return scale_pow2(fma(T, q, T), ki >> 6);
+}
+
+// log2 d as an unevaluated sum L + res with L = fl(log2 d) and |res| <= ulp(L)/2, accurate to ~2^-60
+// ABSOLUTE (not relative to L): d = 2^E m, m in [1,2); pick j with 2^(j/64) ~ m, z = m / 2^(j/64) - 1
+// (exact table hi + lo), log2 d = (E + j/64) + log2(1 + z) with a degree-9 series.  Runs once per
+// (pair, dimension) per CTA, never in the candidate loop.
+__device__ __forceinline__ void log2_split(double d, double& L, float& res) {
+    if (!(d >= 2.2250738585072014e-308)) {  // pow(0, p > 0) = 0: a hugely negative exponent underflows to 0
+        L = -1100.0;
+        res = 0.0f;
+        return;
+    }
+    const long long bits = __double_as_longlong(d);
+    int E = (int)((bits >> 52) & 0x7ff) - 1023;
+    double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    int j = __double2int_rn(64.0 * log2(m));  // any nearby j keeps |z| small; accuracy does not depend on it
+    if (j >= 64) {
+        j = 0;
+        E += 1;
+        m *= 0.5;
+    }
+    const double T = c_exp2_hi[j], Tl = c_exp2_lo[j];
+    const double z = ((m - T) - Tl) / T;      // m - T exact (Sterbenz); |z| <= 2^(1/128) - 1
+    double q = c_log2p1[8];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) q = fma(q, z, c_log2p1[i]);
+    const double ll = q * z;                  // log2(1 + z)
+    const double lh = (double)E + (double)j * 0.015625;  // exact
+    L = lh + ll;
+    res = (float)(ll - (L - lh));             // Fast2Sum remainder (|lh| >= |ll| or lh == 0)
+}
+
+constexpr int PSI_THREADS = 256;
+constexpr int PSI_GROUP = 32;  // candidates per CTA
+
+template <int K, int PPT>
+__global__ void __launch_bounds__(PSI_THREADS)
+psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restrict__ X,
+               const double* __restrict__ theta, const double* __restrict__ p,
+               const double* __restrict__ lambda, int mode, double* __restrict__ ws) {
+    constexpr int RB = PSI_THREADS * PPT / PK_TILE;  // rows of the pair block
+    constexpr int SPT = PK_TILE / RB;                // row blocks per tile
+    __shared__ double tab[64 * 16];
+    __shared__ double Xr[RB * K], Xc[PK_TILE * K];
+    __shared__ double th[PSI_GROUP * K], pp[PSI_GROUP * K], dg[PSI_GROUP];
+    const int tid = threadIdx.x, bank = tid & 15;
+    // block -> (lower tile, row block)
+    const int t = blockIdx.x / SPT, sb = blockIdx.x % SPT;
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int r0 = ti * PK_TILE + sb * RB, c0 = tj * PK_TILE;
+    const int g0 = blockIdx.y * PSI_GROUP;
+    const int gn = min(PSI_GROUP, C - g0);
+
+    for (int i = tid; i < 64 * 16; i += PSI_THREADS) tab[i] = c_exp2_hi[i >> 4];
+    for (int i = tid; i < RB * K; i += PSI_THREADS) {
+        const int rr = i / K;
+        Xr[i] = (r0 + rr < n) ? X[(size_t)(r0 + rr) * K + (i % K)] : 0.0;
+    }
+    for (int i = tid; i < PK_TILE * K; i += PSI_THREADS) {
+        const int rr = i / K;
+        Xc[i] = (c0 + rr < n) ? X[(size_t)(c0 + rr) * K + (i % K)] : 0.0;
+    }
+    for (int i = tid; i < gn * K; i += PSI_THREADS) {
+        th[i] = theta[(size_t)g0 * K + i];
+        pp[i] = p[(size_t)g0 * K + i];
+    }
+    if (tid < gn) dg[tid] = 1.0 + (mode == PK_MODE_REGRESSION ? lambda[g0 + tid] : PK_EPS_DIAG);
+    __syncthreads();
+
+    const int lr = tid / (PK_TILE / PPT);            // local row
+    const int lc = (tid % (PK_TILE / PPT)) * PPT;    // first local column
+    const int gr = r0 + lr;
+    double lh[PPT][K];
+    float ll[PPT][K];
+    bool live[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        const int gc = c0 + lc + q;
+        live[q] = (gr < n) && (gc < gr);
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            if (live[q]) log2_split(fabs(Xr[lr * K + d] - Xc[(lc + q) * K + d]), lh[q][d], ll[q][d]);
+            else { lh[q][d] = 0.0; ll[q][d] = 0.0f; }
+        }
+    }
+    bool any_live = false;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) any_live |= live[q];
+
+    for (int g = 0; g < gn; ++g) {
+        double out[PPT];
+        const double* thg = th + g * K;
+        const double* ppg = pp + g * K;
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            const int gc = c0 + lc + q;
+            double v;
+            if (live[q]) {
+                double term[K];
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    const double pd = ppg[d];
+                    double w;
+                    if (pd == 2.0) {
+                        const double dd = fabs(Xr[lr * K + d] - Xc[(lc + q) * K + d]);
+                        w = dd * dd;
+                    } else if (pd == 1.0) {
+                        w = fabs(Xr[lr * K + d] - Xc[(lc + q) * K + d]);
+                    } else {
+                        const double s = pd * lh[q][d];
+                        const double e = fma(pd, (double)ll[q][d], fma(pd, lh[q][d], -s));
+                        w = exp2_table(s, e, tab, bank);
+                    }
+                    term[d] = thg[d] * w;
+                }
+                const double S = sum_numpy_order(K, [&](int d) { return term[d]; });
+                v = expneg_table(S, tab, bank);
+            } else if (gr >= n || gc >= n) {
+                v = (gr == gc) ? 1.0 : 0.0;   // identity padding
+            } else {
+                v = (gr == gc) ? dg[g] : 0.0;  // diagonal / strictly upper part of a diagonal tile
+            }
+            out[q] = v;
+        }
+        double* dst = ws + (size_t)(g0 + g) * elems + (size_t)gr * ld + c0 + lc;
+        if (PPT == 4) {
+            reinterpret_cast<double2*>(dst)[0] = make_double2(out[0], out[1]);
+            reinterpret_cast<double2*>(dst)[1] = make_double2(out[2 % PPT], out[3 % PPT]);
+        } else {
+            reinterpret_cast<double2*>(dst)[0] = make_double2(out[0], out[1 % PPT]);
+        }
+    }
+    (void)any_live;
+}
+
+// diagnostic: the device pow / exp building blocks on arrays (tests measure their ulp error)
+__global__ void debug_math_kernel(int64_t m, const double* __restrict__ d, const double* __restrict__ p,
+                                  double* __restrict__ out_pow, double* __restrict__ out_expneg) {
+    __shared__ double tab[64 * 16];
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) tab[i] = c_exp2_hi[i >> 4];
+    __syncthreads();
+    const int bank = threadIdx.x & 15;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        double lh;
+        float ll;
+        log2_split(fabs(d[i]), lh, ll);
+        const double s = p[i] * lh;
+        const double e = fma(p[i], (double)ll, fma(p[i], lh, -s));
+        out_pow[i] = exp2_table(s, e, tab, bank);
+        out_expneg[i] = expneg_table(d[i], tab, bank);
+    }
+}
+
+cudaError_t launch_debug_math(pk_handle* h, int64_t m, const double* d, const double* p, double* out_pow,
+                              double* out_expneg) {
+    cudaError_t e;
+    debug_math_kernel<<<296, 256, 0, h->stream>>>(m, d, p, out_pow, out_expneg);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+// generic fallback (any k <= PK_MAX_K): defined in pk_tiled.cu
+cudaError_t launch_psi_build_generic(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
+                                     const double* lambda, int mode, double* ws);
+cudaError_t launch_aug_init(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
+
+template <int K>
+static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
+                                  const double* lambda, int mode, double* ws) {
+    constexpr int PPT = (K > 6) ? 2 : 4;
+    constexpr int RB = PSI_THREADS * PPT / PK_TILE;
+    const int nt = s.np / PK_TILE;
+    dim3 grid(nt * (nt + 1) / 2 * (PK_TILE / RB), (C + PSI_GROUP - 1) / PSI_GROUP);
+    psi_pop_kernel<K, PPT><<<grid, PSI_THREADS, 0, h->stream>>>(s.n, s.np, s.ld, s.elems(), C, h->dX, theta, p,
+                                                                 lambda, mode, ws);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
+                             const double* lambda, int mode, double* ws, int32_t* info) {
+    cudaError_t e = cudaSuccess;
+    switch (h->k) {
+#define PK_CASE(KK) case KK: e = launch_psi_pop<KK>(h, s, C, theta, p, lambda, mode, ws); break;
+        PK_CASE(1) PK_CASE(2) PK_CASE(3) PK_CASE(4) PK_CASE(5) PK_CASE(6) PK_CASE(7) PK_CASE(8)
+        PK_CASE(9) PK_CASE(10) PK_CASE(11) PK_CASE(12) PK_CASE(13) PK_CASE(14) PK_CASE(15) PK_CASE(16)
+#undef PK_CASE
+        default: e = launch_psi_build_generic(h, s, C, theta, p, lambda, mode, ws); break;
+    }
+    if (e != cudaSuccess) return e;
+    return launch_aug_init(h, s, C, ws, info);
+}
+
+}  // namespace pk

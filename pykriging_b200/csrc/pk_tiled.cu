@@ -401,14 +401,16 @@ nll_epilogue_kernel(int n, int np, int ld, size_t elems, const double* __restric
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
-                             const double* lambda, int mode, double* ws, int32_t* info) {
+cudaError_t launch_psi_build_generic(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
+                                     const double* lambda, int mode, double* ws) {
     const int nt = s.np / PK_TILE;
     dim3 grid(nt * (nt + 1) / 2, C);
     psi_build_kernel<<<grid, 256, 0, h->stream>>>(s.n, h->k, s.np, s.ld, s.elems(), h->dX, theta, p, lambda, mode, ws);
     h->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aug_init(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     const int aug_elems = (s.rows - s.np) * s.ld;
     dim3 g2(min(64, (aug_elems + 255) / 256), C);
     aug_init_kernel<<<g2, 256, 0, h->stream>>>(s.n, s.np, s.ld, s.rows, s.elems(), h->dy, ws, info);

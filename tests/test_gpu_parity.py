@@ -190,3 +190,26 @@ def test_predict_large_batch_matches_oracle(handle):
     assert np.max(np.abs(got["ei"] - ref["ei"])) < 1e-6 * sig
     only = handle.predict_batch(Xq, theta, p, out4[1], out4[2], want=("yhat",))
     assert np.array_equal(only["yhat"], got["yhat"]) and only["s"] is None
+
+
+def test_device_pow_and_exp_accuracy(handle):
+    """The Psi kernel replaces np.power / np.exp (glibc, < 1 ulp) with a log2-split + table-driven 2^x and
+    a table-driven e^-S.  Bound their error in ulps against an 80-bit long-double reference."""
+    rng = np.random.default_rng(0)
+    m = 200000
+    d = np.concatenate([rng.uniform(0, 1, m // 2), 10.0 ** rng.uniform(-6, 0.3, m // 2)])
+    p = rng.uniform(1.0, 2.0, m)
+    S = np.concatenate([rng.uniform(0, 40, m // 2), 10.0 ** rng.uniform(-8, 2.8, m // 2)])
+    got_pow, _ = handle.debug_math(d, p)
+    _, got_exp = handle.debug_math(S, p)
+    ref_pow = np.power(d.astype(np.longdouble), p.astype(np.longdouble))
+    ref_exp = np.exp(-S.astype(np.longdouble))
+    ulp_pow = np.abs((got_pow.astype(np.longdouble) - ref_pow) / np.spacing(ref_pow.astype(np.float64)).astype(np.longdouble))
+    ok = ref_exp > 1e-300
+    ulp_exp = np.abs((got_exp.astype(np.longdouble) - ref_exp)[ok] / np.spacing(ref_exp.astype(np.float64))[ok].astype(np.longdouble))
+    assert float(ulp_pow.max()) < 2.0, float(ulp_pow.max())
+    assert float(ulp_exp.max()) < 1.5, float(ulp_exp.max())
+    # exact special values the reference relies on
+    z, _ = handle.debug_math(np.array([0.0, 1.0, 1.0]), np.array([1.5, 1.3, 2.0]))
+    assert z[0] == 0.0 and z[1] == 1.0 and z[2] == 1.0
+    print("max ulp error: pow %.3f exp %.3f" % (float(ulp_pow.max()), float(ulp_exp.max())))

@@ -29,6 +29,33 @@ __global__ void dmma_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// half of the warps issue DMMA, the other half DFMA: do the two share execution resources?
+__global__ void mixed_kernel(double* out, int iters) {
+    const int warp = threadIdx.x >> 5;
+    if (warp & 1) {
+        double c[8][2];
+        for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+        double a = threadIdx.x * 1e-3, b = 1.0 - threadIdx.x * 1e-3;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+        }
+        double s = 0;
+        for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else {
+        double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+        const double b = 1.0000001, c = 1e-9;
+        for (int i = 0; i < iters * 8; ++i) {  // 8x the iterations: same stand-alone duration as the DMMA warps
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+        out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    }
+}
+
 int main() {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, 0);
@@ -54,6 +81,19 @@ int main() {
             printf("{\"sms\": %d, \"threads\": %d, \"blocks_per_sm\": %d, \"dfma_tflops\": %.2f, \"dmma_tflops\": %.2f}\n",
                    sms, threads, bps, fl_f / best_f * 1e-9, fl_m / best_m * 1e-9);
         }
+    }
+    {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            float ms;
+            cudaEventRecord(e0); mixed_kernel<<<sms * 2, 512>>>(out, iters); cudaEventRecord(e1);
+            cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+        }
+        // per block: 8 warps DMMA (8 x 256 FMA x iters each), 8 warps DFMA (8 x 32 FMA x iters each)
+        const double fl_m = 2.0 * 256 * 8 * iters * 8.0 * sms * 2;
+        const double fl_f = 2.0 * 8 * (8.0 * iters) * 256.0 * sms * 2;
+        printf("{\"mixed_ms\": %.3f, \"mixed_dmma_tflops\": %.2f, \"mixed_dfma_tflops\": %.2f, \"note\": \"concurrent DMMA+DFMA warps; both rates are over the same interval\"}\n",
+               best, fl_m / best * 1e-9, fl_f / best * 1e-9);
     }
     // sustained (2 s) DMMA
     {
