@@ -105,49 +105,62 @@ __global__ void aug_init_kernel(int n, int np, int ld, int rows, size_t elems, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// GEMM core: acc(BM x 64) = A(BM x K) * B(64 x K)^T, A and B row-major with leading dimension ld
-// (K contiguous), staged through shared memory with a 3-stage cp.async pipeline and consumed by
-// DMMA 8x8x4 fragments.  Warp tile 32x32 (4x4 DMMA tiles, 32 FP64 accumulators per thread).
+// GEMM core: acc(rows x 64) = A(rows x K) * B(64 x K)^T, A and B row-major with leading dimension ld
+// (K contiguous), staged through shared memory with a multi-stage cp.async pipeline and consumed by
+// DMMA 8x8x4 fragments.  256 threads = 4 (M) x 2 (N) warps, warp tile 32x32 (4x4 DMMA tiles,
+// 32 FP64 accumulators per thread), CTA tile up to 128 x 64.
 // ------------------------------------------------------------------------------------------------
 constexpr int KC = 16;            // K chunk per pipeline stage
 constexpr int SLD = KC + 4;       // smem row stride (doubles): 20 -> conflict-free fragment loads
 constexpr int STAGES = 3;
+constexpr int BM = 128;           // rows per CTA tile
+constexpr int THREADS = 256;
+constexpr int A_STAGE = BM * SLD;
+constexpr int B_STAGE = PK_TILE * SLD;
+constexpr int PIPE_DOUBLES = STAGES * (A_STAGE + B_STAGE);
+constexpr int TLD = PK_TILE + 1;  // 65: odd stride -> conflict-free row-per-thread walks (diag tile)
+constexpr int LLD = PK_TILE + 4;  // 68 (== 4 mod 16): L_jj rows, conflict-free DMMA B-fragment loads
+constexpr int XLD = 12;           // solved 8-column block of the panel, conflict-free A-fragment loads
+constexpr int TRSM_DOUBLES = PK_TILE * LLD + PK_TILE + 2 * BM * XLD;
+constexpr int DIAG_DOUBLES = PK_TILE * TLD + PK_TILE * LLD + 2 * PK_TILE;
+constexpr int SMEM_MAX1 = (PIPE_DOUBLES > TRSM_DOUBLES) ? PIPE_DOUBLES : TRSM_DOUBLES;
+constexpr int SMEM_DOUBLES = (SMEM_MAX1 > DIAG_DOUBLES) ? SMEM_MAX1 : DIAG_DOUBLES;
 
-template <int BM, int THREADS>
-struct GemmSmem {
-    static constexpr int A_STAGE = BM * SLD;
-    static constexpr int B_STAGE = PK_TILE * SLD;
-    static constexpr int PIPE_DOUBLES = STAGES * (A_STAGE + B_STAGE);
+// Rows of a CTA tile: local rows [0, split) map to global rows rowA + r, local rows [split, ..) to
+// rowB + (r - split).  (The look-ahead CTA carries tile (j+1, j) AND the 8 augmented rows.)
+struct RowMap {
+    int rowA, split, rowB;
+    __device__ __forceinline__ int operator()(int r) const { return r < split ? rowA + r : rowB + (r - split); }
 };
 
-template <int BM, int THREADS>
-__device__ __forceinline__ void gemm_load_stage(double* As, double* Bs, const double* __restrict__ Ag,
-                                                const double* __restrict__ Bg, int ld, int k0, int a_rows_valid) {
-    // A: BM rows x 8 chunks of 16 B ; B: 64 rows x 8 chunks
-    for (int i = threadIdx.x; i < BM * 8; i += THREADS) {
+// a_rows: rows of A actually loaded (multiple of 8, <= BM)
+__device__ __forceinline__ void gemm_load_stage(double* As, double* Bs, const double* __restrict__ M,
+                                                const RowMap& rm, int brow0, int ld, int k0, int a_rows) {
+    for (int i = threadIdx.x; i < a_rows * 8; i += THREADS) {
         const int r = i >> 3, ch = i & 7;
-        const int rs = (r < a_rows_valid) ? r : (a_rows_valid - 1);  // clamp: never read past the matrix
-        cp_async16(As + r * SLD + ch * 2, Ag + (size_t)rs * ld + k0 + ch * 2);
+        cp_async16(As + r * SLD + ch * 2, M + (size_t)rm(r) * ld + k0 + ch * 2);
     }
     for (int i = threadIdx.x; i < PK_TILE * 8; i += THREADS) {
         const int r = i >> 3, ch = i & 7;
-        cp_async16(Bs + r * SLD + ch * 2, Bg + (size_t)r * ld + k0 + ch * 2);
+        cp_async16(Bs + r * SLD + ch * 2, M + (size_t)(brow0 + r) * ld + k0 + ch * 2);
     }
 }
 
-// acc[mi][ni][2]; warp (wm, wn) covers rows wm*32.., cols wn*32..
-template <int BM, int THREADS>
-__device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], double* pipe, const double* __restrict__ Ag,
-                                              const double* __restrict__ Bg, int ld, int K, int a_rows_valid,
-                                              int wm, int wn, int mi_count) {
-    using S = GemmSmem<BM, THREADS>;
+__device__ __forceinline__ double neg(double x) {
+    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));  // sign flip on the ALU pipe
+}
+
+// acc[mi][ni][2] -= A(rows x K) * B(64 x K)^T ; warp (wm, wn) covers rows wm*32.., cols wn*32..
+__device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], double* pipe, const double* __restrict__ M,
+                                              const RowMap& rm, int brow0, int ld, int K, int a_rows, int wm, int wn,
+                                              int mi_count) {
     double* As = pipe;
-    double* Bs = pipe + STAGES * S::A_STAGE;
+    double* Bs = pipe + STAGES * A_STAGE;
     const int lane = threadIdx.x & 31;
     const int nk = K / KC;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) gemm_load_stage<BM, THREADS>(As + s * S::A_STAGE, Bs + s * S::B_STAGE, Ag, Bg, ld, s * KC, a_rows_valid);
+        if (s < nk) gemm_load_stage(As + s * A_STAGE, Bs + s * B_STAGE, M, rm, brow0, ld, s * KC, a_rows);
         cp_async_commit();
     }
     const int fr = lane >> 2, fc = lane & 3;
@@ -157,23 +170,25 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], double* pi
         const int nxt = it + STAGES - 1;
         if (nxt < nk) {
             const int s = nxt % STAGES;
-            gemm_load_stage<BM, THREADS>(As + s * S::A_STAGE, Bs + s * S::B_STAGE, Ag, Bg, ld, nxt * KC, a_rows_valid);
+            gemm_load_stage(As + s * A_STAGE, Bs + s * B_STAGE, M, rm, brow0, ld, nxt * KC, a_rows);
         }
         cp_async_commit();
-        const double* a_s = As + (it % STAGES) * S::A_STAGE + (wm * 32 + fr) * SLD + fc;
-        const double* b_s = Bs + (it % STAGES) * S::B_STAGE + (wn * 32 + fr) * SLD + fc;
+        const double* a_s = As + (it % STAGES) * A_STAGE + (wm * 32 + fr) * SLD + fc;
+        const double* b_s = Bs + (it % STAGES) * B_STAGE + (wn * 32 + fr) * SLD + fc;
+        if (mi_count > 0) {
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-            double a[4], b[4];
+            for (int kk = 0; kk < KC; kk += 4) {
+                double a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = (mi < mi_count) ? a_s[mi * 8 * SLD + kk] : 0.0;
+                for (int mi = 0; mi < 4; ++mi) a[mi] = (mi < mi_count) ? neg(a_s[mi * 8 * SLD + kk]) : 0.0;
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = b_s[ni * 8 * SLD + kk];
+                for (int ni = 0; ni < 4; ++ni) b[ni] = b_s[ni * 8 * SLD + kk];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                if (mi < mi_count) {
+                for (int mi = 0; mi < 4; ++mi) {
+                    if (mi < mi_count) {
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    }
                 }
             }
         }
@@ -182,130 +197,99 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], double* pi
     __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Diagonal tile: T = Psi_jj - L[j,0:j] L[j,0:j]^T, then unblocked Cholesky in shared memory.
-// grid = candidates, 128 threads (2x2 warps of 32x32).
-// ------------------------------------------------------------------------------------------------
-constexpr int DIAG_THREADS = 128;
-constexpr int TLD = PK_TILE + 1;  // 65: odd stride -> conflict-free row-per-thread walks
-
-__global__ void __launch_bounds__(DIAG_THREADS)
-chol_diag_kernel(int j, int n, int ld, size_t elems, double piv_tol, double* __restrict__ ws,
-                 int32_t* __restrict__ info) {
-    extern __shared__ __align__(16) double smem[];
-    const int cand = blockIdx.x;
-    if (info[cand] != 0) return;
-    double* M = ws + (size_t)cand * elems;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;
-    double acc[4][4][2];
+// acc = M[rows, col0 .. col0+64) in DMMA accumulator layout (issued before the main loop: the loads
+// overlap the pipeline prologue)
+__device__ __forceinline__ void load_acc(double (&acc)[4][4][2], const double* __restrict__ M, const RowMap& rm, int ld,
+                                         int col0, int wm, int wn, int mi_count) {
+    const int lane = threadIdx.x & 31;
+    const int fr = lane >> 2, fc2 = (lane & 3) * 2;
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 4; ++mi) {
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    const double* Ag = M + (size_t)(j * PK_TILE) * ld;
-    gemm_mainloop<PK_TILE, DIAG_THREADS>(acc, smem, Ag, Ag, ld, j * PK_TILE, PK_TILE, wm, wn, 4);
-
-    double* T = smem;  // aliases the (drained) pipeline buffers
-    {
-        const int fr = lane >> 2, fc2 = (lane & 3) * 2;
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
+        for (int ni = 0; ni < 4; ++ni) {
+            if (mi < mi_count) {
                 const int r = wm * 32 + mi * 8 + fr, c = wn * 32 + ni * 8 + fc2;
-                const double2 v = *reinterpret_cast<const double2*>(M + (size_t)(j * PK_TILE + r) * ld + j * PK_TILE + c);
-                T[r * TLD + c] = v.x - acc[mi][ni][0];
-                T[r * TLD + c + 1] = v.y - acc[mi][ni][1];
+                const double2 v = *reinterpret_cast<const double2*>(M + (size_t)rm(r) * ld + col0 + c);
+                acc[mi][ni][0] = v.x;
+                acc[mi][ni][1] = v.y;
+            } else {
+                acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             }
-    }
-    // In-tile unblocked Cholesky.  Off-diagonal entries are updated by sequential FMAs; every pivot is
-    // formed as t_cc - (sum_k l_ck^2) with the sum kept in a register of the thread that owns row c
-    // (dot-product form of dpotf2, see pk_small.cu).
-    const int r = tid & 63, h = tid >> 6;
-    double dsum = 0.0;                   // meaningful in threads with h == 0
-    // original diagonal entry Psi_rr of this thread's row (scale of the pivot threshold)
-    const double diag0 = M[(size_t)(j * PK_TILE + r) * ld + j * PK_TILE + r];
-    double* piv_s = smem + PK_TILE * TLD;  // 1 double: pivot broadcast
-    for (int c = 0; c < PK_TILE; ++c) {
-        __syncthreads();
-        if (tid == c) {
-            piv_s[0] = T[c * TLD + c] - dsum;
-            piv_s[1] = piv_tol * diag0;
         }
-        __syncthreads();
-        const double piv = piv_s[0];
-        if (!(piv > piv_s[1])) {  // dpotrf convention: index of the first non-positive (or NaN) pivot
-            if (tid == 0) info[cand] = j * PK_TILE + c + 1;
-            return;
-        }
-        const double l = sqrt(piv);
-        const double rinv = 1.0 / l;
-        if (h == 0 && r > c) T[r * TLD + c] *= rinv;
-        __syncthreads();
-        if (tid == 0) T[c * TLD + c] = l;
-        if (r > c) {
-            const double lrc = T[r * TLD + c];
-            for (int cc = c + 1 + h; cc < r; cc += 2) T[r * TLD + cc] = fma(-lrc, T[cc * TLD + c], T[r * TLD + cc]);
-            if (h == 0) dsum = fma(lrc, lrc, dsum);
-        }
-    }
-    __syncthreads();
-    // write L_jj (lower) and zeros above the diagonal
-    for (int i = tid; i < PK_TILE * PK_TILE; i += DIAG_THREADS) {
-        const int rr = i >> 6, cc = i & 63;
-        M[(size_t)(j * PK_TILE + rr) * ld + j * PK_TILE + cc] = (cc <= rr) ? T[rr * TLD + cc] : 0.0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Rows below the diagonal tile of block column j: T = M[i,j] - L[i,0:j] L[j,0:j]^T, L[i,j] = T L_jj^-T.
-// grid = (row blocks of 128, candidates), 256 threads (4x2 warps of 32x32).
+// In-tile unblocked Cholesky of the 64x64 tile T (smem, stride TLD), 256 threads, ONE barrier per
+// column.  Off-diagonal entries are updated by sequential FMAs in k order; every pivot is formed as
+// t_cc - (sum_k l_ck^2) with the sum accumulated separately (dsum) and subtracted once -- the
+// dot-product form of LAPACK's dpotf2 (see pk_small.cu).  The scaled column is written to Lout
+// (smem, stride LLD) while T keeps the unscaled values, so no second barrier is needed.
+// Returns 0 or the (1-based, tile-local) index of the first pivot <= piv_tol * diag0[c].
 // ------------------------------------------------------------------------------------------------
-constexpr int OFF_BM = 128;
-constexpr int OFF_THREADS = 256;
-constexpr int LLD = PK_TILE + 2;  // 66: L_jj rows 16-byte aligned for broadcast LDS.128
-
-__global__ void __launch_bounds__(OFF_THREADS, 2)
-chol_off_kernel(int j, int rows, int ld, size_t elems, double* __restrict__ ws, const int32_t* __restrict__ info) {
-    extern __shared__ __align__(16) double smem[];
-    const int cand = blockIdx.y;
-    if (info[cand] != 0) return;
-    double* M = ws + (size_t)cand * elems;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;
-    const int row0 = (j + 1) * PK_TILE + blockIdx.x * OFF_BM;
-    const int rows_valid = min(OFF_BM, rows - row0);            // multiple of 8, >= 8
-    const int mi_count = max(0, min(4, (rows_valid - wm * 32) / 8));
-
-    double acc[4][4][2];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    const double* Ag = M + (size_t)row0 * ld;
-    const double* Bg = M + (size_t)(j * PK_TILE) * ld;
-    gemm_mainloop<OFF_BM, OFF_THREADS>(acc, smem, Ag, Bg, ld, j * PK_TILE, rows_valid, wm, wn, mi_count);
-
-    double* T = smem;                      // OFF_BM x TLD
-    double* Ljj = smem + OFF_BM * TLD;     // 64 x LLD
-    double* rdiag = Ljj + PK_TILE * LLD;   // 64
-    {
-        const int fr = lane >> 2, fc2 = (lane & 3) * 2;
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            if (mi < mi_count) {
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    const int r = wm * 32 + mi * 8 + fr, c = wn * 32 + ni * 8 + fc2;
-                    const double2 v = *reinterpret_cast<const double2*>(M + (size_t)(row0 + r) * ld + j * PK_TILE + c);
-                    T[r * TLD + c] = v.x - acc[mi][ni][0];
-                    T[r * TLD + c + 1] = v.y - acc[mi][ni][1];
-                }
+__device__ __forceinline__ int potf2_tile(double* T, double* Lout, double* dsum, const double* diag0,
+                                          double piv_tol) {
+    const int tid = threadIdx.x;
+    const int r = tid & 63, h = tid >> 6;  // 4 threads per row
+    if (tid < PK_TILE) dsum[tid] = 0.0;
+    for (int c = 0; c < PK_TILE; ++c) {
+        __syncthreads();
+        const double piv = T[c * TLD + c] - dsum[c];
+        if (!(piv > piv_tol * diag0[c])) return c + 1;  // uniform: every thread reads the same values
+        // 1/sqrt(piv) straight from the reciprocal-square-root unit (+ Newton), l = piv * rinv: halves the
+        // serial sqrt -> divide latency chain of the 64 dependent pivot steps (<= 2 ulp on l and rinv)
+        const double rinv = rsqrt(piv);
+        const double l = piv * rinv;
+        if (r > c) {
+            const double lrc = T[r * TLD + c] * rinv;
+            int cc = c + 1 + h;
+            for (; cc + 12 < r; cc += 16) {  // 4 independent updates in flight
+                const double u0 = T[cc * TLD + c], u1 = T[(cc + 4) * TLD + c], u2 = T[(cc + 8) * TLD + c],
+                             u3 = T[(cc + 12) * TLD + c];
+                const double v0 = T[r * TLD + cc], v1 = T[r * TLD + cc + 4], v2 = T[r * TLD + cc + 8],
+                             v3 = T[r * TLD + cc + 12];
+                T[r * TLD + cc] = fma(-lrc, u0 * rinv, v0);
+                T[r * TLD + cc + 4] = fma(-lrc, u1 * rinv, v1);
+                T[r * TLD + cc + 8] = fma(-lrc, u2 * rinv, v2);
+                T[r * TLD + cc + 12] = fma(-lrc, u3 * rinv, v3);
             }
+            for (; cc < r; cc += 4) T[r * TLD + cc] = fma(-lrc, T[cc * TLD + c] * rinv, T[r * TLD + cc]);
+            if (h == 0) {
+                Lout[r * LLD + c] = lrc;
+                dsum[r] = fma(lrc, lrc, dsum[r]);
+            }
+        } else if (h == 0) {
+            Lout[r * LLD + c] = (r == c) ? l : 0.0;
         }
     }
-    for (int i = tid; i < PK_TILE * (PK_TILE / 2); i += OFF_THREADS) {
+    __syncthreads();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Panel rows of block column j:  T = M[rows, j] - L[rows, 0:j] L[j, 0:j]^T  (DMMA main loop, T stays
+// in the accumulator registers), then X L_jj^T = T solved IN REGISTERS:
+//   for each 8-column block cb: the warps that own those columns run the 8-step substitution inside
+//   each thread quad (the four lanes of a quad hold the 8 columns of a row; the solved value is
+//   broadcast with a quad shuffle), publish the solved block to shared memory, and after one barrier
+//   every warp folds it into its remaining columns with two DMMA k-steps per 8x8 tile.
+// 8 barriers, ~230 FP64 instructions per thread, 896 DMMAs per CTA -- instead of a 2016-FMA
+// row-per-thread substitution fed from shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void panel_rows(double* smem, double* __restrict__ M, int ld, int j, const RowMap& rm,
+                                           int rows_valid) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int mi_count = max(0, min(4, (rows_valid - wm * 32) / 8));
+    const int fr = lane >> 2, q = lane & 3;
+    double acc[4][4][2];
+    load_acc(acc, M, rm, ld, j * PK_TILE, wm, wn, mi_count);
+    gemm_mainloop(acc, smem, M, rm, j * PK_TILE, ld, j * PK_TILE, rows_valid, wm, wn, mi_count);
+
+    double* Ljj = smem;                        // 64 x LLD
+    double* rdiag = Ljj + PK_TILE * LLD;       // 64
+    double* Xs = rdiag + PK_TILE;              // 2 x BM x XLD
+    for (int i = tid; i < PK_TILE * (PK_TILE / 2); i += THREADS) {
         const int rr = i >> 5, c2 = (i & 31) * 2;
         const double2 v = *reinterpret_cast<const double2*>(M + (size_t)(j * PK_TILE + rr) * ld + j * PK_TILE + c2);
         *reinterpret_cast<double2*>(Ljj + rr * LLD + c2) = v;
@@ -314,46 +298,195 @@ chol_off_kernel(int j, int rows, int ld, size_t elems, double* __restrict__ ws, 
     }
     __syncthreads();
 
-    // forward substitution X L_jj^T = T, one thread per row, 8-column register blocks
-    if (tid < rows_valid) {
-        double* trow = T + tid * TLD;
 #pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
-            double x[8];
+    for (int cb = 0; cb < 8; ++cb) {
+        double* Xb = Xs + (cb & 1) * BM * XLD;
+        if (wn == (cb >> 2)) {
+            // move the owned 8-column block into a small register array (keeps the loop rolled: the
+            // accumulator file is only ever indexed with compile-time constants)
+            double t0[4], t1[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = trow[cb * 8 + i];
-#pragma unroll 1
-            for (int pb = 0; pb < cb; ++pb) {
-                double xp[8];
+            for (int mi = 0; mi < 4; ++mi) {
+                switch (cb & 3) {
+                    case 0: t0[mi] = acc[mi][0][0]; t1[mi] = acc[mi][0][1]; break;
+                    case 1: t0[mi] = acc[mi][1][0]; t1[mi] = acc[mi][1][1]; break;
+                    case 2: t0[mi] = acc[mi][2][0]; t1[mi] = acc[mi][2][1]; break;
+                    default: t0[mi] = acc[mi][3][0]; t1[mi] = acc[mi][3][1]; break;
+                }
+            }
+            const double* Lb = Ljj + (cb * 8) * LLD + cb * 8;   // diagonal 8x8 block of L_jj
+            // 8-step substitution inside the quad; the 4 row groups (mi) are independent chains
 #pragma unroll
-                for (int q = 0; q < 8; ++q) xp[q] = trow[pb * 8 + q];
+            for (int c = 0; c < 8; ++c) {
+                const int qo = c >> 1;
+                const double rd = rdiag[cb * 8 + c];
+                const double l0 = Lb[(2 * q) * LLD + c];      // L[col 2q  ][c]
+                const double l1 = Lb[(2 * q + 1) * LLD + c];  // L[col 2q+1][c]
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const double2* lrow = reinterpret_cast<const double2*>(Ljj + (cb * 8 + i) * LLD + pb * 8);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const double2 l2 = lrow[q];
-                        x[i] = fma(-xp[2 * q], l2.x, x[i]);
-                        x[i] = fma(-xp[2 * q + 1], l2.y, x[i]);
+                for (int mi = 0; mi < 4; ++mi) {
+                    double xc = ((c & 1) ? t1[mi] : t0[mi]) * rd;
+                    xc = __shfl_sync(0xffffffffu, xc, (lane & ~3) | qo);
+                    if (q == qo) {
+                        if (c & 1) t1[mi] = xc; else t0[mi] = xc;
                     }
+                    if (2 * q > c) t0[mi] = fma(-xc, l0, t0[mi]);
+                    if (2 * q + 1 > c) t1[mi] = fma(-xc, l1, t1[mi]);
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const double* lrow = Ljj + (cb * 8 + i) * LLD + cb * 8;
+            for (int mi = 0; mi < 4; ++mi) {
+                switch (cb & 3) {
+                    case 0: acc[mi][0][0] = t0[mi]; acc[mi][0][1] = t1[mi]; break;
+                    case 1: acc[mi][1][0] = t0[mi]; acc[mi][1][1] = t1[mi]; break;
+                    case 2: acc[mi][2][0] = t0[mi]; acc[mi][2][1] = t1[mi]; break;
+                    default: acc[mi][3][0] = t0[mi]; acc[mi][3][1] = t1[mi]; break;
+                }
+                if (mi < mi_count) {
+                    const int r = wm * 32 + mi * 8 + fr;
+                    Xb[r * XLD + 2 * q] = t0[mi];
+                    Xb[r * XLD + 2 * q + 1] = t1[mi];
+                }
+            }
+        }
+        if (cb == 7) break;
+        __syncthreads();
+        // fold the solved block into the remaining columns: acc[:, gb] -= X_cb * L[gb, cb]^T
+        if (mi_count > 0) {
+            double a[4][2];
 #pragma unroll
-                for (int q = 0; q < i; ++q) x[i] = fma(-x[q], lrow[q], x[i]);
-                x[i] *= rdiag[cb * 8 + i];
+            for (int mi = 0; mi < 4; ++mi) {
+                a[mi][0] = neg(Xb[(wm * 32 + mi * 8 + fr) * XLD + q]);
+                a[mi][1] = neg(Xb[(wm * 32 + mi * 8 + fr) * XLD + 4 + q]);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) trow[cb * 8 + i] = x[i];
+            for (int ni = 0; ni < 4; ++ni) {
+                const int gb = wn * 4 + ni;
+                if (gb > cb) {
+                    const double b0 = Ljj[(gb * 8 + fr) * LLD + cb * 8 + q];
+                    const double b1 = Ljj[(gb * 8 + fr) * LLD + cb * 8 + 4 + q];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        if (mi < mi_count) {
+                            dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi][0], b0);
+                            dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi][1], b1);
+                        }
+                    }
+                }
+            }
         }
     }
-    __syncthreads();
-    for (int i = tid; i < rows_valid * PK_TILE; i += OFF_THREADS) {
-        const int rr = i >> 6, cc = i & 63;
-        M[(size_t)(row0 + rr) * ld + j * PK_TILE + cc] = T[rr * TLD + cc];
+    // write the solved panel back (accumulator layout -> 16-byte stores, 64 B contiguous per quad)
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        if (mi < mi_count) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int r = wm * 32 + mi * 8 + fr, c = wn * 32 + ni * 8 + 2 * q;
+                *reinterpret_cast<double2*>(M + (size_t)rm(r) * ld + j * PK_TILE + c) =
+                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
+        }
     }
+    __syncthreads();  // global writes of this CTA are visible to all of its threads from here on
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal tile jd: T = Psi[jd,jd] - L[jd, 0:jd] L[jd, 0:jd]^T, unblocked Cholesky, write L[jd,jd].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void diag_tile(double* smem, double* __restrict__ M, int ld, int jd, double piv_tol,
+                                          int32_t* __restrict__ info, int cand) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int mi_count = (wm < 2) ? 4 : 0;  // 64 rows: two of the four M-warps hold data
+    const RowMap rm{jd * PK_TILE, BM, 0};
+    double acc[4][4][2];
+    load_acc(acc, M, rm, ld, jd * PK_TILE, wm, wn, mi_count);
+    gemm_mainloop(acc, smem, M, rm, jd * PK_TILE, ld, jd * PK_TILE, PK_TILE, wm, wn, mi_count);
+    double* T = smem;                       // 64 x TLD
+    double* Lout = T + PK_TILE * TLD;       // 64 x LLD
+    double* dsum = Lout + PK_TILE * LLD;    // 64
+    double* diag0 = dsum + PK_TILE;         // 64
+    {
+        const int fr = lane >> 2, fc2 = (lane & 3) * 2;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+                if (mi < mi_count) {
+                    const int r = wm * 32 + mi * 8 + fr, c = wn * 32 + ni * 8 + fc2;
+                    T[r * TLD + c] = acc[mi][ni][0];
+                    T[r * TLD + c + 1] = acc[mi][ni][1];
+                }
+    }
+    if (tid < PK_TILE) diag0[tid] = M[(size_t)(jd * PK_TILE + tid) * ld + jd * PK_TILE + tid];
+    __syncthreads();
+    const int bad = potf2_tile(T, Lout, dsum, diag0, piv_tol);
+    if (bad) {
+        if (tid == 0) info[cand] = jd * PK_TILE + bad;  // dpotrf convention: order of the failing minor
+        return;
+    }
+    for (int i = tid; i < PK_TILE * PK_TILE; i += THREADS) {
+        const int rr = i >> 6, cc = i & 63;
+        M[(size_t)(jd * PK_TILE + rr) * ld + jd * PK_TILE + cc] = (cc <= rr) ? Lout[rr * LLD + cc] : 0.0;
+    }
+}
+
+// first diagonal tile (j = 0): grid = candidates
+__global__ void __launch_bounds__(THREADS, 2)
+chol_first_kernel(int ld, size_t elems, double piv_tol, double* __restrict__ ws, int32_t* __restrict__ info) {
+    extern __shared__ __align__(16) double smem[];
+    const int cand = blockIdx.x;
+    if (info[cand] != 0) return;
+    diag_tile(smem, ws + (size_t)cand * elems, ld, 0, piv_tol, info, cand);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One launch per block column j.  grid = (1 + row blocks, candidates):
+//   blockIdx.x == 0: LOOK-AHEAD role -- the 64 rows of tile (j+1, j) together with the 8 augmented
+//       rows (1^T, y^T), then immediately the diagonal tile (j+1, j+1), so the latency-bound
+//       unblocked factorisation overlaps the DMMA-bound panel CTAs of the same launch (for the last
+//       block column only the augmented rows remain);
+//   blockIdx.x >= 1: PANEL role -- 128-row blocks of rows [(j+2)*64, np) and, for pk_fit, of the
+//       inverse rows [np+8, rows).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 2)
+chol_step_kernel(int j, int nt, int rows, int ld, size_t elems, double piv_tol, double* __restrict__ ws,
+                 int32_t* __restrict__ info) {
+    extern __shared__ __align__(16) double smem[];
+    const int cand = blockIdx.y;
+    if (info[cand] != 0) return;
+    double* M = ws + (size_t)cand * elems;
+    const int np = nt * PK_TILE;
+    const bool has_next = (j + 1 < nt);
+    RowMap rm;
+    int rows_valid;
+    bool lookahead = false;
+    if (blockIdx.x == 0) {
+        if (has_next) {
+            rm = RowMap{(j + 1) * PK_TILE, PK_TILE, np};
+            rows_valid = PK_TILE + PK_AUG_ROWS;
+            lookahead = true;
+        } else {
+            rm = RowMap{np, BM, 0};
+            rows_valid = PK_AUG_ROWS;
+        }
+    } else {
+        const int blk = (int)blockIdx.x - 1;
+        const int first = (j + 2) * PK_TILE;                       // rows below the look-ahead tile
+        const int nblk1 = (np > first) ? (np - first + BM - 1) / BM : 0;
+        int row0;
+        if (blk < nblk1) {
+            row0 = first + blk * BM;
+            rows_valid = min(BM, np - row0);
+        } else {
+            row0 = np + PK_AUG_ROWS + (blk - nblk1) * BM;          // inverse rows (pk_fit)
+            rows_valid = min(BM, rows - row0);
+        }
+        if (rows_valid <= 0) return;
+        rm = RowMap{row0, BM, 0};
+    }
+    panel_rows(smem, M, ld, j, rm, rows_valid);
+    if (lookahead) diag_tile(smem, M, ld, j + 1, piv_tol, info, cand);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -420,26 +553,25 @@ cudaError_t launch_aug_init(pk_handle* h, const TiledShape& s, int C, double* ws
 
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     const int nt = s.np / PK_TILE;
-    const size_t diag_smem = sizeof(double) * (size_t)max(GemmSmem<PK_TILE, DIAG_THREADS>::PIPE_DOUBLES, PK_TILE * TLD + 8);
-    const size_t off_smem = sizeof(double) * (size_t)max(GemmSmem<OFF_BM, OFF_THREADS>::PIPE_DOUBLES,
-                                                          OFF_BM * TLD + PK_TILE * LLD + PK_TILE);
+    const size_t smem = sizeof(double) * (size_t)SMEM_DOUBLES;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem);
+        cudaError_t e = cudaFuncSetAttribute(chol_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(chol_off_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off_smem);
+        e = cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
+    chol_first_kernel<<<C, THREADS, smem, h->stream>>>(s.ld, s.elems(), h->pivot_tol, ws, info);
+    h->launches++;
     for (int j = 0; j < nt; ++j) {
-        chol_diag_kernel<<<C, DIAG_THREADS, diag_smem, h->stream>>>(j, s.n, s.ld, s.elems(), h->pivot_tol, ws, info);
+        const int first = (j + 2) * PK_TILE;
+        const int nblk1 = (s.np > first) ? (s.np - first + BM - 1) / BM : 0;
+        const int inv_rows = s.rows - (s.np + PK_AUG_ROWS);
+        const int nblk2 = (inv_rows + BM - 1) / BM;
+        dim3 grid(1 + nblk1 + nblk2, C);
+        chol_step_kernel<<<grid, THREADS, smem, h->stream>>>(j, nt, s.rows, s.ld, s.elems(), h->pivot_tol, ws, info);
         h->launches++;
-        const int rows_below = s.rows - (j + 1) * PK_TILE;
-        if (rows_below > 0) {
-            dim3 grid((rows_below + OFF_BM - 1) / OFF_BM, C);
-            chol_off_kernel<<<grid, OFF_THREADS, off_smem, h->stream>>>(j, s.rows, s.ld, s.elems(), ws, info);
-            h->launches++;
-        }
     }
     return cudaGetLastError();
 }
