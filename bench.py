@@ -172,6 +172,7 @@ def run_ours(args, rank, world, local_rank):
     X, y = make_samples(N_SAMPLES, K_DIMS)
     model = kriging(X, y, device=local_rank)   # normalises (krige.py:117-133) and uploads X, y
     h = model._pk_handle()
+    h.set_cholesky_variant(args.chol_variant)
     stream = torch.cuda.ExternalStream(h.stream, device=dev)
     n_steps = args.warmup + args.steps
     C, k = POP, K_DIMS
@@ -301,6 +302,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chol-variant", type=int, default=0, help="0 auto, 1 per-block-column launches, 2 persistent CTA")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -119,6 +119,12 @@ int64_t pk_launch_count(const pk_handle *h);
  * (DESIGN.md "failure parity"). */
 int pk_set_pivot_tolerance(pk_handle *h, double tol);
 
+/* Tuning / test knob for the blocked Cholesky behind pk_nll_batch and pk_fit (np.linalg.cholesky,
+ * matrixops.py:31,41): 0 = automatic (default), 1 = one launch per 64-wide block column with the row
+ * blocks of every candidate spread over the grid (few candidates, large n), 2 = one persistent CTA
+ * per candidate (populations with at least as many candidates as SMs). */
+int pk_set_cholesky_variant(pk_handle *h, int variant);
+
 /* Phase timing for roofline accounting (bench.py): when enabled, CUDA events are recorded on the
  * handle's stream around the phases of every pk_nll_batch / pk_predict_batch call.
  * pk_phase_times() synchronises, ADDS the elapsed milliseconds since the last call into

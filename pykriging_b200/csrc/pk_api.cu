@@ -137,6 +137,7 @@ int pk_create(pk_handle** out, int device) {
         return 1;
     }
     e = cudaMalloc((void**)&h->d_hp, sizeof(double) * 2 * PK_MAX_K);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_queue, sizeof(unsigned int));
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);
@@ -152,7 +153,7 @@ int pk_destroy(pk_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
-                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp};
+                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -175,6 +176,12 @@ int64_t pk_launch_count(const pk_handle* h) { return h ? h->launches : 0; }
 int pk_set_pivot_tolerance(pk_handle* h, double tol) {
     if (!h || !(tol >= 0.0)) return 1;
     h->pivot_tol = tol;
+    return 0;
+}
+
+int pk_set_cholesky_variant(pk_handle* h, int variant) {
+    if (!h || variant < 0 || variant > 2) return 1;
+    h->chol_variant = variant;
     return 0;
 }
 

@@ -20,6 +20,8 @@ struct pk_handle {
     std::vector<int> ev_phase;          // phase id of every event pair
     size_t ev_used = 0;
     double pivot_tol = 2.0 * PK_EPS_DIAG;  // relative pivot threshold, 2 ulps (see pk_set_pivot_tolerance)
+    int chol_variant = 0;                  // 0 auto, 1 one launch per block column, 2 persistent CTA per candidate
+    unsigned int* d_queue = nullptr;       // candidate queue of the persistent Cholesky kernel
 
     // model data (pk_set_data)
     int n = 0, k = 0;
@@ -91,6 +93,8 @@ cudaError_t launch_small_nll(pk_handle* h, int C, const double* theta, const dou
 cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
                              const double* lambda, int mode, double* ws, int32_t* info);
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
+cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
+cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,
                                 int out_stride, int32_t* info);
 cudaError_t launch_extract_psi(pk_handle* h, const TiledShape& s, const double* M, double* out, int C);

@@ -105,6 +105,32 @@ __device__ __forceinline__ void log2_split(double d, double& L, float& res) {
     res = (float)(ll - (L - lh));             // Fast2Sum remainder (|lh| >= |ll| or lh == 0)
 }
 
+// ---- lean 2^x for the candidate loop ---------------------------------------------------------------
+// Same arithmetic as exp2_table, written so that the hot loop carries no branches, no 64-bit immediates
+// (the polynomial lives in the constant bank and is read as a DFMA operand) and no address
+// re-computation: `tabp` is the byte address of this lane's bank copy of the 2^(j/64) table.  The
+// result is scaled by adding the clamped binary exponent to the high word, so anything below
+// 2^-1022 comes out as ~1e-308 instead of 0 (it is then multiplied by theta <= 100 and added to a
+// sum that is >= 0: indistinguishable from pow(0, p) = 0 in every Psi entry) .
+__constant__ double c_e2[5] = {0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58fp-3, 0x1.c6b08d704a0c0p-5,
+                               0x1.3b2ab6fba4e77p-7, 0x1.5d87fe78a6731p-10};
+
+__device__ __forceinline__ double exp2_lean(double s, double e, const char* __restrict__ tabp) {
+    const double kd = s + MAGIC64;
+    const int ki = __double2loint(kd);
+    const double kf = kd - MAGIC64;
+    const double r = (s - kf) + e;
+    double q = fma(r, c_e2[4], c_e2[3]);
+    q = fma(r, q, c_e2[2]);
+    q = fma(r, q, c_e2[1]);
+    q = fma(r, q, c_e2[0]);
+    q = q * r;
+    const double T = *reinterpret_cast<const double*>(tabp + ((ki & 63) << 7));
+    const double v = fma(T, q, T);
+    const int n = min(max(ki >> 6, -1022), 1023);
+    return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
+}
+
 constexpr int PSI_THREADS = 256;
 constexpr int PSI_GROUP = 32;  // candidates per CTA
 
@@ -118,6 +144,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
     __shared__ double tab[64 * 16];
     __shared__ double Xr[RB * K], Xc[PK_TILE * K];
     __shared__ double th[PSI_GROUP * K], pp[PSI_GROUP * K], dg[PSI_GROUP];
+    __shared__ int spec[PSI_GROUP];  // candidate has an exponent that is exactly 1 or 2 (exact d / d*d path)
     const int tid = threadIdx.x, bank = tid & 15;
     // block -> (lower tile, row block)
     const int t = blockIdx.x / SPT, sb = blockIdx.x % SPT;
@@ -142,8 +169,17 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
         th[i] = theta[(size_t)g0 * K + i];
         pp[i] = p[(size_t)g0 * K + i];
     }
-    if (tid < gn) dg[tid] = 1.0 + (mode == PK_MODE_REGRESSION ? lambda[g0 + tid] : PK_EPS_DIAG);
+    if (tid < gn) {
+        dg[tid] = 1.0 + (mode == PK_MODE_REGRESSION ? lambda[g0 + tid] : PK_EPS_DIAG);
+        int sp = 0;
+        for (int d = 0; d < K; ++d) {
+            const double pd = p[(size_t)(g0 + tid) * K + d];
+            sp |= (pd == 1.0 || pd == 2.0) ? 1 : 0;
+        }
+        spec[tid] = sp;
+    }
     __syncthreads();
+    const char* tabp = reinterpret_cast<const char*>(tab + bank);
 
     const int lr = tid / (PK_TILE / PPT);            // local row
     const int lc = (tid % (PK_TILE / PPT)) * PPT;    // first local column
@@ -173,7 +209,33 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
         for (int q = 0; q < PPT; ++q) {
             const int gc = c0 + lc + q;
             double v;
-            if (live[q]) {
+            if (live[q] && !spec[g]) {
+                // generic exponents: k table-driven 2^x, theta folded in with an FMA, NumPy's summation tree
+                auto w = [&](int d) {
+                    const double pd = ppg[d];
+                    const double s = pd * lh[q][d];
+                    const double e = fma(pd, (double)ll[q][d], fma(pd, lh[q][d], -s));
+                    return exp2_lean(s, e, tabp);
+                };
+                double S;
+                if (K < 8) {
+                    S = 0.0;
+#pragma unroll
+                    for (int d = 0; d < K; ++d) S = fma(thg[d], w(d), S);
+                } else {
+                    double r[8];
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) r[d] = thg[d] * w(d);
+#pragma unroll
+                    for (int d = 8; d < K - (K % 8); ++d) r[d & 7] = fma(thg[d], w(d), r[d & 7]);
+                    S = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+                    for (int d = K - (K % 8); d < K; ++d) S = fma(thg[d], w(d), S);
+                }
+                v = expneg_table(S, tab, bank);
+            } else if (live[q]) {
+                // a candidate with an exponent that is exactly 1 or 2 (bounder-clipped PSO particles,
+                // krige.py:383): np.power returns d and d*d exactly there, so do the same
                 double term[K];
 #pragma unroll
                 for (int d = 0; d < K; ++d) {

@@ -551,7 +551,7 @@ cudaError_t launch_aug_init(pk_handle* h, const TiledShape& s, int C, double* ws
     return cudaGetLastError();
 }
 
-cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
+cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     const int nt = s.np / PK_TILE;
     const size_t smem = sizeof(double) * (size_t)SMEM_DOUBLES;
     static bool attr_done = false;
@@ -574,6 +574,15 @@ cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws
         h->launches++;
     }
     return cudaGetLastError();
+}
+
+// Variant choice: the persistent kernel keeps one CTA per candidate busy for the whole factorisation,
+// so it wants at least ~2/3 of the SMs' worth of candidates; below that (pk_fit, n = 4096 with a
+// handful of candidates) the per-block-column launches expose the parallelism inside a matrix.
+cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
+    int v = h->chol_variant;
+    if (v == 0) v = (C >= (2 * h->sm_count) / 3) ? 2 : 1;
+    return (v == 2) ? launch_cholesky_cta(h, s, C, ws, info) : launch_cholesky_steps(h, s, C, ws, info);
 }
 
 cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,

@@ -154,6 +154,74 @@ def test_tiled_path_matches_oracle_on_seeded_inputs(handle, n, k, seed):
         assert rel_err(out["sigma2"][i], s2) < tol, (i, cond)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("n,k,seed", [(130, 4, 3), (333, 7, 5), (640, 10, 6), (1024, 10, 7)])
+def test_cholesky_variants_match_oracle(handle, variant, n, k, seed):
+    """Both blocked-Cholesky variants (per-block-column launches / persistent CTA per candidate) against
+    the oracle, including candidates whose Psi is not positive definite and the info convention."""
+    X = onp.rlh(n, k, seed)
+    y = onp.f_stybtang_norm(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    cands = np.concatenate([onp.candidates_uniform(4, k, seed + 10), onp.candidates_loguniform(8, k, seed + 20, lo=-3)])
+    cands[2, k:] = 2.0
+    cands[5, :k] = 1e-5   # numerically singular with p = 2: must fail
+    cands[5, k:] = 2.0
+    handle.set_cholesky_variant(variant)
+    try:
+        out = handle.nll_batch(cands[:, :k], cands[:, k:])
+    finally:
+        handle.set_cholesky_variant(0)
+    assert out["info"][5] > 0 and np.isnan(out["nll"][5])
+    checked = 0
+    for i, c in enumerate(cands):
+        Psi = onp.psi_fast(Xn, c[:k], c[k:])
+        nll, mu, s2, lndet, info = onp.neglikelihood_fast(Psi, yn)
+        if info != 0:
+            assert out["info"][i] > 0
+            continue
+        cond = np.linalg.cond(Psi)
+        if cond > 1e12:
+            continue
+        assert out["info"][i] == 0
+        tol = tol_for_cond(cond)
+        assert rel_err(out["nll"][i], nll) < tol, (i, cond)
+        assert rel_err(out["mu"][i], mu) < tol, (i, cond)
+        assert rel_err(out["sigma2"][i], s2) < tol, (i, cond)
+        assert abs(out["lndet"][i] - lndet) < tol * max(1.0, abs(lndet))
+        checked += 1
+    assert checked >= 6
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_fit_predict_with_both_cholesky_variants(handle, variant):
+    """pk_fit carries L^-1 as extra panel rows through the same kernels: predictions must agree."""
+    X = onp.rlh(300, 3, 9)
+    y = onp.f_squared(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    theta, p = np.array([3.0, 1.0, 0.5]), np.array([1.9, 1.7, 2.0])
+    handle.set_cholesky_variant(variant)
+    try:
+        out4, info = handle.fit(theta, p)
+    finally:
+        handle.set_cholesky_variant(0)
+    assert info == 0
+    Psi = onp.psi_fast(Xn, theta, p)
+    nll, mu, s2, lndet, _ = onp.neglikelihood_fast(Psi, yn)
+    tol = tol_for_cond(np.linalg.cond(Psi))
+    assert rel_err(out4[0], nll) < tol and rel_err(out4[1], mu) < tol and rel_err(out4[2], s2) < tol
+    U = handle.get_U()
+    assert np.allclose(U.T @ U, Psi, rtol=0, atol=1e-12)
+    rng = np.random.default_rng(4)
+    Xq = rng.uniform(0, 1, (1000, 3))
+    ref = onp.predict_batch_fast(Xn, yn, theta, p, onp.EPS_DIAG, Xq, y_min=0.0)
+    got = handle.predict_batch(Xq, theta, p, out4[1], out4[2], y_min=0.0)
+    sig = np.sqrt(out4[2])
+    assert np.max(np.abs(got["yhat"] - ref["yhat"])) < 1e-8
+    assert np.max(np.abs(got["s"] - ref["s"])) < 1e-5 * sig
+
+
 def test_small_and_tiled_paths_agree(handle):
     """n = 128 runs in the fused small-n kernel, n = 129 in the tiled path: same model +/- one point."""
     X = onp.rlh(129, 3, 21)
