@@ -37,7 +37,7 @@ constexpr int TS = PK_TILE + 4;    // 68: stride of the diagonal tile while it i
 constexpr int DLD = 12;            // row stride of the inverted 8x8 diagonal blocks
 constexpr int D_DOUBLES = 8 * 8 * DLD;
 constexpr int SMEM_DOUBLES = PIPE_DOUBLES + D_DOUBLES + PK_TILE + 2;  // + diag0[64] + control words
-static_assert(PK_TILE * TS <= PIPE_DOUBLES, "the diagonal tile reuses the pipeline buffers");
+static_assert(PK_TILE * TS <= STAGES * A_STAGE, "the diagonal tile reuses the pipeline buffers");
 
 __device__ __forceinline__ double negd(double x) {
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));  // sign flip on the ALU pipe
@@ -223,15 +223,15 @@ __device__ __forceinline__ int panel_factor(double* T, const double* diag0, int 
             v[s][2 * c + 1] = t.y;
         }
     }
+    // The failure test is recorded, not branched on: a non-positive pivot only turns the rest of the
+    // (discarded) panel into NaNs, and keeping the compare off the dependent chain matters because every
+    // FP64 instruction of this warp queues behind the other CTA's DMMAs.
     int bad = 0;
+    double piv = __shfl_sync(0xffffffffu, v[SLOT][0], c0 & 31);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const int gc = c0 + c;
-        const double piv = __shfl_sync(0xffffffffu, v[SLOT][c], gc & 31);
-        if (!(piv > piv_tol * diag0[gc])) {
-            bad = gc + 1;
-            break;
-        }
+        if (!(piv > piv_tol * diag0[gc]) && bad == 0) bad = gc + 1;
         const double rinv = rsqrt(piv);  // l_cc = piv * rinv (<= 2 ulp), rows below scale by rinv
         double l[2];
 #pragma unroll
@@ -239,6 +239,8 @@ __device__ __forceinline__ int panel_factor(double* T, const double* diag0, int 
             l[s] = v[s][c] * rinv;
             v[s][c] = l[s];
         }
+        if (c < 7)  // next pivot straight from its owner lane: a_cc - l^2 is the same FMA the update below performs
+            piv = __shfl_sync(0xffffffffu, fma(-l[SLOT], l[SLOT], v[SLOT][c + 1]), (gc + 1) & 31);
 #pragma unroll
         for (int c2 = c + 1; c2 < 8; ++c2) {
             const double m = __shfl_sync(0xffffffffu, l[SLOT], (c0 + c2) & 31);  // L[c0 + c2][gc]
@@ -313,24 +315,87 @@ __device__ __forceinline__ void invert_diag_block(const double* T, double* Dsm, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Diagonal tile update T = Psi_jj - L[j,0:j] L[j,0:j]^T, LOWER 8x8 blocks only (36 of 64).  Warp w owns
+// block row br(w) = w for w < 4 and 11 - w otherwise, so the two warps that share a scheduler carry
+// 9 blocks together and the four tensor pipes stay balanced.  A and B are the same 64 rows: only the
+// B stages are loaded.  NI = br + 1 is dispatched by a warp-uniform switch (no predicated-off DMMAs).
+// ------------------------------------------------------------------------------------------------
+template <int NI>
+__device__ __forceinline__ void diag_consume(double (&acc)[8][2], const double* Bs, int br, int lane) {
+    const int fr = lane >> 2, fc = lane & 3;
+    const double* a_s = Bs + (br * 8 + fr) * SLD + fc;
+    const double* b_s = Bs + fr * SLD + fc;
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+        const double a = negd(a_s[kk]);
+        double b[NI];
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) b[ni] = b_s[ni * 8 * SLD + kk];
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) dmma884(acc[ni][0], acc[ni][1], a, b[ni]);
+    }
+}
+
+__device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, q = lane & 3;
+    const int br = (warp < 4) ? warp : 11 - warp;
+    double* Bs = pipe + STAGES * A_STAGE;
+    const int row0 = j * PK_TILE;
+    const int nk = j * (PK_TILE / KC);
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(nullptr, Bs + s * B_STAGE, M, ld, 0, 0, row0, s * KC, false);
+        cp_async_commit();
+    }
+    double acc[8][2];
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        if (ni <= br) {
+            const double2 v =
+                *reinterpret_cast<const double2*>(M + (size_t)(row0 + br * 8 + fr) * ld + row0 + ni * 8 + 2 * q);
+            acc[ni][0] = v.x;
+            acc[ni][1] = v.y;
+        } else {
+            acc[ni][0] = acc[ni][1] = 0.0;
+        }
+    }
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nxt = it + STAGES - 1;
+        if (nxt < nk) load_stage(nullptr, Bs + (nxt % STAGES) * B_STAGE, M, ld, 0, 0, row0, nxt * KC, false);
+        cp_async_commit();
+        const double* bs = Bs + (it % STAGES) * B_STAGE;
+        switch (br) {
+            case 0: diag_consume<1>(acc, bs, br, lane); break;
+            case 1: diag_consume<2>(acc, bs, br, lane); break;
+            case 2: diag_consume<3>(acc, bs, br, lane); break;
+            case 3: diag_consume<4>(acc, bs, br, lane); break;
+            case 4: diag_consume<5>(acc, bs, br, lane); break;
+            case 5: diag_consume<6>(acc, bs, br, lane); break;
+            case 6: diag_consume<7>(acc, bs, br, lane); break;
+            default: diag_consume<8>(acc, bs, br, lane); break;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // the stages are drained: T (aliasing the A stages) may be written
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        if (ni <= br)
+            *reinterpret_cast<double2*>(T + (br * 8 + fr) * TS + ni * 8 + 2 * q) = make_double2(acc[ni][0], acc[ni][1]);
+    }
+}
+
 // Diagonal tile of block column j.  Returns 0 or the tile-local failing column (CTA uniform).
 __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag0, int* ctl, double* __restrict__ M,
                                          int ld, int j, double piv_tol) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int fr = lane >> 2, q = lane & 3;
     const int row0 = j * PK_TILE;
     if (tid < PK_TILE) diag0[tid] = M[(size_t)(row0 + tid) * ld + row0 + tid];
-    double acc[2][8][2];
-    block_rows<false>(acc, pipe, Dsm, M, ld, j, row0, PK_TILE);
     double* T = pipe;
-    if (warp < 4) {
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 8; ++ni)
-                *reinterpret_cast<double2*>(T + (warp * 16 + mi * 8 + fr) * TS + ni * 8 + 2 * q) =
-                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-    }
+    diag_gemm(T, pipe, M, ld, j);
     if (tid == 0) ctl[1] = 0;
     __syncthreads();
     for (int kb = 0; kb < 8; ++kb) {

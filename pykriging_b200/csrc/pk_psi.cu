@@ -24,6 +24,9 @@ namespace pk {
 __constant__ double c_exp2_hi[64] = {PK_EXP2_HI_LIST};
 __constant__ double c_exp2_lo[64] = {PK_EXP2_LO_LIST};
 __constant__ double c_log2p1[9] = {PK_LOG2P1_LIST};
+__constant__ double c_l2c_rc[64] = {PK_LOG2C_RC_LIST};
+__constant__ double c_l2c_hi[64] = {PK_LOG2C_HI_LIST};
+__constant__ double c_l2c_lo[64] = {PK_LOG2C_LO_LIST};
 
 // ---- table-driven 2^x and e^-S ----------------------------------------------------------------------
 // tab = shared copy of g_exp2_table replicated over the 16 eight-byte banks: tab[j * 16 + (lane & 15)]
@@ -75,34 +78,33 @@ __device__ __forceinline__ double expneg_table(double S, const double* __restric
     return scale_pow2(fma(T, q, T), ki >> 6);
 }
 
-// log2 d as an unevaluated sum L + res with L = fl(log2 d) and |res| <= ulp(L)/2, accurate to ~2^-60
-// ABSOLUTE (not relative to L): d = 2^E m, m in [1,2); pick j with 2^(j/64) ~ m, z = m / 2^(j/64) - 1
-// (exact table hi + lo), log2 d = (E + j/64) + log2(1 + z) with a degree-9 series.  Runs once per
-// (pair, dimension) per CTA, never in the candidate loop.
+// log2 d as an unevaluated sum L + res with L = fl(log2 d) and |res| <= ulp(L)/2, accurate to ~2^-59
+// ABSOLUTE (not relative to L): d = 2^E m, m in [1,2); the top six mantissa bits j select the centre
+// c_j = 1 + (2j+1)/128 of m's 1/64-wide interval, z = (m - c_j) / c_j (m - c_j is exact, 1/c_j is tabulated),
+// log2 d = (E + hi_j) + (lo_j + log2(1 + z)) with log2 c_j = hi_j + lo_j tabulated (hi_j on a 2^-40 grid, so
+// E + hi_j is exact) and a degree-9 series for log2(1 + z), |z| <= 2^-7.  No division, no libm call.
+// Runs once per (pair, dimension) per CTA, never in the candidate loop.
 __device__ __forceinline__ void log2_split(double d, double& L, float& res) {
     if (!(d >= 2.2250738585072014e-308)) {  // pow(0, p > 0) = 0: a hugely negative exponent underflows to 0
         L = -1100.0;
         res = 0.0f;
         return;
     }
-    const long long bits = __double_as_longlong(d);
-    int E = (int)((bits >> 52) & 0x7ff) - 1023;
-    double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-    int j = __double2int_rn(64.0 * log2(m));  // any nearby j keeps |z| small; accuracy does not depend on it
-    if (j >= 64) {
-        j = 0;
-        E += 1;
-        m *= 0.5;
-    }
-    const double T = c_exp2_hi[j], Tl = c_exp2_lo[j];
-    const double z = ((m - T) - Tl) / T;      // m - T exact (Sterbenz); |z| <= 2^(1/128) - 1
+    const int hi = __double2hiint(d);
+    const int E = ((hi >> 20) & 0x7ff) - 1023;
+    const int j = (hi >> 14) & 63;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(d));
+    const double c = fma((double)(2 * j + 1), 0.0078125, 1.0);  // exact
+    const double z = (m - c) * c_l2c_rc[j];
     double q = c_log2p1[8];
 #pragma unroll
     for (int i = 7; i >= 0; --i) q = fma(q, z, c_log2p1[i]);
-    const double ll = q * z;                  // log2(1 + z)
-    const double lh = (double)E + (double)j * 0.015625;  // exact
-    L = lh + ll;
-    res = (float)(ll - (L - lh));             // Fast2Sum remainder (|lh| >= |ll| or lh == 0)
+    const double t = fma(q, z, c_l2c_lo[j]);     // lo_j + log2(1 + z)
+    const double lh = (double)E + c_l2c_hi[j];   // exact
+    L = lh + t;
+    const double bb = L - lh;                    // TwoSum: (lh + t) = L + r exactly
+    const double r = (lh - (L - bb)) + (t - bb);
+    res = (float)r;
 }
 
 // ---- lean 2^x for the candidate loop ---------------------------------------------------------------
@@ -132,7 +134,7 @@ __device__ __forceinline__ double exp2_lean(double s, double e, const char* __re
 }
 
 constexpr int PSI_THREADS = 256;
-constexpr int PSI_GROUP = 32;  // candidates per CTA
+constexpr int PSI_GROUP = 64;  // candidates per CTA (amortises the log2 split of the CTA's pairs)
 
 template <int K, int PPT>
 __global__ void __launch_bounds__(PSI_THREADS)
@@ -286,7 +288,8 @@ __global__ void debug_math_kernel(int64_t m, const double* __restrict__ d, const
         log2_split(fabs(d[i]), lh, ll);
         const double s = p[i] * lh;
         const double e = fma(p[i], (double)ll, fma(p[i], lh, -s));
-        out_pow[i] = exp2_table(s, e, tab, bank);
+        // odd elements go through the lean (hot-loop) variant, even ones through the range-checked one
+        out_pow[i] = (i & 1) ? exp2_lean(s, e, reinterpret_cast<const char*>(tab + bank)) : exp2_table(s, e, tab, bank);
         out_expneg[i] = expneg_table(d[i], tab, bank);
     }
 }
