@@ -19,6 +19,9 @@
 //
 // Two CTAs are resident per SM (256 threads, 128 registers, ~99 KB shared memory each): while one
 // sits in the latency-bound 64x64 factorisation the other keeps the FP64 tensor pipe busy.
+#include <cstdio>
+#include <cstdlib>
+
 #include "pk_internal.h"
 
 namespace pk {
@@ -41,23 +44,6 @@ static_assert(PK_TILE * TS <= STAGES * A_STAGE, "the diagonal tile reuses the pi
 
 __device__ __forceinline__ double negd(double x) {
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));  // sign flip on the ALU pipe
-}
-
-// One pipeline stage: B = L[j*64 .. +64, k0 .. k0+16) always, A = M[row0 .. row0+a_rows, k0 .. k0+16)
-// only while the chunk lies left of block column j (the last four chunks carry L_jj itself for the
-// triangular solve and need no A operand).
-__device__ __forceinline__ void load_stage(double* As, double* Bs, const double* __restrict__ M, int ld, int row0,
-                                           int a_rows, int brow0, int k0, bool with_a) {
-    if (with_a) {
-        for (int i = threadIdx.x; i < a_rows * 8; i += THREADS) {
-            const int r = i >> 3, ch = i & 7;
-            cp_async16(As + r * SLD + ch * 2, M + (size_t)(row0 + r) * ld + k0 + ch * 2);
-        }
-    }
-    for (int i = threadIdx.x; i < PK_TILE * 8; i += THREADS) {
-        const int r = i >> 3, ch = i & 7;
-        cp_async16(Bs + r * SLD + ch * 2, M + (size_t)(brow0 + r) * ld + k0 + ch * 2);
-    }
 }
 
 // acc(8*MI x 64 per warp) -= A(8*MI x 16) * B(64 x 16)^T for one stage.  MI (rows of 8 this warp owns in
@@ -132,75 +118,134 @@ __device__ __forceinline__ void trsm_consume(double (&acc)[2][8][2], const doubl
     }
 }
 
-// acc = M[row0 + 16 warp .., j*64 .. +64) -= L[rows, 0:j*64] L[j, 0:j*64]^T, then (with_trsm) the
-// in-register solve against L_jj.  rows_valid (multiple of 8) rows of the pass exist.
-template <bool WITH_TRSM>
-__device__ __forceinline__ void block_rows(double (&acc)[2][8][2], double* pipe, const double* Dsm,
-                                           const double* __restrict__ M, int ld, int j, int row0, int rows_valid) {
+// The original tile enters through the pipeline as well: the A stage of solve chunk T holds columns
+// 16T .. 16T+15 of M[rows, j] (still Psi / identity / right-hand sides), which are added to the two
+// accumulator blocks that chunk is about to solve.  No accumulator pre-load from global memory.
+template <int T, int MI>
+__device__ __forceinline__ void add_tile_chunk(double (&acc)[2][8][2], const double* As, int warp, int lane) {
+    const int fr = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const double2 v = *reinterpret_cast<const double2*>(As + (warp * 16 + mi * 8 + fr) * SLD + half * 8 + 2 * q);
+            acc[mi][2 * T + half][0] += v.x;
+            acc[mi][2 * T + half][1] += v.y;
+        }
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void solve_chunk(double (&acc)[2][8][2], const double* As, const double* Bs,
+                                            const double* Dsm, int warp, int lane, int mi_count) {
+    if (mi_count == 2) {
+        add_tile_chunk<T, 2>(acc, As, warp, lane);
+        trsm_consume<T, 2>(acc, Bs, Dsm, lane);
+    } else if (mi_count == 1) {
+        add_tile_chunk<T, 1>(acc, As, warp, lane);
+        trsm_consume<T, 1>(acc, Bs, Dsm, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Panel of block column j: every row below the diagonal tile (rows [(j+1)*64, rows)), 128 rows per
+// pass, as ONE continuous stream of pipeline chunks.  A pass consists of 4j product chunks
+//     acc -= M[rows, 16c..] * L[j, 16c..]^T
+// followed by four solve chunks (A stage = original tile columns, B stage = L_jj columns).  The
+// cp.async pipeline never drains between passes: while a pass is being solved and stored, the first
+// chunks of the next pass are already in flight.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
+                                             int rows) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
-    const int mi_count = max(0, min(2, (rows_valid - warp * 16) / 8));
     double* As = pipe;
     double* Bs = pipe + STAGES * A_STAGE;
     const int brow0 = j * PK_TILE;
+    const int first = (j + 1) * PK_TILE;
     const int nk_gemm = j * (PK_TILE / KC);
-    const int nkt = nk_gemm + (WITH_TRSM ? PK_TILE / KC : 0);
-    // start the pipeline first, then fetch the accumulator tile while the copies are in flight
+    const int nkt = nk_gemm + PK_TILE / KC;
+    const int nblk = (rows - first + BM - 1) / BM;
+    const int total = nblk * nkt;
+    // Producer: every thread owns one 16-byte column slot (lc) of rows lr, lr+32, .. of a stage; its global
+    // source pointers are carried along (advance by KC per chunk, by BM rows per pass), so issuing a stage
+    // costs a handful of instructions -- the tensor pipe idles while the CTA is busy with anything else.
+    const int lr = tid >> 3, lc = (tid & 7) * 2;
+    const size_t ld32 = (size_t)32 * ld;
+    const double* gB = M + (size_t)(brow0 + lr) * ld + lc;
+    const double* gA = M + (size_t)(first + lr) * ld + lc;
+    int p_row0 = first, p_rows = min(BM, rows - first), pk = 0, ps = 0;
+    auto produce = [&]() {
+        double* as = As + ps * A_STAGE + lr * SLD + lc;
+        double* bs = Bs + ps * B_STAGE + lr * SLD + lc;
+        const double* ga = gA + pk * KC;
+        const double* gb = gB + pk * KC;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (lr + 32 * i < p_rows) cp_async16(as + i * 32 * SLD, ga + i * ld32);
+        cp_async16(bs, gb);
+        cp_async16(bs + 32 * SLD, gb + ld32);
+        ps = (ps == STAGES - 1) ? 0 : ps + 1;
+        if (++pk == nkt) {
+            pk = 0;
+            p_row0 += BM;
+            gA += (size_t)BM * ld;
+            p_rows = min(BM, rows - p_row0);
+        }
+    };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nkt) load_stage(As + s * A_STAGE, Bs + s * B_STAGE, M, ld, row0, rows_valid, brow0, s * KC, s < nk_gemm);
+        if (s < total) produce();
         cp_async_commit();
     }
+    double acc[2][8][2];
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) {
-            if (mi < mi_count) {
-                const double2 v = *reinterpret_cast<const double2*>(
-                    M + (size_t)(row0 + warp * 16 + mi * 8 + fr) * ld + brow0 + ni * 8 + 2 * q);
-                acc[mi][ni][0] = v.x;
-                acc[mi][ni][1] = v.y;
-            } else {
-                acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            }
-        }
-    }
-    for (int it = 0; it < nk_gemm; ++it) {
+        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    int cb = 0, ck = 0, cs = 0;
+    int row0 = first;
+    int mi_count = max(0, min(2, (min(BM, rows - row0) - warp * 16) / 8));
+    for (int g = 0; g < total; ++g) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        const int nxt = it + STAGES - 1;
-        if (nxt < nkt) {
-            const int s = nxt % STAGES;
-            load_stage(As + s * A_STAGE, Bs + s * B_STAGE, M, ld, row0, rows_valid, brow0, nxt * KC, nxt < nk_gemm);
-        }
+        if (g + STAGES - 1 < total) produce();
         cp_async_commit();
-        const int s = it % STAGES;
-        if (mi_count == 2) gemm_consume<2>(acc, As + s * A_STAGE, Bs + s * B_STAGE, warp, lane);
-        else if (mi_count == 1) gemm_consume<1>(acc, As + s * A_STAGE, Bs + s * B_STAGE, warp, lane);
-    }
-    if (WITH_TRSM) {
-#define PK_TRSM_STEP(TT)                                                                                          \
-        {                                                                                                          \
-            const int it = nk_gemm + TT;                                                                           \
-            cp_async_wait<STAGES - 2>();                                                                           \
-            __syncthreads();                                                                                       \
-            const int nxt = it + STAGES - 1;                                                                       \
-            if (nxt < nkt) {                                                                                       \
-                const int s2 = nxt % STAGES;                                                                       \
-                load_stage(As + s2 * A_STAGE, Bs + s2 * B_STAGE, M, ld, row0, rows_valid, brow0, nxt * KC, false); \
-            }                                                                                                      \
-            cp_async_commit();                                                                                     \
-            if (mi_count == 2) trsm_consume<TT, 2>(acc, Bs + (it % STAGES) * B_STAGE, Dsm, lane);                  \
-            else if (mi_count == 1) trsm_consume<TT, 1>(acc, Bs + (it % STAGES) * B_STAGE, Dsm, lane);             \
+        const double* as = As + cs * A_STAGE;
+        const double* bs = Bs + cs * B_STAGE;
+        cs = (cs == STAGES - 1) ? 0 : cs + 1;
+        if (ck < nk_gemm) {
+            if (mi_count == 2) gemm_consume<2>(acc, as, bs, warp, lane);
+            else if (mi_count == 1) gemm_consume<1>(acc, as, bs, warp, lane);
+        } else {
+            switch (ck - nk_gemm) {
+                case 0: solve_chunk<0>(acc, as, bs, Dsm, warp, lane, mi_count); break;
+                case 1: solve_chunk<1>(acc, as, bs, Dsm, warp, lane, mi_count); break;
+                case 2: solve_chunk<2>(acc, as, bs, Dsm, warp, lane, mi_count); break;
+                default: solve_chunk<3>(acc, as, bs, Dsm, warp, lane, mi_count); break;
+            }
         }
-        PK_TRSM_STEP(0)
-        PK_TRSM_STEP(1)
-        PK_TRSM_STEP(2)
-        PK_TRSM_STEP(3)
-#undef PK_TRSM_STEP
+        if (++ck == nkt) {
+            // pass complete: store the solved rows, reset the accumulators, move to the next pass
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                if (mi < mi_count) {
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni)
+                        *reinterpret_cast<double2*>(M + (size_t)(row0 + warp * 16 + mi * 8 + fr) * ld + brow0 + ni * 8 +
+                                                    2 * q) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                }
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            }
+            ck = 0;
+            ++cb;
+            row0 = first + cb * BM;
+            mi_count = max(0, min(2, (min(BM, rows - row0) - warp * 16) / 8));
+        }
     }
     cp_async_wait<0>();
-    __syncthreads();  // every warp is done with the stages (the caller reuses them)
+    __syncthreads();  // stages drained; the stores of this column are visible to the whole CTA
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,11 +389,23 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
     double* Bs = pipe + STAGES * A_STAGE;
     const int row0 = j * PK_TILE;
     const int nk = j * (PK_TILE / KC);
+    const int lr = tid >> 3, lc = (tid & 7) * 2;
+    const size_t ld32 = (size_t)32 * ld;
+    const double* gB = M + (size_t)(row0 + lr) * ld + lc;
+    int ps = 0;
+    auto produce = [&]() {
+        double* bs = Bs + ps * B_STAGE + lr * SLD + lc;
+        cp_async16(bs, gB);
+        cp_async16(bs + 32 * SLD, gB + ld32);
+        gB += KC;
+        ps = (ps == STAGES - 1) ? 0 : ps + 1;
+    };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) load_stage(nullptr, Bs + s * B_STAGE, M, ld, 0, 0, row0, s * KC, false);
+        if (s < nk) produce();
         cp_async_commit();
     }
+    int cs = 0;
     double acc[8][2];
 #pragma unroll
     for (int ni = 0; ni < 8; ++ni) {
@@ -364,10 +421,10 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
     for (int it = 0; it < nk; ++it) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        const int nxt = it + STAGES - 1;
-        if (nxt < nk) load_stage(nullptr, Bs + (nxt % STAGES) * B_STAGE, M, ld, 0, 0, row0, nxt * KC, false);
+        if (it + STAGES - 1 < nk) produce();
         cp_async_commit();
-        const double* bs = Bs + (it % STAGES) * B_STAGE;
+        const double* bs = Bs + cs * B_STAGE;
+        cs = (cs == STAGES - 1) ? 0 : cs + 1;
         switch (br) {
             case 0: diag_consume<1>(acc, bs, br, lane); break;
             case 1: diag_consume<2>(acc, bs, br, lane); break;
@@ -390,14 +447,21 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
 
 // Diagonal tile of block column j.  Returns 0 or the tile-local failing column (CTA uniform).
 __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag0, int* ctl, double* __restrict__ M,
-                                         int ld, int j, double piv_tol) {
+                                         int ld, int j, double piv_tol, long long* tm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = j * PK_TILE;
     if (tid < PK_TILE) diag0[tid] = M[(size_t)(row0 + tid) * ld + row0 + tid];
     double* T = pipe;
+    long long t0 = 0;
+    if (tm) t0 = clock64();
     diag_gemm(T, pipe, M, ld, j);
     if (tid == 0) ctl[1] = 0;
     __syncthreads();
+    if (tm) {
+        const long long t1 = clock64();
+        tm[0] += t1 - t0;
+        t0 = t1;
+    }
     for (int kb = 0; kb < 8; ++kb) {
         if (warp == 0) {
             const int bad = (kb < 4) ? panel_factor<0>(T, diag0, kb, piv_tol, lane)
@@ -411,6 +475,11 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
             __syncthreads();
         }
     }
+    if (tm) {
+        const long long t1 = clock64();
+        tm[1] += t1 - t0;
+        t0 = t1;
+    }
     invert_diag_block(T, Dsm, warp, lane);
     for (int i = tid; i < PK_TILE * (PK_TILE / 2); i += THREADS) {
         const int rr = i >> 5, c2 = (i & 31) * 2;
@@ -419,19 +488,24 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
             make_double2((c2 <= rr) ? t.x : 0.0, (c2 + 1 <= rr) ? t.y : 0.0);
     }
     __syncthreads();  // L_jj is in global memory and D in shared memory for every thread of the CTA
+    if (tm) tm[2] += clock64() - t0;
     return 0;
 }
 
+// TIMING: thread 0 accumulates clock64() per phase {diag product, 64x64 factorisation, inverse + copy-out,
+// panel column, candidates} into dbg[5 * blockIdx.x ..] (diagnostic build of the same kernel).
+template <bool TIMING>
 __global__ void __launch_bounds__(THREADS, 2)
 chol_cta_kernel(int C, int nt, int rows, int ld, size_t elems, double piv_tol, double* __restrict__ ws,
-                int32_t* __restrict__ info, unsigned int* __restrict__ queue) {
+                int32_t* __restrict__ info, unsigned int* __restrict__ queue, long long* __restrict__ dbg, int alias) {
+    long long tmv[5] = {0, 0, 0, 0, 0};
+    long long* tm = TIMING ? tmv : nullptr;
     extern __shared__ __align__(16) double smem[];
     double* pipe = smem;
     double* Dsm = pipe + PIPE_DOUBLES;
     double* diag0 = Dsm + D_DOUBLES;
     int* ctl = reinterpret_cast<int*>(diag0 + PK_TILE);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int fr = lane >> 2, q = lane & 3;
+    const int tid = threadIdx.x;
     for (;;) {
         __syncthreads();
         if (tid == 0) ctl[0] = (int)atomicAdd(queue, 1u);
@@ -439,31 +513,22 @@ chol_cta_kernel(int C, int nt, int rows, int ld, size_t elems, double piv_tol, d
         const int cand = ctl[0];
         if (cand >= C) break;
         if (info[cand] != 0) continue;
-        double* M = ws + (size_t)cand * elems;
+        double* M = ws + (size_t)(alias ? (cand & 7) : cand) * elems;  // alias: timing experiment only (results are garbage)
         for (int j = 0; j < nt; ++j) {
-            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, piv_tol);
-            if (bad) {
+            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, piv_tol, tm);
+            if (bad && !alias) {
                 if (tid == 0) info[cand] = j * PK_TILE + bad;  // dpotrf convention: order of the failing minor
                 break;
             }
-            for (int row0 = (j + 1) * PK_TILE; row0 < rows; row0 += BM) {
-                const int rows_valid = min(BM, rows - row0);
-                double acc[2][8][2];
-                block_rows<true>(acc, pipe, Dsm, M, ld, j, row0, rows_valid);
-                const int mi_count = max(0, min(2, (rows_valid - warp * 16) / 8));
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi) {
-                    if (mi < mi_count) {
-#pragma unroll
-                        for (int ni = 0; ni < 8; ++ni)
-                            *reinterpret_cast<double2*>(M + (size_t)(row0 + warp * 16 + mi * 8 + fr) * ld +
-                                                        j * PK_TILE + ni * 8 + 2 * q) =
-                                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-                    }
-                }
-            }
-            __syncthreads();  // the panel of column j is visible to the whole CTA before column j+1 reads it
+            long long t0 = 0;
+            if (TIMING) t0 = clock64();
+            panel_column(pipe, Dsm, M, ld, j, rows);
+            if (TIMING) tmv[3] += clock64() - t0;
         }
+        if (TIMING) tmv[4] += 1;
+    }
+    if (TIMING && tid == 0) {
+        for (int i = 0; i < 5; ++i) dbg[5 * blockIdx.x + i] = tmv[i];
     }
 }
 
@@ -475,15 +540,38 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e =
-            cudaFuncSetAttribute(cta::chol_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(cta::chol_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(cta::chol_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     cudaError_t e = cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned int), h->stream);
     if (e != cudaSuccess) return e;
-    const int grid = (C < 2 * h->sm_count) ? C : 2 * h->sm_count;
-    cta::chol_cta_kernel<<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(), h->pivot_tol, ws,
-                                                                  info, h->d_queue);
+    int per_sm = 2;
+    if (const char* e = getenv("PK_CHOL_CTAS_PER_SM")) per_sm = (atoi(e) == 1) ? 1 : 2;  // experiment knob
+    const int grid = (C < per_sm * h->sm_count) ? C : per_sm * h->sm_count;
+    if (getenv("PK_CTA_TIMING")) {  // diagnostic: per-phase cycle counts of the persistent kernel, printed to stderr
+        long long* dbg = nullptr;
+        cudaMalloc((void**)&dbg, sizeof(long long) * 5 * grid);
+        cudaMemset(dbg, 0, sizeof(long long) * 5 * grid);
+        cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
+                                                                            ws, info, h->d_queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0);
+        cudaStreamSynchronize(h->stream);
+        std::vector<long long> host(5 * (size_t)grid);
+        cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        double sum[5] = {0, 0, 0, 0, 0};
+        for (int b2 = 0; b2 < grid; ++b2)
+            for (int i = 0; i < 5; ++i) sum[i] += (double)host[5 * b2 + i];
+        fprintf(stderr,
+                "[pk cta timing] grid %d, candidates %.0f; cycles per candidate: diag product %.0f, factorise 64x64 %.0f, "
+                "inverse+copy %.0f, panel column %.0f\n",
+                grid, sum[4], sum[0] / sum[4], sum[1] / sum[4], sum[2] / sum[4], sum[3] / sum[4]);
+    } else {
+        cta::chol_cta_kernel<false><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(),
+                                                                             h->pivot_tol, ws, info, h->d_queue, nullptr, 0);
+    }
     h->launches++;
     return cudaGetLastError();
 }

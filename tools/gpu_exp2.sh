@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+PK_CTA_TIMING=1 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "pk cta" | tail -2
+PK_CTA_TIMING=1 PK_CHOL_CTAS_PER_SM=1 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "pk cta" | tail -2
