@@ -53,6 +53,83 @@ def make_candidates(C, k, seed):
     return np.ascontiguousarray(theta), np.ascontiguousarray(p)
 
 
+PRED_N, PRED_K, PRED_GRID = 512, 2, 4096  # C5: EI over a 4096 x 4096 = 16 777 216-point grid, n = 512 model
+
+
+def make_branin_samples(n, seed=5):
+    rng = np.random.default_rng(seed)
+    X = np.zeros((n, 2))
+    for d in range(2):
+        X[:, d] = rng.permutation(np.arange(1, n + 1, 1))
+    X = (X - 0.5) / n
+    x1, x2 = X[:, 0] * 15 - 5, X[:, 1] * 15
+    y = (x2 - 5.1 / (4 * np.pi ** 2) * x1 ** 2 + 5 / np.pi * x1 - 6) ** 2 + 10 * (1 - 1 / (8 * np.pi)) * np.cos(x1) + 10
+    return X, y
+
+
+def run_predictions(torch, dev, local_rank, rank, world, dist):
+    """predictions/s (the second half of BASELINE.json's metric): yhat, s and EI for this rank's rows of
+    the 16 Mi-point query grid on a fitted n = 512 model, query points resident in HBM."""
+    from pykriging_b200.krige import kriging
+
+    X, y = make_branin_samples(PRED_N)
+    model = kriging(X, y, device=local_rank)
+    model.update([5.0, 5.0, 1.8, 1.8])
+    model.neglikelihood()
+    h = model._pk_handle()
+    m_total = PRED_GRID * PRED_GRID
+    per = -(-m_total // world)
+    lo, hi = min(rank * per, m_total), min((rank + 1) * per, m_total)
+    m = hi - lo
+    idx = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+    ax = torch.linspace(0.0, 1.0, PRED_GRID, dtype=torch.float64, device=dev)
+    Xq = torch.stack([ax[idx // PRED_GRID], ax[idx % PRED_GRID]], dim=1).contiguous()
+    del idx
+    out = torch.empty(3, m, dtype=torch.float64, device=dev)
+    theta = np.array([5.0, 5.0])
+    pl = np.array([1.8, 1.8])
+    y_min = float(np.min(model.y))
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+
+    def go():
+        h.predict_batch_raw(m, Xq, theta, pl, float(model.mu), float(model.SigmaSqr), y_min, -1.0, 0.0, out[0], out[1],
+                            out[2])
+
+    go()
+    h.synchronize()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(reps):
+            go()
+        ev1.record(stream)
+    h.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    best = float(out[2].max().item())
+    del Xq, out
+    return {"value": m_total / (ms * 1e-3), "unit": "predictions/s", "ms": ms, "points": m_total, "n": PRED_N,
+            "k": PRED_K, "outputs": "yhat, s, EI per point", "scaling": "strong (grid rows sharded over ranks)",
+            "flops_per_point_algorithmic": PRED_N ** 2,
+            "tflops_algorithmic": m_total * PRED_N ** 2 / (ms * 1e-3) * 1e-12, "max_ei": best}
+
+
+def load_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed `ncu --set full` capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def config_dict(n_gpus):
     return {"workload": "C3: 10-D synthetic (rlh seed 1234, Styblinski-Tang), n=1024 samples, population of "
                         "1024 (theta,p) candidates per GPU per step (512 uniform + 512 log-uniform theta)",
@@ -248,6 +325,10 @@ def run_ours(args, rank, world, local_rank):
     value = evals / (ms_max * 1e-3)
     e2e_value = evals / (e2e_ms_max * 1e-3)
 
+    pred = None
+    if not args.no_predictions:
+        pred = run_predictions(torch, dev, local_rank, rank, world, dist)
+    traffic = load_traffic()
     if rank == 0:
         n = N_SAMPLES
         flops_chol = (n ** 3) / 3.0 * C * args.steps
@@ -269,17 +350,26 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * C * k * 8,
                     "d2h_bytes_per_step": 4 * C * 8 + 4 * C, "api": "pk_nll_batch (C ABI) with pinned host buffers"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "blocked Cholesky (chol_diag_kernel + chol_off_kernel, DMMA 8x8x4)",
+            "roofline": {"kernel": "cta::chol_cta_kernel (persistent blocked Cholesky, one CTA per candidate, "
+                                   "DMMA 8x8x4)" if args.chol_variant != 1 else "chol_first_kernel + chol_step_kernel",
                          "bound": "tensor", "achieved": chol_tf, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-                         "frac": (chol_tf / peak["dmma_tflops"]) if chol_tf else None, "traffic": None,
+                         "frac": (chol_tf / peak["dmma_tflops"]) if chol_tf else None,
+                         "traffic": (traffic or {}).get("chol_cta_kernel_dram_bytes_per_launch"),
+                         "traffic_source": (traffic or {}).get("source"),
                          "algorithmic": "n^3/3 flop per eval = %.4g flop x %d evals per step" % (n ** 3 / 3.0, C),
                          "peak_source": "FP64 DMMA peak measured in this process (pk_fp64_peak; "
                                         "MEASURED_PEAKS.json has no FP64 entry)",
                          "phase_ms_per_step": {kk: v / args.steps for kk, v in phases.items()}},
-            "roofline_psi": {"kernel": "psi_build_kernel", "bound": "hbm", "achieved": psi_gbs, "peak": hbm_peak,
+            "roofline_psi": {"kernel": "psi_pop_kernel<10,2>", "bound": "hbm", "achieved": psi_gbs, "peak": hbm_peak,
                              "unit": "GB/s", "frac": (psi_gbs / hbm_peak) if psi_gbs else None,
                              "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                             "algorithmic": "8 B per lower-triangle tile entry written; FP64-ALU bound for general p"},
+                             "algorithmic": "8 B per lower-triangle tile entry written; FP64-ALU bound for general p "
+                                            "(10 table-driven 2^x + 1 e^-S per entry, see fp64_pipe_frac)",
+                             "fp64_instr_per_entry": 10 * 14 + 11,
+                             "fp64_pipe_frac": ((10 * 14 + 11) * (n * (n - 1) / 2) * C * args.steps * 2.0 /
+                                                (phases["psi"] * 1e-3) * 1e-12 / peak["dfma_tflops"])
+                             if phases["psi"] > 0 else None},
+            "predictions": pred,
             "fp64_peak": peak, "failed_factorisations_last_step": fails,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -302,6 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-predictions", action="store_true")
     ap.add_argument("--chol-variant", type=int, default=0, help="0 auto, 1 per-block-column launches, 2 persistent CTA")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -321,8 +321,8 @@ class kriging(matrixops):
         if cands.size == 0:
             return []
         k = self.k
-        out = self._pk_handle().nll_batch(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
-                                          None, _lib.MODE_INTERP)
+        out = self._pk_nll_population(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
+                                      None, _lib.MODE_INTERP)
         fitness = []
         last_ok = -1
         for i in range(len(cands)):

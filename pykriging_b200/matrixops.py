@@ -16,7 +16,7 @@ The reference's ``distance`` tensor (n x n x k, 84 MB at n=1024, k=10) is never 
 """
 import numpy as np
 
-from . import _lib
+from . import _lib, sharding
 
 
 class matrixops(object):
@@ -48,6 +48,32 @@ class matrixops(object):
         self.__dict__["_pk_device"] = int(device)
         self._pk_reset_factor()
         self.updateData()
+
+    # -- multi-GPU: one process per GPU, candidates / query points sharded over ranks ------------------
+    def enable_sharding(self, group=None, min_points=4096):
+        """Shard every batched ``fittingObjective`` call (and batched predictions of at least
+        ``min_points`` points) over the ranks of ``group`` (default process group).  Every rank must
+        hold the same model and call the same methods with the same arguments; each evaluates its
+        slice on its own GPU and one all_gather of scalars returns the full result everywhere."""
+        self.__dict__["_pk_shard"] = (group, int(min_points))
+
+    def disable_sharding(self):
+        self.__dict__.pop("_pk_shard", None)
+
+    def _pk_nll_population(self, theta, p, lam, mode):
+        """NegLnLike / mu / SigmaSqr / LnDetPsi / info of a population (dict of arrays), sharded if enabled."""
+        h = self._pk_handle()
+        shard = self.__dict__.get("_pk_shard")
+        if shard is None:
+            return h.nll_batch(theta, p, lam, mode)
+
+        def eval_slice(lo, hi):
+            o = h.nll_batch(theta[lo:hi], p[lo:hi], None if lam is None else lam[lo:hi], mode)
+            return np.stack([o["nll"], o["mu"], o["sigma2"], o["lndet"], o["info"].astype(np.float64)], axis=1)
+
+        rows = sharding.sharded_rows(theta.shape[0], eval_slice, shard[0])
+        return {"nll": rows[:, 0].copy(), "mu": rows[:, 1].copy(), "sigma2": rows[:, 2].copy(),
+                "lndet": rows[:, 3].copy(), "info": rows[:, 4].astype(np.int32)}
 
     def _pk_reset_factor(self):
         self._has_U = False          # reference: self.U = None
@@ -163,9 +189,24 @@ class matrixops(object):
         Xq = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=float)))
         mu = float(self.mu)
         s2 = float(self.SigmaSqr) if self.SigmaSqr is not None else float("nan")
-        return self._pk_handle().predict_batch(Xq, np.asarray(self.theta, dtype=float),
-                                               np.asarray(self.pl, dtype=float), mu, s2, y_min=y_min,
-                                               ei_weight=ei_weight, var_extra=var_extra, want=want)
+        h = self._pk_handle()
+        theta, pl = np.asarray(self.theta, dtype=float), np.asarray(self.pl, dtype=float)
+        shard = self.__dict__.get("_pk_shard")
+        if shard is None or Xq.shape[0] < shard[1]:
+            return h.predict_batch(Xq, theta, pl, mu, s2, y_min=y_min, ei_weight=ei_weight, var_extra=var_extra,
+                                   want=want)
+        names = [nm for nm in ("yhat", "s", "ei") if nm in want]
+
+        def eval_slice(lo, hi):
+            o = h.predict_batch(Xq[lo:hi], theta, pl, mu, s2, y_min=y_min, ei_weight=ei_weight,
+                                var_extra=var_extra, want=want)
+            return np.stack([o[nm] for nm in names], axis=1)
+
+        rows = sharding.sharded_rows(Xq.shape[0], eval_slice, shard[0])
+        out = {"yhat": None, "s": None, "ei": None}
+        for c, nm in enumerate(names):
+            out[nm] = rows[:, c].copy()
+        return out
 
     def predict_normalized(self, x):
         return np.float64(self._pk_predict(x, ("yhat",))["yhat"][0])

@@ -75,8 +75,8 @@ class regression_kriging(kriging):
         if cands.size == 0:
             return []
         k = self.k
-        out = self._pk_handle().nll_batch(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
-                                          np.ascontiguousarray(cands[:, -1]), _lib.MODE_REGRESSION)
+        out = self._pk_nll_population(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
+                                      np.ascontiguousarray(cands[:, -1]), _lib.MODE_REGRESSION)
         fitness = []
         last_ok = -1
         # factor present before this call? (then a failed candidate repeats ITS likelihood)

@@ -1,0 +1,102 @@
+"""World-size-2 (and 3) gloo tests of the multi-GPU host logic: candidate / query-grid sharding,
+the scalar all_gather, the global arg-max and the elite broadcast.  The per-shard evaluator is a
+NumPy stand-in (the CUDA library cannot run here); what is under test is that every rank ends up
+with exactly the single-process result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _fake_nll(theta, p):
+    # deterministic stand-in with the output layout of Handle.nll_batch
+    nll = np.sum(theta * np.sin(p), axis=1)
+    info = (theta[:, 0] < 0.05).astype(np.float64) * 3
+    return np.stack([nll, nll * 0.5, nll * nll, np.cos(nll), info], axis=1)
+
+
+def _worker(rank, world, port, count, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from pykriging_b200 import sharding
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        theta, p = rng.uniform(0, 1, (count, 4)), rng.uniform(1, 2, (count, 4))
+        calls = []
+
+        def eval_slice(lo, hi):
+            calls.append((lo, hi))
+            return _fake_nll(theta[lo:hi], p[lo:hi])
+
+        rows = sharding.sharded_rows(count, eval_slice)
+        lo, hi = sharding.shard_bounds(count, rank, world)
+        vals = rows[lo:hi, 0]
+        best = sharding.global_argmax(vals, lo)
+        elite = sharding.broadcast_candidate(np.arange(9.0) + 100 * rank, src=world - 1)
+        q.put((rank, rows, calls, best, elite))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,count", [(2, 300), (2, 7), (3, 10), (2, 1)])
+def test_population_sharding_matches_single_process(world, count):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, count, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    rng = np.random.default_rng(5)
+    theta, p = rng.uniform(0, 1, (count, 4)), rng.uniform(1, 2, (count, 4))
+    want = _fake_nll(theta, p)
+    covered = []
+    for rank, rows, calls, best, elite in results:
+        assert rows.shape == want.shape
+        assert np.array_equal(rows, want)  # bit-identical on every rank
+        covered += calls
+        assert best[1] == int(np.argmax(want[:, 0])) and best[0] == want[:, 0].max()
+        assert np.array_equal(elite, np.arange(9.0) + 100 * (world - 1))
+    # the slices partition [0, count) exactly once
+    covered = sorted(c for c in covered if c[1] > c[0])
+    assert covered[0][0] == 0 and covered[-1][1] == count
+    for a, b in zip(covered, covered[1:]):
+        assert a[1] == b[0]
+
+
+def test_shard_bounds_partition():
+    from pykriging_b200.sharding import shard_bounds
+
+    for count in (0, 1, 7, 8, 1024, 16777216):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(count, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == count
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= -(-count // world)
+
+
+def test_single_process_passthrough():
+    from pykriging_b200 import sharding
+
+    rows = sharding.sharded_rows(5, lambda lo, hi: np.arange(lo, hi, dtype=float)[:, None] * np.ones((1, 3)))
+    assert rows.shape == (5, 3) and rows[4, 2] == 4.0
+    assert sharding.global_argmax(np.array([1.0, 5.0, 5.0]), 10) == (5.0, 11)
