@@ -40,7 +40,7 @@ constexpr int TS = PK_TILE + 4;    // 68: stride of the diagonal tile while it i
 constexpr int DLD = 12;            // row stride of the inverted 8x8 diagonal blocks
 constexpr int D_DOUBLES = 8 * 8 * DLD;
 constexpr int SMEM_DOUBLES = PIPE_DOUBLES + D_DOUBLES + PK_TILE + 2;  // + diag0[64] + control words
-static_assert(PK_TILE * TS <= STAGES * A_STAGE, "the diagonal tile reuses the pipeline buffers");
+static_assert((PK_TILE + 32) * TS <= STAGES * A_STAGE, "the diagonal tile reuses the pipeline buffers");
 
 __device__ __forceinline__ double negd(double x) {
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));  // sign flip on the ALU pipe
@@ -49,14 +49,14 @@ __device__ __forceinline__ double negd(double x) {
 // acc(8*MI x 64 per warp) -= A(8*MI x 16) * B(64 x 16)^T for one stage.  MI (rows of 8 this warp owns in
 // the pass) is a template parameter, selected by a warp-uniform branch: a DMMA that is merely
 // predicated off still occupies its issue slots on the tensor pipe (measured: profiles/).
-template <int MI>
-__device__ __forceinline__ void gemm_consume(double (&acc)[2][8][2], const double* As, const double* Bs, int warp,
+template <int MI, int HALF>
+__device__ __forceinline__ void gemm_consume(double (&acc)[2][8][2], const double* As, const double* Bs, int wrow,
                                              int lane) {
     const int fr = lane >> 2, fc = lane & 3;
-    const double* a_s = As + (warp * 16 + fr) * SLD + fc;
+    const double* a_s = As + (wrow + fr) * SLD + fc;
     const double* b_s = Bs + fr * SLD + fc;
 #pragma unroll
-    for (int kk = 0; kk < KC; kk += 4) {
+    for (int kk = HALF * (KC / 2); kk < (HALF + 1) * (KC / 2); kk += 4) {
         double a[MI], b[8];
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi) a[mi] = negd(a_s[mi * 8 * SLD + kk]);
@@ -84,36 +84,33 @@ __device__ __forceinline__ void acc_to_afrag(double v0, double v1, int lane, dou
 
 // Triangular solve, pipeline chunk T (columns 16T .. 16T+15 of L_jj are in Bs): for the two 8-column
 // blocks cb of the chunk  X_cb = T_cb * D_cb^T,  then  T_gb -= X_cb * L_jj[gb, cb]^T  for gb > cb.
-template <int T, int MI>
+template <int T, int MI, int half>
 __device__ __forceinline__ void trsm_consume(double (&acc)[2][8][2], const double* Bs, const double* Dsm, int lane) {
     const int fr = lane >> 2, q = lane & 3;
+    constexpr int cb = 2 * T + half;
+    const double d0 = Dsm[(cb * 8 + fr) * DLD + q], d1 = Dsm[(cb * 8 + fr) * DLD + 4 + q];
+    double ax[MI][2];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int cb = 2 * T + half;
-        const double d0 = Dsm[(cb * 8 + fr) * DLD + q], d1 = Dsm[(cb * 8 + fr) * DLD + 4 + q];
-        double ax[MI][2];
+    for (int mi = 0; mi < MI; ++mi) {
+        double a0, a1;
+        acc_to_afrag(acc[mi][cb][0], acc[mi][cb][1], lane, a0, a1);
+        double x0 = 0.0, x1 = 0.0;
+        dmma884(x0, x1, a0, d0);
+        dmma884(x0, x1, a1, d1);
+        acc[mi][cb][0] = x0;
+        acc[mi][cb][1] = x1;
+        acc_to_afrag(x0, x1, lane, a0, a1);
+        ax[mi][0] = negd(a0);
+        ax[mi][1] = negd(a1);
+    }
+#pragma unroll
+    for (int gb = cb + 1; gb < 8; ++gb) {
+        const double b0 = Bs[(gb * 8 + fr) * SLD + half * 8 + q];
+        const double b1 = Bs[(gb * 8 + fr) * SLD + half * 8 + 4 + q];
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi) {
-            double a0, a1;
-            acc_to_afrag(acc[mi][2 * T + half][0], acc[mi][2 * T + half][1], lane, a0, a1);
-            double x0 = 0.0, x1 = 0.0;
-            dmma884(x0, x1, a0, d0);
-            dmma884(x0, x1, a1, d1);
-            acc[mi][2 * T + half][0] = x0;
-            acc[mi][2 * T + half][1] = x1;
-            acc_to_afrag(x0, x1, lane, a0, a1);
-            ax[mi][0] = negd(a0);
-            ax[mi][1] = negd(a1);
-        }
-#pragma unroll
-        for (int gb = 2 * T + half + 1; gb < 8; ++gb) {
-            const double b0 = Bs[(gb * 8 + fr) * SLD + half * 8 + q];
-            const double b1 = Bs[(gb * 8 + fr) * SLD + half * 8 + 4 + q];
-#pragma unroll
-            for (int mi = 0; mi < MI; ++mi) {
-                dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][0], b0);
-                dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][1], b1);
-            }
+            dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][0], b0);
+            dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][1], b1);
         }
     }
 }
@@ -121,29 +118,44 @@ __device__ __forceinline__ void trsm_consume(double (&acc)[2][8][2], const doubl
 // The original tile enters through the pipeline as well: the A stage of solve chunk T holds columns
 // 16T .. 16T+15 of M[rows, j] (still Psi / identity / right-hand sides), which are added to the two
 // accumulator blocks that chunk is about to solve.  No accumulator pre-load from global memory.
-template <int T, int MI>
-__device__ __forceinline__ void add_tile_chunk(double (&acc)[2][8][2], const double* As, int warp, int lane) {
+template <int T, int MI, int half>
+__device__ __forceinline__ void add_tile_chunk(double (&acc)[2][8][2], const double* As, int wrow, int lane) {
     const int fr = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const double2 v = *reinterpret_cast<const double2*>(As + (warp * 16 + mi * 8 + fr) * SLD + half * 8 + 2 * q);
-            acc[mi][2 * T + half][0] += v.x;
-            acc[mi][2 * T + half][1] += v.y;
-        }
+        const double2 v = *reinterpret_cast<const double2*>(As + (wrow + mi * 8 + fr) * SLD + half * 8 + 2 * q);
+        acc[mi][2 * T + half][0] += v.x;
+        acc[mi][2 * T + half][1] += v.y;
     }
 }
 
-template <int T>
-__device__ __forceinline__ void solve_chunk(double (&acc)[2][8][2], const double* As, const double* Bs,
-                                            const double* Dsm, int warp, int lane, int mi_count) {
+// one half (8 columns) of solve chunk T
+template <int T, int half>
+__device__ __forceinline__ void solve_half(double (&acc)[2][8][2], const double* As, const double* Bs,
+                                           const double* Dsm, int wrow, int lane, int mi_count) {
     if (mi_count == 2) {
-        add_tile_chunk<T, 2>(acc, As, warp, lane);
-        trsm_consume<T, 2>(acc, Bs, Dsm, lane);
+        add_tile_chunk<T, 2, half>(acc, As, wrow, lane);
+        trsm_consume<T, 2, half>(acc, Bs, Dsm, lane);
     } else if (mi_count == 1) {
-        add_tile_chunk<T, 1>(acc, As, warp, lane);
-        trsm_consume<T, 1>(acc, Bs, Dsm, lane);
+        add_tile_chunk<T, 1, half>(acc, As, wrow, lane);
+        trsm_consume<T, 1, half>(acc, Bs, Dsm, lane);
+    }
+}
+
+// half a pipeline chunk of a pass: product chunk (ck < nk_gemm) or solve chunk ck - nk_gemm
+template <int HALF>
+__device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const double* as, const double* bs,
+                                             const double* Dsm, int ck, int nk_gemm, int wrow, int lane, int mi_count) {
+    if (ck < nk_gemm) {
+        if (mi_count == 2) gemm_consume<2, HALF>(acc, as, bs, wrow, lane);
+        else if (mi_count == 1) gemm_consume<1, HALF>(acc, as, bs, wrow, lane);
+    } else {
+        switch (ck - nk_gemm) {
+            case 0: solve_half<0, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count); break;
+            case 1: solve_half<1, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count); break;
+            case 2: solve_half<2, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count); break;
+            default: solve_half<3, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count); break;
+        }
     }
 }
 
@@ -203,28 +215,37 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    // A 128-row pass gives every warp 16 rows (two DMMA row tiles); a 64-row pass (odd number of tiles left)
+    // gives every warp 8 rows, so all four schedulers keep two warps either way.
+    auto pass_shape = [&](int r0, int& wrow, int& mic) {
+        const bool full = (rows - r0) >= BM;
+        wrow = warp * (full ? 16 : 8);
+        mic = full ? 2 : 1;
+    };
     int cb = 0, ck = 0, cs = 0;
-    int row0 = first;
-    int mi_count = max(0, min(2, (min(BM, rows - row0) - warp * 16) / 8));
+    int row0 = first, wrow, mi_count;
+    pass_shape(row0, wrow, mi_count);
+    // The two warps of a scheduler issue their share of the next stage at different points of the chunk
+    // (warps 0-3 before its first half, warps 4-7 between the halves): while one computes addresses the
+    // other keeps the tensor pipe fed.
+    const bool early = warp < 4;
     for (int g = 0; g < total; ++g) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (g + STAGES - 1 < total) produce();
-        cp_async_commit();
+        const bool more = g + STAGES - 1 < total;
+        if (early) {
+            if (more) produce();
+            cp_async_commit();
+        }
         const double* as = As + cs * A_STAGE;
         const double* bs = Bs + cs * B_STAGE;
         cs = (cs == STAGES - 1) ? 0 : cs + 1;
-        if (ck < nk_gemm) {
-            if (mi_count == 2) gemm_consume<2>(acc, as, bs, warp, lane);
-            else if (mi_count == 1) gemm_consume<1>(acc, as, bs, warp, lane);
-        } else {
-            switch (ck - nk_gemm) {
-                case 0: solve_chunk<0>(acc, as, bs, Dsm, warp, lane, mi_count); break;
-                case 1: solve_chunk<1>(acc, as, bs, Dsm, warp, lane, mi_count); break;
-                case 2: solve_chunk<2>(acc, as, bs, Dsm, warp, lane, mi_count); break;
-                default: solve_chunk<3>(acc, as, bs, Dsm, warp, lane, mi_count); break;
-            }
+        consume_half<0>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count);
+        if (!early) {
+            if (more) produce();
+            cp_async_commit();
         }
+        consume_half<1>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count);
         if (++ck == nkt) {
             // pass complete: store the solved rows, reset the accumulators, move to the next pass
 #pragma unroll
@@ -232,7 +253,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
                 if (mi < mi_count) {
 #pragma unroll
                     for (int ni = 0; ni < 8; ++ni)
-                        *reinterpret_cast<double2*>(M + (size_t)(row0 + warp * 16 + mi * 8 + fr) * ld + brow0 + ni * 8 +
+                        *reinterpret_cast<double2*>(M + (size_t)(row0 + wrow + mi * 8 + fr) * ld + brow0 + ni * 8 +
                                                     2 * q) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
                 }
 #pragma unroll
@@ -241,7 +262,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
             ck = 0;
             ++cb;
             row0 = first + cb * BM;
-            mi_count = max(0, min(2, (min(BM, rows - row0) - warp * 16) / 8));
+            pass_shape(row0, wrow, mi_count);
         }
     }
     cp_async_wait<0>();
@@ -249,60 +270,75 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
 }
 
 // ------------------------------------------------------------------------------------------------
-// 64 x 64 Cholesky in shared memory (T, stride TS), 8-wide panels.
+// 64 x 64 Cholesky (+ 8 augmented rows) in shared memory (T, stride TS), 8-wide panels.  Only the 8x8
+// diagonal block of a panel is factorised sequentially; everything below it is DMMA work:
+//   (a) one warp: L_d = chol(T[kb,kb]) and D_kb = L_d^-1 together, by carrying the identity as eight
+//       extra rows through the same eight column steps ([A; I] -> [L; L^-T]);
+//   (b) all warps: T[bi, kb] <- T[bi, kb] D_kb^T for the row blocks below (one 8x8 block per warp);
+//   (c) all warps: trailing update T[bi, bl] -= L[bi, kb] L[bl, kb]^T.
+// The D_kb are exactly the inverted diagonal blocks the panel solve needs afterwards.
 // ------------------------------------------------------------------------------------------------
-// Panel kb, executed by ONE warp: lane l owns rows l and l+32 of the panel's 8 columns in registers;
-// the eight column steps exchange the pivot and the pivot-block column entries with shuffles.
-// Returns 0 or the 1-based tile-local column of the first pivot <= piv_tol * diag0 (warp uniform).
-template <int SLOT>
-__device__ __forceinline__ int panel_factor(double* T, const double* diag0, int kb, double piv_tol, int lane) {
-    double v[2][8];
-    const int c0 = kb * 8;
-#pragma unroll
-    for (int s = SLOT; s < 2; ++s) {
-        const double2* src = reinterpret_cast<const double2*>(T + (lane + 32 * s) * TS + c0);
+// (a): lanes 0..7 own one row of the 8x8 block each (the other lanes mirror them).  Returns 0 or the
+// 1-based tile-local column of the first pivot <= piv_tol * diag0 (warp uniform).  The failure test is
+// recorded, not branched on: a non-positive pivot only turns the rest of the (discarded) tile into NaNs,
+// and the compare stays off the dependent chain -- every FP64 instruction of this warp queues behind
+// the other CTA's DMMAs, so the chain is kept to rsqrt, one multiply and one FMA per column.
+__device__ __forceinline__ int diag_block_factor(double* T, double* Dsm, const double* diag0, int kb, double piv_tol,
+                                                 int lane) {
+    const int r = lane & 7, grp = lane & ~7, c0 = kb * 8;
+    double v0[8], v1[8];
+    {
+        const double2* src = reinterpret_cast<const double2*>(T + (c0 + r) * TS + c0);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const double2 t = src[c];
-            v[s][2 * c] = t.x;
-            v[s][2 * c + 1] = t.y;
+            v0[2 * c] = t.x;
+            v0[2 * c + 1] = t.y;
         }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v1[c] = (c == r) ? 1.0 : 0.0;
     }
-    // The failure test is recorded, not branched on: a non-positive pivot only turns the rest of the
-    // (discarded) panel into NaNs, and keeping the compare off the dependent chain matters because every
-    // FP64 instruction of this warp queues behind the other CTA's DMMAs.
     int bad = 0;
-    double piv = __shfl_sync(0xffffffffu, v[SLOT][0], c0 & 31);
+    double piv = __shfl_sync(0xffffffffu, v0[0], grp);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const int gc = c0 + c;
-        if (!(piv > piv_tol * diag0[gc]) && bad == 0) bad = gc + 1;
-        const double rinv = rsqrt(piv);  // l_cc = piv * rinv (<= 2 ulp), rows below scale by rinv
-        double l[2];
-#pragma unroll
-        for (int s = SLOT; s < 2; ++s) {
-            l[s] = v[s][c] * rinv;
-            v[s][c] = l[s];
-        }
-        if (c < 7)  // next pivot straight from its owner lane: a_cc - l^2 is the same FMA the update below performs
-            piv = __shfl_sync(0xffffffffu, fma(-l[SLOT], l[SLOT], v[SLOT][c + 1]), (gc + 1) & 31);
+        if (!(piv > piv_tol * diag0[c0 + c]) && bad == 0) bad = c0 + c + 1;
+        const double rinv = rsqrt(piv);  // l_cc = piv * rinv (<= 2 ulp)
+        const double l0 = v0[c] * rinv, l1 = v1[c] * rinv;
+        v0[c] = l0;
+        v1[c] = l1;
+        if (c < 7)  // next pivot straight from its owner lane (the same FMA the update below performs)
+            piv = __shfl_sync(0xffffffffu, fma(-l0, l0, v0[c + 1]), grp | (c + 1));
 #pragma unroll
         for (int c2 = c + 1; c2 < 8; ++c2) {
-            const double m = __shfl_sync(0xffffffffu, l[SLOT], (c0 + c2) & 31);  // L[c0 + c2][gc]
-#pragma unroll
-            for (int s = SLOT; s < 2; ++s) v[s][c2] = fma(-l[s], m, v[s][c2]);
+            const double m = __shfl_sync(0xffffffffu, l0, grp | c2);  // L_d[c2][c]
+            v0[c2] = fma(-l0, m, v0[c2]);
+            v1[c2] = fma(-l1, m, v1[c2]);
         }
     }
+    if (lane < 8) {
+        double2* dst = reinterpret_cast<double2*>(T + (c0 + r) * TS + c0);
 #pragma unroll
-    for (int s = SLOT; s < 2; ++s) {
-        const int r = lane + 32 * s;
-        if (r >= c0) {
-            double2* dst = reinterpret_cast<double2*>(T + r * TS + c0);
+        for (int c = 0; c < 4; ++c) dst[c] = make_double2(v0[2 * c], v0[2 * c + 1]);
+        // v1 = row r of L_d^-T, i.e. column r of D = L_d^-1
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = make_double2(v[s][2 * c], v[s][2 * c + 1]);
-        }
+        for (int c = 0; c < 8; ++c) Dsm[(c0 + c) * DLD + r] = v1[c];
     }
     return bad;
+}
+
+// (b): row block bi = kb + 1 + warp (block 8 = the augmented rows) times D_kb^T, in place.
+__device__ __forceinline__ void panel_scale_blocks(double* T, const double* Dsm, int kb, int warp, int lane) {
+    const int bi = kb + 1 + warp;
+    if (bi > 8) return;
+    const int fr = lane >> 2, q = lane & 3;
+    double* row = T + (bi * 8 + fr) * TS + kb * 8;
+    const double a0 = row[q], a1 = row[4 + q];
+    const double d0 = Dsm[(kb * 8 + fr) * DLD + q], d1 = Dsm[(kb * 8 + fr) * DLD + 4 + q];
+    double x0 = 0.0, x1 = 0.0;
+    dmma884(x0, x1, a0, d0);
+    dmma884(x0, x1, a1, d1);
+    *reinterpret_cast<double2*>(row + 2 * q) = make_double2(x0, x1);
 }
 
 // trailing update after panel kb: T[bi, bl] -= L[bi, kb] L[bl, kb]^T for kb < bl <= bi, 8x8 blocks
@@ -310,8 +346,8 @@ __device__ __forceinline__ int panel_factor(double* T, const double* diag0, int 
 __device__ __forceinline__ void trailing_update(double* T, int kb, int warp, int lane) {
     const int fr = lane >> 2, q = lane & 3;
     int cnt = 0;
-    for (int bi = kb + 1; bi < 8; ++bi) {
-        for (int bl = kb + 1; bl <= bi; ++bl, ++cnt) {
+    for (int bi = kb + 1; bi < 9; ++bi) {  // block row 8 = the augmented rows
+        for (int bl = kb + 1; bl <= min(bi, 7); ++bl, ++cnt) {
             if ((cnt & 7) != warp) continue;
             double2* cp = reinterpret_cast<double2*>(T + (bi * 8 + fr) * TS + bl * 8 + 2 * q);
             double2 c = *cp;
@@ -326,63 +362,38 @@ __device__ __forceinline__ void trailing_update(double* T, int kb, int warp, int
     }
 }
 
-// D_w = inv(L_jj[w, w]) (8 x 8 lower triangular), one warp per block; lanes 0..7 own a row each
-// (the other lanes mirror them), rows finalised top-down and broadcast with shuffles.
-__device__ __forceinline__ void invert_diag_block(const double* T, double* Dsm, int w, int lane) {
-    const int r = lane & 7;
-    double Lr[8], s[8], Dr[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        Lr[m] = T[(w * 8 + r) * TS + w * 8 + m];
-        s[m] = 0.0;
-        Dr[m] = 0.0;
-    }
-    double rinv = 1.0;
-#pragma unroll
-    for (int m = 0; m < 8; ++m)
-        if (r == m) rinv = 1.0 / Lr[m];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        if (r == m) {
-#pragma unroll
-            for (int c = 0; c < m; ++c) Dr[c] = -rinv * s[c];
-            Dr[m] = rinv;
-        }
-#pragma unroll
-        for (int c = 0; c <= m; ++c) {
-            const double bm = __shfl_sync(0xffffffffu, Dr[c], (lane & ~7) | m);
-            if (r > m) s[c] = fma(Lr[m], bm, s[c]);
-        }
-    }
-    if (lane < 8) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) Dsm[(w * 8 + r) * DLD + c] = Dr[c];
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Diagonal tile update T = Psi_jj - L[j,0:j] L[j,0:j]^T, LOWER 8x8 blocks only (36 of 64).  Warp w owns
 // block row br(w) = w for w < 4 and 11 - w otherwise, so the two warps that share a scheduler carry
 // 9 blocks together and the four tensor pipes stay balanced.  A and B are the same 64 rows: only the
 // B stages are loaded.  NI = br + 1 is dispatched by a warp-uniform switch (no predicated-off DMMAs).
 // ------------------------------------------------------------------------------------------------
-template <int NI>
-__device__ __forceinline__ void diag_consume(double (&acc)[8][2], const double* Bs, int br, int lane) {
+template <int NI, bool AUG, int HALF>
+__device__ __forceinline__ void diag_consume(double (&acc)[8][2], double (&accA)[2][2], const double* Bs,
+                                             const double* Aaug, int br, int lane) {
     const int fr = lane >> 2, fc = lane & 3;
     const double* a_s = Bs + (br * 8 + fr) * SLD + fc;
     const double* b_s = Bs + fr * SLD + fc;
 #pragma unroll
-    for (int kk = 0; kk < KC; kk += 4) {
+    for (int kk = HALF * (KC / 2); kk < (HALF + 1) * (KC / 2); kk += 4) {
         const double a = negd(a_s[kk]);
         double b[NI];
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) b[ni] = b_s[ni * 8 * SLD + kk];
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) dmma884(acc[ni][0], acc[ni][1], a, b[ni]);
+        if (AUG) {
+            // the 8 augmented rows (1^T, y^T, ...) x column blocks 2*br, 2*br+1 (br == warp < 4 here)
+            const double aa = negd(Aaug[fr * SLD + fc + kk]);
+            const double b0 = b_s[(2 * br) * 8 * SLD + kk], b1 = b_s[(2 * br + 1) * 8 * SLD + kk];
+            dmma884(accA[0][0], accA[0][1], aa, b0);
+            dmma884(accA[1][0], accA[1][1], aa, b1);
+        }
     }
 }
 
-__device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j) {
+__device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j,
+                                          int np) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     const int br = (warp < 4) ? warp : 11 - warp;
@@ -392,12 +403,15 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
     const int lr = tid >> 3, lc = (tid & 7) * 2;
     const size_t ld32 = (size_t)32 * ld;
     const double* gB = M + (size_t)(row0 + lr) * ld + lc;
+    const double* gAug = M + (size_t)(np + (lr & 7)) * ld + lc;  // threads 0..63: the 8 augmented rows
     int ps = 0;
     auto produce = [&]() {
         double* bs = Bs + ps * B_STAGE + lr * SLD + lc;
         cp_async16(bs, gB);
         cp_async16(bs + 32 * SLD, gB + ld32);
+        if (tid < 64) cp_async16(pipe + ps * A_STAGE + lr * SLD + lc, gAug);
         gB += KC;
+        gAug += KC;
         ps = (ps == STAGES - 1) ? 0 : ps + 1;
     };
 #pragma unroll
@@ -418,23 +432,45 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
             acc[ni][0] = acc[ni][1] = 0.0;
         }
     }
+    double accA[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    if (warp < 4) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double2 v =
+                *reinterpret_cast<const double2*>(M + (size_t)(np + fr) * ld + row0 + (2 * warp + i) * 8 + 2 * q);
+            accA[i][0] = v.x;
+            accA[i][1] = v.y;
+        }
+    }
     for (int it = 0; it < nk; ++it) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (it + STAGES - 1 < nk) produce();
-        cp_async_commit();
-        const double* bs = Bs + cs * B_STAGE;
-        cs = (cs == STAGES - 1) ? 0 : cs + 1;
-        switch (br) {
-            case 0: diag_consume<1>(acc, bs, br, lane); break;
-            case 1: diag_consume<2>(acc, bs, br, lane); break;
-            case 2: diag_consume<3>(acc, bs, br, lane); break;
-            case 3: diag_consume<4>(acc, bs, br, lane); break;
-            case 4: diag_consume<5>(acc, bs, br, lane); break;
-            case 5: diag_consume<6>(acc, bs, br, lane); break;
-            case 6: diag_consume<7>(acc, bs, br, lane); break;
-            default: diag_consume<8>(acc, bs, br, lane); break;
+        const bool more = it + STAGES - 1 < nk;
+        if (warp < 4) {
+            if (more) produce();
+            cp_async_commit();
         }
+        const double* bs = Bs + cs * B_STAGE;
+        const double* aa = pipe + cs * A_STAGE;
+        cs = (cs == STAGES - 1) ? 0 : cs + 1;
+#define PK_DIAG_HALF(HH)                                                                        \
+        switch (warp) {                                                                         \
+            case 0: diag_consume<1, true, HH>(acc, accA, bs, aa, br, lane); break;              \
+            case 1: diag_consume<2, true, HH>(acc, accA, bs, aa, br, lane); break;              \
+            case 2: diag_consume<3, true, HH>(acc, accA, bs, aa, br, lane); break;              \
+            case 3: diag_consume<4, true, HH>(acc, accA, bs, aa, br, lane); break;              \
+            case 4: diag_consume<8, false, HH>(acc, accA, bs, aa, br, lane); break;             \
+            case 5: diag_consume<7, false, HH>(acc, accA, bs, aa, br, lane); break;             \
+            case 6: diag_consume<6, false, HH>(acc, accA, bs, aa, br, lane); break;             \
+            default: diag_consume<5, false, HH>(acc, accA, bs, aa, br, lane); break;            \
+        }
+        PK_DIAG_HALF(0)
+        if (warp >= 4) {
+            if (more) produce();
+            cp_async_commit();
+        }
+        PK_DIAG_HALF(1)
+#undef PK_DIAG_HALF
     }
     cp_async_wait<0>();
     __syncthreads();  // the stages are drained: T (aliasing the A stages) may be written
@@ -443,18 +479,24 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
         if (ni <= br)
             *reinterpret_cast<double2*>(T + (br * 8 + fr) * TS + ni * 8 + 2 * q) = make_double2(acc[ni][0], acc[ni][1]);
     }
+    if (warp < 4) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            *reinterpret_cast<double2*>(T + (PK_TILE + fr) * TS + (2 * warp + i) * 8 + 2 * q) =
+                make_double2(accA[i][0], accA[i][1]);
+    }
 }
 
 // Diagonal tile of block column j.  Returns 0 or the tile-local failing column (CTA uniform).
 __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag0, int* ctl, double* __restrict__ M,
-                                         int ld, int j, double piv_tol, long long* tm) {
+                                         int ld, int j, int np, double piv_tol, long long* tm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = j * PK_TILE;
     if (tid < PK_TILE) diag0[tid] = M[(size_t)(row0 + tid) * ld + row0 + tid];
     double* T = pipe;
     long long t0 = 0;
     if (tm) t0 = clock64();
-    diag_gemm(T, pipe, M, ld, j);
+    diag_gemm(T, pipe, M, ld, j, np);
     if (tid == 0) ctl[1] = 0;
     __syncthreads();
     if (tm) {
@@ -463,29 +505,47 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
         t0 = t1;
     }
     for (int kb = 0; kb < 8; ++kb) {
+        long long ta = 0;
+        if (tm) ta = clock64();
         if (warp == 0) {
-            const int bad = (kb < 4) ? panel_factor<0>(T, diag0, kb, piv_tol, lane)
-                                     : panel_factor<1>(T, diag0, kb, piv_tol, lane);
+            const int bad = diag_block_factor(T, Dsm, diag0, kb, piv_tol, lane);
             if (bad && lane == 0) ctl[1] = bad;
         }
         __syncthreads();
+        if (tm) {
+            const long long tb = clock64();
+            tm[5] += tb - ta;
+            ta = tb;
+        }
         if (ctl[1]) return ctl[1];
+        panel_scale_blocks(T, Dsm, kb, warp, lane);
+        __syncthreads();
+        if (tm) {
+            const long long tb = clock64();
+            tm[6] += tb - ta;
+            ta = tb;
+        }
         if (kb < 7) {
             trailing_update(T, kb, warp, lane);
             __syncthreads();
         }
+        if (tm) tm[7] += clock64() - ta;
     }
     if (tm) {
         const long long t1 = clock64();
         tm[1] += t1 - t0;
         t0 = t1;
     }
-    invert_diag_block(T, Dsm, warp, lane);
     for (int i = tid; i < PK_TILE * (PK_TILE / 2); i += THREADS) {
         const int rr = i >> 5, c2 = (i & 31) * 2;
         const double2 t = *reinterpret_cast<const double2*>(T + rr * TS + c2);
         *reinterpret_cast<double2*>(M + (size_t)(row0 + rr) * ld + row0 + c2) =
             make_double2((c2 <= rr) ? t.x : 0.0, (c2 + 1 <= rr) ? t.y : 0.0);
+    }
+    {   // the solved augmented rows: a = L^-1 1, d = L^-1 y for this block column
+        const int rr = tid >> 5, c2 = (tid & 31) * 2;
+        *reinterpret_cast<double2*>(M + (size_t)(np + rr) * ld + row0 + c2) =
+            *reinterpret_cast<const double2*>(T + (PK_TILE + rr) * TS + c2);
     }
     __syncthreads();  // L_jj is in global memory and D in shared memory for every thread of the CTA
     if (tm) tm[2] += clock64() - t0;
@@ -493,12 +553,12 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
 }
 
 // TIMING: thread 0 accumulates clock64() per phase {diag product, 64x64 factorisation, inverse + copy-out,
-// panel column, candidates} into dbg[5 * blockIdx.x ..] (diagnostic build of the same kernel).
+// panel column, candidates} into dbg[8 * blockIdx.x ..] (diagnostic build of the same kernel).
 template <bool TIMING>
 __global__ void __launch_bounds__(THREADS, 2)
 chol_cta_kernel(int C, int nt, int rows, int ld, size_t elems, double piv_tol, double* __restrict__ ws,
                 int32_t* __restrict__ info, unsigned int* __restrict__ queue, long long* __restrict__ dbg, int alias) {
-    long long tmv[5] = {0, 0, 0, 0, 0};
+    long long tmv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long* tm = TIMING ? tmv : nullptr;
     extern __shared__ __align__(16) double smem[];
     double* pipe = smem;
@@ -515,26 +575,27 @@ chol_cta_kernel(int C, int nt, int rows, int ld, size_t elems, double piv_tol, d
         if (info[cand] != 0) continue;
         double* M = ws + (size_t)(alias ? (cand & 7) : cand) * elems;  // alias: timing experiment only (results are garbage)
         for (int j = 0; j < nt; ++j) {
-            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, piv_tol, tm);
+            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, tm);
             if (bad && !alias) {
                 if (tid == 0) info[cand] = j * PK_TILE + bad;  // dpotrf convention: order of the failing minor
                 break;
             }
             long long t0 = 0;
             if (TIMING) t0 = clock64();
-            panel_column(pipe, Dsm, M, ld, j, rows);
+            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE);
             if (TIMING) tmv[3] += clock64() - t0;
         }
         if (TIMING) tmv[4] += 1;
     }
     if (TIMING && tid == 0) {
-        for (int i = 0; i < 5; ++i) dbg[5 * blockIdx.x + i] = tmv[i];
+        for (int i = 0; i < 8; ++i) dbg[8 * blockIdx.x + i] = tmv[i];
     }
 }
 
 }  // namespace cta
 
 cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
+    if (s.with_inverse || s.rows != s.np + PK_AUG_ROWS) return cudaErrorInvalidValue;  // population shape only
     const int nt = s.np / PK_TILE;
     const size_t smem = sizeof(double) * (size_t)cta::SMEM_DOUBLES;
     static bool attr_done = false;
@@ -553,21 +614,22 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
     const int grid = (C < per_sm * h->sm_count) ? C : per_sm * h->sm_count;
     if (getenv("PK_CTA_TIMING")) {  // diagnostic: per-phase cycle counts of the persistent kernel, printed to stderr
         long long* dbg = nullptr;
-        cudaMalloc((void**)&dbg, sizeof(long long) * 5 * grid);
-        cudaMemset(dbg, 0, sizeof(long long) * 5 * grid);
+        cudaMalloc((void**)&dbg, sizeof(long long) * 8 * grid);
+        cudaMemset(dbg, 0, sizeof(long long) * 8 * grid);
         cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
                                                                             ws, info, h->d_queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0);
         cudaStreamSynchronize(h->stream);
-        std::vector<long long> host(5 * (size_t)grid);
+        std::vector<long long> host(8 * (size_t)grid);
         cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
         cudaFree(dbg);
-        double sum[5] = {0, 0, 0, 0, 0};
+        double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int b2 = 0; b2 < grid; ++b2)
-            for (int i = 0; i < 5; ++i) sum[i] += (double)host[5 * b2 + i];
+            for (int i = 0; i < 8; ++i) sum[i] += (double)host[8 * b2 + i];
         fprintf(stderr,
                 "[pk cta timing] grid %d, candidates %.0f; cycles per candidate: diag product %.0f, factorise 64x64 %.0f, "
-                "inverse+copy %.0f, panel column %.0f\n",
-                grid, sum[4], sum[0] / sum[4], sum[1] / sum[4], sum[2] / sum[4], sum[3] / sum[4]);
+                "copy-out %.0f, panel column %.0f; factorise = 8x8 block %.0f + scale %.0f + trailing %.0f\n",
+                grid, sum[4], sum[0] / sum[4], sum[1] / sum[4], sum[2] / sum[4], sum[3] / sum[4], sum[5] / sum[4],
+                sum[6] / sum[4], sum[7] / sum[4]);
     } else {
         cta::chol_cta_kernel<false><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(),
                                                                              h->pivot_tol, ws, info, h->d_queue, nullptr, 0);

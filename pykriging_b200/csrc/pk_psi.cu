@@ -117,18 +117,21 @@ __device__ __forceinline__ void log2_split(double d, double& L, float& res) {
 __constant__ double c_e2[5] = {0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58fp-3, 0x1.c6b08d704a0c0p-5,
                                0x1.3b2ab6fba4e77p-7, 0x1.5d87fe78a6731p-10};
 
-__device__ __forceinline__ double exp2_lean(double s, double e, const char* __restrict__ tabp) {
-    const double kd = s + MAGIC64;
-    const int ki = __double2loint(kd);
+// 2^(pd * (lh + ll)): the product never appears as a rounded double -- the reduction constant is added
+// inside the FMA (kd), and the reduced argument r = pd*lh - kf + pd*ll is formed by two FMAs, each exact
+// product rounded once at magnitude <= 2^-7 (absolute error < 2^-60).  10 FP64 instructions.
+__device__ __forceinline__ double exp2_lean(double pd, double lh, double ll, const char* __restrict__ tabp) {
+    const double kd = fma(pd, lh, MAGIC64);
+    const int ki = __double2loint(kd);          // round(64 * pd * lh) in the low mantissa bits
     const double kf = kd - MAGIC64;
-    const double r = (s - kf) + e;
+    double r = fma(pd, lh, -kf);
+    r = fma(pd, ll, r);
     double q = fma(r, c_e2[4], c_e2[3]);
     q = fma(r, q, c_e2[2]);
     q = fma(r, q, c_e2[1]);
     q = fma(r, q, c_e2[0]);
-    q = q * r;
     const double T = *reinterpret_cast<const double*>(tabp + ((ki & 63) << 7));
-    const double v = fma(T, q, T);
+    const double v = fma(T * r, q, T);
     const int n = min(max(ki >> 6, -1022), 1023);
     return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
 }
@@ -145,7 +148,8 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
     constexpr int SPT = PK_TILE / RB;                // row blocks per tile
     __shared__ double tab[64 * 16];
     __shared__ double Xr[RB * K], Xc[PK_TILE * K];
-    __shared__ double th[PSI_GROUP * K], pp[PSI_GROUP * K], dg[PSI_GROUP];
+    __shared__ double2 thp[PSI_GROUP * K];  // (theta_d, p_d) pairs: one 16-byte broadcast load per (candidate, dimension)
+    __shared__ double dg[PSI_GROUP];
     __shared__ int spec[PSI_GROUP];  // candidate has an exponent that is exactly 1 or 2 (exact d / d*d path)
     const int tid = threadIdx.x, bank = tid & 15;
     // block -> (lower tile, row block)
@@ -168,8 +172,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
         Xc[i] = (c0 + rr < n) ? X[(size_t)(c0 + rr) * K + (i % K)] : 0.0;
     }
     for (int i = tid; i < gn * K; i += PSI_THREADS) {
-        th[i] = theta[(size_t)g0 * K + i];
-        pp[i] = p[(size_t)g0 * K + i];
+        thp[i] = make_double2(theta[(size_t)g0 * K + i], p[(size_t)g0 * K + i]);
     }
     if (tid < gn) {
         dg[tid] = 1.0 + (mode == PK_MODE_REGRESSION ? lambda[g0 + tid] : PK_EPS_DIAG);
@@ -205,34 +208,49 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
 
     for (int g = 0; g < gn; ++g) {
         double out[PPT];
-        const double* thg = th + g * K;
-        const double* ppg = pp + g * K;
+        const double2* tpg = thp + g * K;
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
             const int gc = c0 + lc + q;
             double v;
             if (live[q] && !spec[g]) {
                 // generic exponents: k table-driven 2^x, theta folded in with an FMA, NumPy's summation tree
-                auto w = [&](int d) {
-                    const double pd = ppg[d];
-                    const double s = pd * lh[q][d];
-                    const double e = fma(pd, (double)ll[q][d], fma(pd, lh[q][d], -s));
-                    return exp2_lean(s, e, tabp);
+                // term(d) = theta_d * |d|^p_d
+                auto tw = [&](int d, double& th_d) {
+                    const double2 tp = tpg[d];
+                    th_d = tp.x;
+                    return exp2_lean(tp.y, lh[q][d], (double)ll[q][d], tabp);
                 };
                 double S;
                 if (K < 8) {
                     S = 0.0;
 #pragma unroll
-                    for (int d = 0; d < K; ++d) S = fma(thg[d], w(d), S);
+                    for (int d = 0; d < K; ++d) {
+                        double t;
+                        const double wv = tw(d, t);
+                        S = fma(t, wv, S);
+                    }
                 } else {
                     double r[8];
 #pragma unroll
-                    for (int d = 0; d < 8; ++d) r[d] = thg[d] * w(d);
+                    for (int d = 0; d < 8; ++d) {
+                        double t;
+                        const double wv = tw(d, t);
+                        r[d] = t * wv;
+                    }
 #pragma unroll
-                    for (int d = 8; d < K - (K % 8); ++d) r[d & 7] = fma(thg[d], w(d), r[d & 7]);
+                    for (int d = 8; d < K - (K % 8); ++d) {
+                        double t;
+                        const double wv = tw(d, t);
+                        r[d & 7] = fma(t, wv, r[d & 7]);
+                    }
                     S = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
 #pragma unroll
-                    for (int d = K - (K % 8); d < K; ++d) S = fma(thg[d], w(d), S);
+                    for (int d = K - (K % 8); d < K; ++d) {
+                        double t;
+                        const double wv = tw(d, t);
+                        S = fma(t, wv, S);
+                    }
                 }
                 v = expneg_table(S, tab, bank);
             } else if (live[q]) {
@@ -241,7 +259,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                 double term[K];
 #pragma unroll
                 for (int d = 0; d < K; ++d) {
-                    const double pd = ppg[d];
+                    const double pd = tpg[d].y;
                     double w;
                     if (pd == 2.0) {
                         const double dd = fabs(Xr[lr * K + d] - Xc[(lc + q) * K + d]);
@@ -253,7 +271,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                         const double e = fma(pd, (double)ll[q][d], fma(pd, lh[q][d], -s));
                         w = exp2_table(s, e, tab, bank);
                     }
-                    term[d] = thg[d] * w;
+                    term[d] = tpg[d].x * w;
                 }
                 const double S = sum_numpy_order(K, [&](int d) { return term[d]; });
                 v = expneg_table(S, tab, bank);
@@ -289,7 +307,8 @@ __global__ void debug_math_kernel(int64_t m, const double* __restrict__ d, const
         const double s = p[i] * lh;
         const double e = fma(p[i], (double)ll, fma(p[i], lh, -s));
         // odd elements go through the lean (hot-loop) variant, even ones through the range-checked one
-        out_pow[i] = (i & 1) ? exp2_lean(s, e, reinterpret_cast<const char*>(tab + bank)) : exp2_table(s, e, tab, bank);
+        out_pow[i] = (i & 1) ? exp2_lean(p[i], lh, (double)ll, reinterpret_cast<const char*>(tab + bank))
+                             : exp2_table(s, e, tab, bank);
         out_expneg[i] = expneg_table(d[i], tab, bank);
     }
 }
