@@ -139,8 +139,11 @@ __device__ __forceinline__ double exp2_lean(double pd, double lh, double ll, con
 constexpr int PSI_THREADS = 256;
 constexpr int PSI_GROUP = 64;  // candidates per CTA (amortises the log2 split of the CTA's pairs)
 
+// PPT pairs per thread: large K keeps ONE pair per thread so that the per-pair log2 tables (3 registers per
+// dimension) leave room for three resident CTAs per SM -- the per-candidate 2^x chain is latency bound and
+// needs the extra warps more than it needs wider stores.
 template <int K, int PPT>
-__global__ void __launch_bounds__(PSI_THREADS)
+__global__ void __launch_bounds__(PSI_THREADS, (PPT == 1) ? (K <= 12 ? 3 : 2) : 1)
 psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restrict__ X,
                const double* __restrict__ theta, const double* __restrict__ p,
                const double* __restrict__ lambda, int mode, double* __restrict__ ws) {
@@ -286,8 +289,10 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
         if (PPT == 4) {
             reinterpret_cast<double2*>(dst)[0] = make_double2(out[0], out[1]);
             reinterpret_cast<double2*>(dst)[1] = make_double2(out[2 % PPT], out[3 % PPT]);
-        } else {
+        } else if (PPT == 2) {
             reinterpret_cast<double2*>(dst)[0] = make_double2(out[0], out[1 % PPT]);
+        } else {
+            dst[0] = out[0];  // a warp still writes 256 contiguous bytes
         }
     }
     (void)any_live;
@@ -329,7 +334,7 @@ cudaError_t launch_aug_init(pk_handle* h, const TiledShape& s, int C, double* ws
 template <int K>
 static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
                                   const double* lambda, int mode, double* ws) {
-    constexpr int PPT = (K > 6) ? 2 : 4;
+    constexpr int PPT = (K > 6) ? 1 : 4;
     constexpr int RB = PSI_THREADS * PPT / PK_TILE;
     const int nt = s.np / PK_TILE;
     dim3 grid(nt * (nt + 1) / 2 * (PK_TILE / RB), (C + PSI_GROUP - 1) / PSI_GROUP);
