@@ -125,6 +125,12 @@ int pk_set_pivot_tolerance(pk_handle *h, double tol);
  * per candidate (populations with at least as many candidates as SMs). */
 int pk_set_cholesky_variant(pk_handle *h, int variant);
 
+/* Tuning / test knob for the fused predictor behind pk_predict_batch (predict_normalized /
+ * predicterr_normalized / expimp loops, matrixops.py:68-95, krige.py:201-258): 0 = automatic,
+ * 1 = psi tile in shared memory + L^-1 streamed through shared memory (any n up to 2944),
+ * 2 = v = L^-1 psi held in registers, psi chunks generated on the fly (n <= 512; falls back otherwise). */
+int pk_set_predict_variant(pk_handle *h, int variant);
+
 /* Phase timing for roofline accounting (bench.py): when enabled, CUDA events are recorded on the
  * handle's stream around the phases of every pk_nll_batch / pk_predict_batch call.
  * pk_phase_times() synchronises, ADDS the elapsed milliseconds since the last call into

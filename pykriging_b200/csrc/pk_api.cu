@@ -185,6 +185,12 @@ int pk_set_cholesky_variant(pk_handle* h, int variant) {
     return 0;
 }
 
+int pk_set_predict_variant(pk_handle* h, int variant) {
+    if (!h || variant < 0 || variant > 2) return 1;
+    h->predict_variant = variant;
+    return 0;
+}
+
 int pk_debug_math(pk_handle* h, int64_t m, const double* d, const double* p, double* out_pow, double* out_expneg) {
     if (!h || m < 0 || !d || !p || !out_pow || !out_expneg) return 1;
     if (m == 0) return 0;

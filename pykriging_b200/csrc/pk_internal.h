@@ -21,6 +21,7 @@ struct pk_handle {
     size_t ev_used = 0;
     double pivot_tol = 2.0 * PK_EPS_DIAG;  // relative pivot threshold, 2 ulps (see pk_set_pivot_tolerance)
     int chol_variant = 0;                  // 0 auto, 1 one launch per block column, 2 persistent CTA per candidate
+    int predict_variant = 0;               // 0 auto, 1 shared-memory psi tile kernel (any n), 2 register-resident (n <= 512)
     unsigned int* d_queue = nullptr;       // candidate queue of the persistent Cholesky kernel
 
     // model data (pk_set_data)

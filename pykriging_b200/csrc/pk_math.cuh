@@ -1,0 +1,141 @@
+// Table-driven FP64 transcendentals shared by the Psi and predictor kernels: log2 split, 2^x, e^-S.
+// They replace np.power / np.exp of matrixops.py:28,70 (glibc, < 1 ulp) with < 2 ulp (pow) and < 1.5 ulp
+// (exp) implementations whose hot part is branch free (tests/test_gpu_parity.py::test_device_pow_and_exp_accuracy).
+#pragma once
+#include "pk_common.cuh"
+#include "pk_exp2_table.h"
+
+namespace pk {
+
+// 2^(j/64) as hi + lo (mpmath-generated, tools/gen_exp2_table.py) and the log2(1+z) series
+static __constant__ double c_exp2_hi[64] = {PK_EXP2_HI_LIST};
+static __constant__ double c_exp2_lo[64] = {PK_EXP2_LO_LIST};
+static __constant__ double c_log2p1[9] = {PK_LOG2P1_LIST};
+static __constant__ double c_l2c_rc[64] = {PK_LOG2C_RC_LIST};
+static __constant__ double c_l2c_hi[64] = {PK_LOG2C_HI_LIST};
+static __constant__ double c_l2c_lo[64] = {PK_LOG2C_LO_LIST};
+
+// ---- table-driven 2^x and e^-S ----------------------------------------------------------------------
+// tab = shared copy of g_exp2_table replicated over the 16 eight-byte banks: tab[j * 16 + (lane & 15)]
+// is conflict free for any j pattern.
+constexpr double MAGIC64 = 6755399441055744.0 / 64.0;  // 1.5 * 2^52 / 64: rounds to multiples of 1/64
+constexpr double MAGIC1 = 6755399441055744.0;          // 1.5 * 2^52
+
+__device__ __forceinline__ double scale_pow2(double v, int n) {
+    // v in [1, 2): returns v * 2^n with flush-to-zero below the normal range and inf above it
+    if (n < -1021) return 0.0;
+    if (n > 1022) return CUDART_INF;
+    const long long bits = __double_as_longlong(v) + ((long long)n << 52);
+    return __longlong_as_double(bits);
+}
+
+// 2^(s + e) where s is a double and e a tiny correction (|e| << 1/64)
+__device__ __forceinline__ double exp2_table(double s, double e, const double* __restrict__ tab, int bank) {
+    const double kd = s + MAGIC64;
+    const int ki = __double2loint(kd);          // round(s * 64) in the low mantissa bits
+    const double kf = kd - MAGIC64;             // round(s * 64) / 64
+    const double r = (s - kf) + e;              // |r| <= 1/128 (+ e)
+    // 2^r - 1 = r (c1 + r (c2 + r (c3 + r (c4 + r c5)))), |r| <= 2^-7: truncation < 2^-56
+    double q = fma(r, 0x1.5d87fe78a6731p-10, 0x1.3b2ab6fba4e77p-7);  // ln2^5/120, ln2^4/24
+    q = fma(r, q, 0x1.c6b08d704a0c0p-5);                              // ln2^3/6
+    q = fma(r, q, 0x1.ebfbdff82c58fp-3);                              // ln2^2/2
+    q = fma(r, q, 0x1.62e42fefa39efp-1);                              // ln2
+    q = q * r;
+    const double T = tab[(ki & 63) * 16 + bank];
+    return scale_pow2(fma(T, q, T), ki >> 6);
+}
+
+// e^(-S), S >= 0 (also fine for negative S), Cody-Waite reduction with ln2/64 split in two
+__device__ __forceinline__ double expneg_table(double S, const double* __restrict__ tab, int bank) {
+    const double t = S * -0x1.71547652b82fep+6;  // -64 / ln 2
+    const double kd = t + MAGIC1;
+    const int ki = __double2loint(kd);
+    const double kf = kd - MAGIC1;              // k = round(-S * 64 / ln2)
+    // r = -S - k * ln2/64  (hi part has 21 trailing zero bits: k * hi is exact for |k| < 2^21)
+    double r = fma(kf, -0x1.62e42fee00000p-7, -S);   // fdlibm ln2HI / 64
+    r = fma(kf, -0x1.a39ef35793c76p-39, r);          // fdlibm ln2LO / 64
+    // e^r - 1 = r + r^2/2 + r^3/6 + r^4/24 + r^5/120, |r| <= ln2/128
+    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    q = fma(r, q, 1.6666666666666666e-01);
+    q = fma(r, q, 0.5);
+    q = fma(r, q, 1.0);
+    q = q * r;
+    const double T = tab[(ki & 63) * 16 + bank];
+    if (!(S < 1.0e6)) return (S != S) ? S : 0.0;  // NaN propagates, huge S underflows
+    return scale_pow2(fma(T, q, T), ki >> 6);
+}
+
+// log2 d as an unevaluated sum L + res with L = fl(log2 d) and |res| <= ulp(L)/2, accurate to ~2^-59
+// ABSOLUTE (not relative to L): d = 2^E m, m in [1,2); the top six mantissa bits j select the centre
+// c_j = 1 + (2j+1)/128 of m's 1/64-wide interval, z = (m - c_j) / c_j (m - c_j is exact, 1/c_j is tabulated),
+// log2 d = (E + hi_j) + (lo_j + log2(1 + z)) with log2 c_j = hi_j + lo_j tabulated (hi_j on a 2^-40 grid, so
+// E + hi_j is exact) and a degree-9 series for log2(1 + z), |z| <= 2^-7.  No division, no libm call.
+// Runs once per (pair, dimension) per CTA, never in the candidate loop.
+__device__ __forceinline__ void log2_split(double d, double& L, float& res) {
+    if (!(d >= 2.2250738585072014e-308)) {  // pow(0, p > 0) = 0: a hugely negative exponent underflows to 0
+        L = -1100.0;
+        res = 0.0f;
+        return;
+    }
+    const int hi = __double2hiint(d);
+    const int E = ((hi >> 20) & 0x7ff) - 1023;
+    const int j = (hi >> 14) & 63;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(d));
+    const double c = fma((double)(2 * j + 1), 0.0078125, 1.0);  // exact
+    const double z = (m - c) * c_l2c_rc[j];
+    double q = c_log2p1[8];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) q = fma(q, z, c_log2p1[i]);
+    const double t = fma(q, z, c_l2c_lo[j]);     // lo_j + log2(1 + z)
+    const double lh = (double)E + c_l2c_hi[j];   // exact
+    L = lh + t;
+    const double bb = L - lh;                    // TwoSum: (lh + t) = L + r exactly
+    const double r = (lh - (L - bb)) + (t - bb);
+    res = (float)r;
+}
+
+// ---- lean 2^x for the candidate loop ---------------------------------------------------------------
+// Same arithmetic as exp2_table, written so that the hot loop carries no branches, no 64-bit immediates
+// (the polynomial lives in the constant bank and is read as a DFMA operand) and no address
+// re-computation: `tabp` is the byte address of this lane's bank copy of the 2^(j/64) table.  The
+// result is scaled by adding the clamped binary exponent to the high word, so anything below
+// 2^-1022 comes out as ~1e-308 instead of 0 (it is then multiplied by theta <= 100 and added to a
+// sum that is >= 0: indistinguishable from pow(0, p) = 0 in every Psi entry) .
+static __constant__ double c_e2[5] = {0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58fp-3, 0x1.c6b08d704a0c0p-5,
+                               0x1.3b2ab6fba4e77p-7, 0x1.5d87fe78a6731p-10};
+
+// 2^(pd * (lh + ll)): the product never appears as a rounded double -- the reduction constant is added
+// inside the FMA (kd), and the reduced argument r = pd*lh - kf + pd*ll is formed by two FMAs, each exact
+// product rounded once at magnitude <= 2^-7 (absolute error < 2^-60).  10 FP64 instructions.
+__device__ __forceinline__ double exp2_lean(double pd, double lh, double ll, const char* __restrict__ tabp) {
+    const double kd = fma(pd, lh, MAGIC64);
+    const int ki = __double2loint(kd);          // round(64 * pd * lh) in the low mantissa bits
+    const double kf = kd - MAGIC64;
+    double r = fma(pd, lh, -kf);
+    r = fma(pd, ll, r);
+    double q = fma(r, c_e2[4], c_e2[3]);
+    q = fma(r, q, c_e2[2]);
+    q = fma(r, q, c_e2[1]);
+    q = fma(r, q, c_e2[0]);
+    const double T = *reinterpret_cast<const double*>(tabp + ((ki & 63) << 7));
+    const double v = fma(T * r, q, T);
+    const int n = min(max(ki >> 6, -1022), 1023);
+    return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
+}
+
+// fill the bank-replicated shared copy of the 2^(j/64) table (64 x 16 doubles); caller synchronises
+__device__ __forceinline__ void fill_exp2_table(double* tab, int tid, int nthreads) {
+    for (int i = tid; i < 64 * 16; i += nthreads) tab[i] = c_exp2_hi[i >> 4];
+}
+
+// |d|^p with the reference's exact special cases (pk_common.cuh pow_abs) and the table-driven general path
+__device__ __forceinline__ double pow_abs_lean(double d, double p, const char* tabp) {
+    if (p == 2.0) return d * d;
+    if (p == 1.0) return d;
+    double lh;
+    float ll;
+    log2_split(d, lh, ll);
+    return exp2_lean(p, lh, (double)ll, tabp);
+}
+
+}  // namespace pk

@@ -11,6 +11,7 @@
 //     s     = sqrt(|SigmaSqr (1 + extra - q)|),  EI(yhat, s, y_min)
 // HBM traffic per query: 8k bytes in, 8..24 bytes out; L^-1 (n^2/2 doubles) streams from L2.
 #include "pk_internal.h"
+#include "pk_math.cuh"
 
 namespace pk {
 
@@ -212,6 +213,161 @@ predict_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X, co
     }
 }
 
+
+// ---- fused predictor, register-resident variant (n <= 512) ------------------------------------------
+// v = L^-1 psi for a tile of 32 query points is held ENTIRELY in accumulator registers: warp w owns the
+// 8-column blocks {w, w+8, w+16, ..} of v (one block per 64 columns, NT = np/64 of them) for all 32 queries,
+// i.e. 4 x NT DMMA tiles = 64 FP64 accumulators per thread at n = 512.  The K loop runs over the samples
+// r in chunks of 16: the psi chunk (32 queries x 16 samples) is computed on the fly into a double-buffered
+// shared-memory A stage (it never exists as a whole tile), the B operand L^-1[c, r] is read straight from
+// L2 into registers -- each element is used by exactly one warp, so staging it through shared memory would
+// buy nothing -- and software-prefetched one k-step ahead.  Column blocks left of the chunk are skipped
+// (L^-1 is lower triangular) by dispatching on the first live block through a warp-uniform switch; because
+// every warp owns a slice of every 64-column tile, the triangular saving is spread evenly over the warps.
+constexpr int PR_QT = 32;
+constexpr int PR_KC = 16;
+constexpr int PR_ALD = PR_KC + 4;
+
+template <int NT, int LO>
+__device__ __forceinline__ void pred_consume(double (&acc)[4][NT][2], double (&breg)[2][NT], const double* As,
+                                             const double* __restrict__ brow, size_t ni_stride, int kcol,
+                                             bool prefetch_next_chunk, int lane) {
+    const int fr = lane >> 2, fc = lane & 3;
+    const double* a_s = As + fr * PR_ALD + fc;
+#pragma unroll
+    for (int ks = 0; ks < PR_KC / 4; ++ks) {
+        // prefetch the B fragments of the next k-step (next chunk's first step from the last one)
+        if (ks < PR_KC / 4 - 1 || prefetch_next_chunk) {
+#pragma unroll
+            for (int ni = LO; ni < NT; ++ni) breg[(ks + 1) & 1][ni] = __ldg(brow + ni * ni_stride + kcol + 4 * (ks + 1));
+        }
+        double a[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[mi * 8 * PR_ALD + 4 * ks];
+#pragma unroll
+        for (int ni = LO; ni < NT; ++ni) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], breg[ks & 1][ni]);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(PRED_THREADS, 1)
+predict_reg_kernel(int n, int k, int64_t m, const double* __restrict__ X, const double* __restrict__ Xq,
+                   const double* __restrict__ hp, const double* __restrict__ linv, const double* __restrict__ w,
+                   double mu, double sigma2, double y_min, double ei_weight, double var_extra, int need_s,
+                   double* __restrict__ yhat_out, double* __restrict__ s_out, double* __restrict__ ei_out) {
+    constexpr int np = NT * PK_TILE;
+    __shared__ double tab[64 * 16];
+    __shared__ double As[2][PR_QT * PR_ALD];
+    __shared__ double xq[PR_QT * PK_MAX_K];
+    __shared__ double2 thp[PK_MAX_K];
+    __shared__ double ypart[8][PR_QT];
+    __shared__ double qpart[8][PR_QT + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int64_t q0 = (int64_t)blockIdx.x * PR_QT;
+    const int qv = (int)min((int64_t)PR_QT, m - q0);
+
+    fill_exp2_table(tab, tid, PRED_THREADS);
+    for (int i = tid; i < PR_QT * k; i += PRED_THREADS) {
+        const int q = i / k;
+        xq[q * PK_MAX_K + (i - q * k)] = (q < qv) ? Xq[q0 * k + i] : 0.0;
+    }
+    if (tid < k) thp[tid] = make_double2(hp[tid], hp[PK_MAX_K + tid]);
+    __syncthreads();
+    const char* tabp = reinterpret_cast<const char*>(tab + (tid & 15));
+
+    // psi producer: this thread owns query pq and samples ps0, ps0 + 8 of every chunk
+    const int pq = lane, ps0 = warp;
+    double ys = 0.0;
+    auto make_psi = [&](int kc, double* dst) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = kc * PR_KC + ps0 + 8 * h;
+            double v = 0.0;
+            if (r < n && pq < qv) {
+                const double* xr = X + (size_t)r * k;
+                const double* xqq = xq + pq * PK_MAX_K;
+                const double S = sum_numpy_order(k, [&](int d) {
+                    const double2 tp = thp[d];
+                    return tp.x * pow_abs_lean(fabs(__ldg(xr + d) - xqq[d]), tp.y, tabp);
+                });
+                v = expneg_table(S, tab, tid & 15);
+                ys = fma(v, __ldg(w + r), ys);
+            }
+            dst[pq * PR_ALD + ps0 + 8 * h] = v;
+        }
+    };
+
+    constexpr int NCH = np / PR_KC;
+    double acc[4][NT][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    double breg[2][NT];
+    // B fragment base: row (8 warp + fr) of the first 64-column tile, k offset fc; block ni adds 64 rows
+    const double* brow = linv + (size_t)(8 * warp + fr) * np + fc;
+    const size_t ni_stride = (size_t)PK_TILE * np;
+    if (need_s) {
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) breg[0][ni] = __ldg(brow + ni * ni_stride);
+    }
+    make_psi(0, As[0]);
+    for (int kc = 0; kc < NCH; ++kc) {
+        __syncthreads();  // chunk kc of psi is complete; the other A stage is free again
+        if (kc + 1 < NCH) make_psi(kc + 1, As[(kc + 1) & 1]);
+        if (need_s) {
+            const int num = PR_KC * kc - 8 * warp + 56;
+            const int lo = (num <= 0) ? 0 : (num >> 6);
+            const bool pf = kc + 1 < NCH;
+            const double* as = As[kc & 1];
+            const int kcol = PR_KC * kc;
+            switch (lo) {
+#define PK_PRED_CASE(LL)                                                                              \
+                case LL:                                                                              \
+                    if (LL < NT) pred_consume<NT, (LL < NT ? LL : 0)>(acc, breg, as, brow, ni_stride, kcol, pf, lane); \
+                    break;
+                PK_PRED_CASE(0) PK_PRED_CASE(1) PK_PRED_CASE(2) PK_PRED_CASE(3)
+                PK_PRED_CASE(4) PK_PRED_CASE(5) PK_PRED_CASE(6) PK_PRED_CASE(7)
+#undef PK_PRED_CASE
+                default: break;
+            }
+        }
+    }
+    // ---- reductions: yhat partials over the 8 sample slots, |v|^2 over columns ---------------------
+    ypart[warp][lane] = ys;
+    if (need_s) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            double v = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) v += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (fc == 0) qpart[warp][mi * 8 + fr] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < qv) {
+        double ysum = 0.0, qs = 0.0;
+#pragma unroll
+        for (int z = 0; z < 8; ++z) ysum += ypart[z][tid];
+        const double yhat = mu + ysum;
+        if (yhat_out) yhat_out[q0 + tid] = yhat;
+        if (need_s) {
+#pragma unroll
+            for (int z = 0; z < 8; ++z) qs += qpart[z][tid];
+            const double ssqr = sigma2 * (1.0 + var_extra - qs);
+            const double S = sqrt(fabs(ssqr));
+            if (s_out) s_out[q0 + tid] = S;
+            if (ei_out) ei_out[q0 + tid] = expected_improvement(yhat, S, y_min, ei_weight);
+        }
+    }
+}
+
 // ---- launchers -------------------------------------------------------------------------------------
 cudaError_t launch_fit_finalize(pk_handle* h, const TiledShape& s) {
     dim3 grid(s.np / 32, s.np / 32), block(32, 8);
@@ -259,10 +415,30 @@ static cudaError_t launch_predict_t(pk_handle* h, int64_t m, const double* Xq, c
     return cudaGetLastError();
 }
 
+template <int NT>
+static cudaError_t launch_predict_reg(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu,
+                                      double sigma2, double y_min, double ei_weight, double var_extra, double* yhat,
+                                      double* sout, double* ei) {
+    const int need_s = (sout != nullptr || ei != nullptr) ? 1 : 0;
+    const int64_t blocks = (m + PR_QT - 1) / PR_QT;
+    predict_reg_kernel<NT><<<(unsigned)blocks, PRED_THREADS, 0, h->stream>>>(h->n, h->k, m, h->dX, Xq, hp, h->d_linv,
+                                                                            h->d_w, mu, sigma2, y_min, ei_weight,
+                                                                            var_extra, need_s, yhat, sout, ei);
+    h->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
                            double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
                            double* ei) {
     const int np = h->fit_np;
+    if (np <= 512 && h->predict_variant != 1) {
+        switch (np / PK_TILE) {
+#define PK_PR(NN) case NN: return launch_predict_reg<NN>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+            PK_PR(1) PK_PR(2) PK_PR(3) PK_PR(4) PK_PR(5) PK_PR(6) PK_PR(7) PK_PR(8)
+#undef PK_PR
+        }
+    }
     if (np <= 512) return launch_predict_t<32>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
     if (np <= 1280) return launch_predict_t<16>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
     if (np <= 3072) return launch_predict_t<8>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
