@@ -123,18 +123,51 @@ __device__ __forceinline__ double exp2_lean(double pd, double lh, double ll, con
     return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
 }
 
+// log2_split with the three 64-entry tables in a bank-replicated shared-memory copy (ltab = 3 x 64 x 16
+// doubles filled by fill_log2_tables; bank = lane & 15): for kernels that take a log2 per (query, sample,
+// dimension) -- a constant-bank lookup with a per-lane index serialises, this one does not.
+__device__ __forceinline__ void log2_split_smem(double d, const double* __restrict__ ltab, int bank, double& L,
+                                                float& res) {
+    const bool zero = !(d >= 2.2250738585072014e-308);
+    const int hi = __double2hiint(d);
+    const int E = ((hi >> 20) & 0x7ff) - 1023;
+    const int j = (hi >> 14) & 63;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(d));
+    const double c = fma((double)(2 * j + 1), 0.0078125, 1.0);  // exact
+    const double* e = ltab + j * 16 + bank;
+    const double z = (m - c) * e[0];
+    double q = c_log2p1[8];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) q = fma(q, z, c_log2p1[i]);
+    const double t = fma(q, z, e[2 * 1024]);
+    const double lh = (double)E + e[1024];
+    const double Ls = lh + t;
+    const double bb = Ls - lh;
+    const double r = (lh - (Ls - bb)) + (t - bb);
+    L = zero ? -1100.0 : Ls;   // pow(0, p > 0) = 0: a hugely negative exponent underflows to 0
+    res = zero ? 0.0f : (float)r;
+}
+
+__device__ __forceinline__ void fill_log2_tables(double* ltab, int tid, int nthreads) {
+    for (int i = tid; i < 64 * 16; i += nthreads) {
+        ltab[i] = c_l2c_rc[i >> 4];
+        ltab[1024 + i] = c_l2c_hi[i >> 4];
+        ltab[2048 + i] = c_l2c_lo[i >> 4];
+    }
+}
+
 // fill the bank-replicated shared copy of the 2^(j/64) table (64 x 16 doubles); caller synchronises
 __device__ __forceinline__ void fill_exp2_table(double* tab, int tid, int nthreads) {
     for (int i = tid; i < 64 * 16; i += nthreads) tab[i] = c_exp2_hi[i >> 4];
 }
 
 // |d|^p with the reference's exact special cases (pk_common.cuh pow_abs) and the table-driven general path
-__device__ __forceinline__ double pow_abs_lean(double d, double p, const char* tabp) {
+__device__ __forceinline__ double pow_abs_lean(double d, double p, const char* tabp, const double* ltab, int bank) {
     if (p == 2.0) return d * d;
     if (p == 1.0) return d;
     double lh;
     float ll;
-    log2_split(d, lh, ll);
+    log2_split_smem(d, ltab, bank, lh, ll);
     return exp2_lean(p, lh, (double)ll, tabp);
 }
 

@@ -215,23 +215,26 @@ predict_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X, co
 
 
 // ---- fused predictor, register-resident variant (n <= 512) ------------------------------------------
-// v = L^-1 psi for a tile of 32 query points is held ENTIRELY in accumulator registers: warp w owns the
-// 8-column blocks {w, w+8, w+16, ..} of v (one block per 64 columns, NT = np/64 of them) for all 32 queries,
-// i.e. 4 x NT DMMA tiles = 64 FP64 accumulators per thread at n = 512.  The K loop runs over the samples
-// r in chunks of 16: the psi chunk (32 queries x 16 samples) is computed on the fly into a double-buffered
-// shared-memory A stage (it never exists as a whole tile), the B operand L^-1[c, r] is read straight from
-// L2 into registers -- each element is used by exactly one warp, so staging it through shared memory would
-// buy nothing -- and software-prefetched one k-step ahead.  Column blocks left of the chunk are skipped
-// (L^-1 is lower triangular) by dispatching on the first live block through a warp-uniform switch; because
-// every warp owns a slice of every 64-column tile, the triangular saving is spread evenly over the warps.
+// v = L^-1 psi for a tile of 32 query points is held ENTIRELY in accumulator registers: the 16 warps of a
+// CTA split the columns of v in 8-column blocks, block b -> warp b % 16 (so every warp owns a slice of every
+// 128 columns and the triangular saving of L^-1 is spread evenly), 4 x NTW DMMA tiles per warp.  The K loop
+// runs over the samples r in chunks of 16: the psi chunk (32 queries x 16 samples, one value per thread) is
+// computed on the fly into a double-buffered shared-memory A stage -- psi never exists as a whole tile --
+// and the B operand L^-1[c, r] is read straight from L2 into registers (each element is used by exactly one
+// warp, so staging it through shared memory would buy nothing), software-prefetched one k-step ahead.
+// Column blocks left of the chunk are skipped by dispatching on the first live block through a
+// warp-uniform switch (a predicated-off DMMA would still occupy the tensor pipe).  Four warps per
+// scheduler: while one warp walks the latency-bound psi chain the others issue DMMAs.
+constexpr int PR_THREADS = 512;
+constexpr int PR_WARPS = PR_THREADS / 32;
 constexpr int PR_QT = 32;
 constexpr int PR_KC = 16;
 constexpr int PR_ALD = PR_KC + 4;
 
-template <int NT, int LO>
-__device__ __forceinline__ void pred_consume(double (&acc)[4][NT][2], double (&breg)[2][NT], const double* As,
+template <int NTW, int LO>
+__device__ __forceinline__ void pred_consume(double (&acc)[4][NTW][2], double (&breg)[2][NTW], const double* As,
                                              const double* __restrict__ brow, size_t ni_stride, int kcol,
-                                             bool prefetch_next_chunk, int lane) {
+                                             bool prefetch_next_chunk, unsigned valid_mask, int lane) {
     const int fr = lane >> 2, fc = lane & 3;
     const double* a_s = As + fr * PR_ALD + fc;
 #pragma unroll
@@ -239,112 +242,155 @@ __device__ __forceinline__ void pred_consume(double (&acc)[4][NT][2], double (&b
         // prefetch the B fragments of the next k-step (next chunk's first step from the last one)
         if (ks < PR_KC / 4 - 1 || prefetch_next_chunk) {
 #pragma unroll
-            for (int ni = LO; ni < NT; ++ni) breg[(ks + 1) & 1][ni] = __ldg(brow + ni * ni_stride + kcol + 4 * (ks + 1));
+            for (int ni = LO; ni < NTW; ++ni)
+                breg[(ks + 1) & 1][ni] =
+                    ((valid_mask >> ni) & 1u) ? __ldg(brow + ni * ni_stride + kcol + 4 * (ks + 1)) : 0.0;
         }
         double a[4];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[mi * 8 * PR_ALD + 4 * ks];
 #pragma unroll
-        for (int ni = LO; ni < NT; ++ni) {
+        for (int ni = LO; ni < NTW; ++ni) {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], breg[ks & 1][ni]);
         }
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(PRED_THREADS, 1)
-predict_reg_kernel(int n, int k, int64_t m, const double* __restrict__ X, const double* __restrict__ Xq,
+constexpr int PR_XS_MAX = 4096;  // sample coordinates staged in shared memory when n * k fits (32 KB)
+
+// KK > 0: number of design variables known at compile time (theta, p, the query point in registers, a
+// straight-line psi chain); KK == 0: any k <= PK_MAX_K.
+template <int NTW, int KK>
+__global__ void __launch_bounds__(PR_THREADS, 1)
+predict_reg_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X, const double* __restrict__ Xq,
                    const double* __restrict__ hp, const double* __restrict__ linv, const double* __restrict__ w,
                    double mu, double sigma2, double y_min, double ei_weight, double var_extra, int need_s,
                    double* __restrict__ yhat_out, double* __restrict__ s_out, double* __restrict__ ei_out) {
-    constexpr int np = NT * PK_TILE;
-    __shared__ double tab[64 * 16];
-    __shared__ double As[2][PR_QT * PR_ALD];
-    __shared__ double xq[PR_QT * PK_MAX_K];
-    __shared__ double2 thp[PK_MAX_K];
-    __shared__ double ypart[8][PR_QT];
-    __shared__ double qpart[8][PR_QT + 1];
+    extern __shared__ __align__(16) double pr_smem[];
+    double* tab = pr_smem;                                          // 64 x 16 : 2^(j/64), bank replicated
+    double* ltab = tab + 64 * 16;                                   // 3 x 64 x 16 : log2 split tables
+    double (*As)[PR_QT * PR_ALD] = reinterpret_cast<double (*)[PR_QT * PR_ALD]>(ltab + 3 * 64 * 16);
+    double* xq = reinterpret_cast<double*>(As + 2);                 // 32 x PK_MAX_K
+    double2* thp = reinterpret_cast<double2*>(xq + PR_QT * PK_MAX_K);  // PK_MAX_K
+    double (*ypart)[PR_QT] = reinterpret_cast<double (*)[PR_QT]>(thp + PK_MAX_K);
+    double (*qpart)[PR_QT + 1] = reinterpret_cast<double (*)[PR_QT + 1]>(ypart + PR_WARPS);
+    double* Xs = reinterpret_cast<double*>(qpart + PR_WARPS);       // n x k when it fits
+    const bool x_staged = (n * k <= PR_XS_MAX);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fc = lane & 3;
     const int64_t q0 = (int64_t)blockIdx.x * PR_QT;
     const int qv = (int)min((int64_t)PR_QT, m - q0);
 
-    fill_exp2_table(tab, tid, PRED_THREADS);
-    for (int i = tid; i < PR_QT * k; i += PRED_THREADS) {
+    fill_exp2_table(tab, tid, PR_THREADS);
+    fill_log2_tables(ltab, tid, PR_THREADS);
+    for (int i = tid; i < PR_QT * k; i += PR_THREADS) {
         const int q = i / k;
         xq[q * PK_MAX_K + (i - q * k)] = (q < qv) ? Xq[q0 * k + i] : 0.0;
     }
     if (tid < k) thp[tid] = make_double2(hp[tid], hp[PK_MAX_K + tid]);
+    if (x_staged)
+        for (int i = tid; i < n * k; i += PR_THREADS) Xs[i] = X[i];
     __syncthreads();
     const char* tabp = reinterpret_cast<const char*>(tab + (tid & 15));
+    const double* Xsrc = x_staged ? Xs : X;
+    // compile-time k: hyper-parameters and this thread's query point live in registers
+    double th_r[KK > 0 ? KK : 1], p_r[KK > 0 ? KK : 1], xq_r[KK > 0 ? KK : 1];
+    bool special = false;  // some exponent is exactly 1 or 2 (exact d / d*d path, CTA uniform)
+    if (KK > 0) {
+#pragma unroll
+        for (int d = 0; d < KK; ++d) {
+            th_r[d] = thp[d].x;
+            p_r[d] = thp[d].y;
+            xq_r[d] = xq[lane * PK_MAX_K + d];
+            special |= (p_r[d] == 1.0 || p_r[d] == 2.0);
+        }
+    }
 
-    // psi producer: this thread owns query pq and samples ps0, ps0 + 8 of every chunk
-    const int pq = lane, ps0 = warp;
+    // psi producer: this thread owns query `lane` and sample slot `warp` of every chunk
     double ys = 0.0;
     auto make_psi = [&](int kc, double* dst) {
+        const int r = kc * PR_KC + warp;
+        double v = 0.0;
+        if (r < n && lane < qv) {
+            const double* xr = Xsrc + (size_t)r * k;
+            double S;
+            if (KK > 0 && !special) {
+                // straight line: KK x (log2 split + 2^x), NumPy's summation order (plain left to right for k < 8)
+                double term[KK > 0 ? KK : 1];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int r = kc * PR_KC + ps0 + 8 * h;
-            double v = 0.0;
-            if (r < n && pq < qv) {
-                const double* xr = X + (size_t)r * k;
-                const double* xqq = xq + pq * PK_MAX_K;
-                const double S = sum_numpy_order(k, [&](int d) {
+                for (int d = 0; d < KK; ++d) {
+                    double lh;
+                    float ll;
+                    log2_split_smem(fabs(xr[d] - xq_r[d]), ltab, tid & 15, lh, ll);
+                    term[d] = th_r[d] * exp2_lean(p_r[d], lh, (double)ll, tabp);
+                }
+                S = sum_numpy_order(KK, [&](int d) { return term[d]; });
+            } else {
+                const double* xqq = xq + lane * PK_MAX_K;
+                S = sum_numpy_order(k, [&](int d) {
                     const double2 tp = thp[d];
-                    return tp.x * pow_abs_lean(fabs(__ldg(xr + d) - xqq[d]), tp.y, tabp);
+                    return tp.x * pow_abs_lean(fabs(xr[d] - xqq[d]), tp.y, tabp, ltab, tid & 15);
                 });
-                v = expneg_table(S, tab, tid & 15);
-                ys = fma(v, __ldg(w + r), ys);
             }
-            dst[pq * PR_ALD + ps0 + 8 * h] = v;
+            v = expneg_table(S, tab, tid & 15);
+            ys = fma(v, __ldg(w + r), ys);
         }
+        dst[lane * PR_ALD + warp] = v;
     };
 
-    constexpr int NCH = np / PR_KC;
-    double acc[4][NT][2];
+    const int nch = np / PR_KC;
+    double acc[4][NTW][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    double breg[2][NT];
-    // B fragment base: row (8 warp + fr) of the first 64-column tile, k offset fc; block ni adds 64 rows
+        for (int ni = 0; ni < NTW; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    double breg[2][NTW];
+    // B fragment base: row (8 warp + fr) of the first 128-column group, k offset fc; block ni adds 128 rows
     const double* brow = linv + (size_t)(8 * warp + fr) * np + fc;
-    const size_t ni_stride = (size_t)PK_TILE * np;
+    const size_t ni_stride = (size_t)(8 * PR_WARPS) * np;
+    unsigned valid_mask = 0;
+#pragma unroll
+    for (int ni = 0; ni < NTW; ++ni)
+        if (8 * PR_WARPS * ni + 8 * warp < np) valid_mask |= 1u << ni;
     if (need_s) {
 #pragma unroll
-        for (int ni = 0; ni < NT; ++ni) breg[0][ni] = __ldg(brow + ni * ni_stride);
+        for (int ni = 0; ni < NTW; ++ni) breg[0][ni] = ((valid_mask >> ni) & 1u) ? __ldg(brow + ni * ni_stride) : 0.0;
     }
     make_psi(0, As[0]);
-    for (int kc = 0; kc < NCH; ++kc) {
+    for (int kc = 0; kc < nch; ++kc) {
         __syncthreads();  // chunk kc of psi is complete; the other A stage is free again
-        if (kc + 1 < NCH) make_psi(kc + 1, As[(kc + 1) & 1]);
+        if (kc + 1 < nch) make_psi(kc + 1, As[(kc + 1) & 1]);
         if (need_s) {
-            const int num = PR_KC * kc - 8 * warp + 56;
-            const int lo = (num <= 0) ? 0 : (num >> 6);
-            const bool pf = kc + 1 < NCH;
+            // first live block: block ni covers columns 128 ni + 8 warp .. + 7 and is needed iff that reaches 16 kc
+            const int num = PR_KC * kc - 8 * warp - 7;
+            const int lo = (num <= 0) ? 0 : ((num + 8 * PR_WARPS - 1) / (8 * PR_WARPS));
+            const bool pf = kc + 1 < nch;
             const double* as = As[kc & 1];
             const int kcol = PR_KC * kc;
             switch (lo) {
-#define PK_PRED_CASE(LL)                                                                              \
-                case LL:                                                                              \
-                    if (LL < NT) pred_consume<NT, (LL < NT ? LL : 0)>(acc, breg, as, brow, ni_stride, kcol, pf, lane); \
+                case 0: pred_consume<NTW, 0>(acc, breg, as, brow, ni_stride, kcol, pf, valid_mask, lane); break;
+                case 1:
+                    if (NTW > 1) pred_consume<NTW, (NTW > 1 ? 1 : 0)>(acc, breg, as, brow, ni_stride, kcol, pf, valid_mask, lane);
                     break;
-                PK_PRED_CASE(0) PK_PRED_CASE(1) PK_PRED_CASE(2) PK_PRED_CASE(3)
-                PK_PRED_CASE(4) PK_PRED_CASE(5) PK_PRED_CASE(6) PK_PRED_CASE(7)
-#undef PK_PRED_CASE
+                case 2:
+                    if (NTW > 2) pred_consume<NTW, (NTW > 2 ? 2 : 0)>(acc, breg, as, brow, ni_stride, kcol, pf, valid_mask, lane);
+                    break;
+                case 3:
+                    if (NTW > 3) pred_consume<NTW, (NTW > 3 ? 3 : 0)>(acc, breg, as, brow, ni_stride, kcol, pf, valid_mask, lane);
+                    break;
                 default: break;
             }
         }
     }
-    // ---- reductions: yhat partials over the 8 sample slots, |v|^2 over columns ---------------------
+    // ---- reductions: yhat partials over the 16 sample slots, |v|^2 over columns -------------------
     ypart[warp][lane] = ys;
     if (need_s) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             double v = 0.0;
 #pragma unroll
-            for (int ni = 0; ni < NT; ++ni) v += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+            for (int ni = 0; ni < NTW; ++ni) v += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             if (fc == 0) qpart[warp][mi * 8 + fr] = v;
@@ -354,12 +400,12 @@ predict_reg_kernel(int n, int k, int64_t m, const double* __restrict__ X, const 
     if (tid < qv) {
         double ysum = 0.0, qs = 0.0;
 #pragma unroll
-        for (int z = 0; z < 8; ++z) ysum += ypart[z][tid];
+        for (int z = 0; z < PR_WARPS; ++z) ysum += ypart[z][tid];
         const double yhat = mu + ysum;
         if (yhat_out) yhat_out[q0 + tid] = yhat;
         if (need_s) {
 #pragma unroll
-            for (int z = 0; z < 8; ++z) qs += qpart[z][tid];
+            for (int z = 0; z < PR_WARPS; ++z) qs += qpart[z][tid];
             const double ssqr = sigma2 * (1.0 + var_extra - qs);
             const double S = sqrt(fabs(ssqr));
             if (s_out) s_out[q0 + tid] = S;
@@ -415,17 +461,39 @@ static cudaError_t launch_predict_t(pk_handle* h, int64_t m, const double* Xq, c
     return cudaGetLastError();
 }
 
-template <int NT>
+template <int NTW, int KK>
+static cudaError_t launch_predict_reg_k(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu,
+                                        double sigma2, double y_min, double ei_weight, double var_extra, double* yhat,
+                                        double* sout, double* ei) {
+    const int need_s = (sout != nullptr || ei != nullptr) ? 1 : 0;
+    const int64_t blocks = (m + PR_QT - 1) / PR_QT;
+    constexpr size_t smem = sizeof(double) * (64 * 16 + 3 * 64 * 16 + 2 * PR_QT * PR_ALD + PR_QT * PK_MAX_K +
+                                              2 * PK_MAX_K + PR_WARPS * PR_QT + PR_WARPS * (PR_QT + 1) + PR_XS_MAX);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e =
+            cudaFuncSetAttribute(predict_reg_kernel<NTW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    predict_reg_kernel<NTW, KK><<<(unsigned)blocks, PR_THREADS, smem, h->stream>>>(
+        h->n, h->fit_np, h->k, m, h->dX, Xq, hp, h->d_linv, h->d_w, mu, sigma2, y_min, ei_weight, var_extra, need_s, yhat,
+        sout, ei);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+template <int NTW>
 static cudaError_t launch_predict_reg(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu,
                                       double sigma2, double y_min, double ei_weight, double var_extra, double* yhat,
                                       double* sout, double* ei) {
-    const int need_s = (sout != nullptr || ei != nullptr) ? 1 : 0;
-    const int64_t blocks = (m + PR_QT - 1) / PR_QT;
-    predict_reg_kernel<NT><<<(unsigned)blocks, PRED_THREADS, 0, h->stream>>>(h->n, h->k, m, h->dX, Xq, hp, h->d_linv,
-                                                                            h->d_w, mu, sigma2, y_min, ei_weight,
-                                                                            var_extra, need_s, yhat, sout, ei);
-    h->launches++;
-    return cudaGetLastError();
+    switch (h->k) {
+        case 1: return launch_predict_reg_k<NTW, 1>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+        case 2: return launch_predict_reg_k<NTW, 2>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+        case 3: return launch_predict_reg_k<NTW, 3>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+        case 4: return launch_predict_reg_k<NTW, 4>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+        default: return launch_predict_reg_k<NTW, 0>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+    }
 }
 
 cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
@@ -433,9 +501,9 @@ cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const doub
                            double* ei) {
     const int np = h->fit_np;
     if (np <= 512 && h->predict_variant != 1) {
-        switch (np / PK_TILE) {
+        switch ((np / PK_TILE + 1) / 2) {  // 8-column blocks per warp: np/8 blocks over 16 warps
 #define PK_PR(NN) case NN: return launch_predict_reg<NN>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
-            PK_PR(1) PK_PR(2) PK_PR(3) PK_PR(4) PK_PR(5) PK_PR(6) PK_PR(7) PK_PR(8)
+            PK_PR(1) PK_PR(2) PK_PR(3) PK_PR(4)
 #undef PK_PR
         }
     }
