@@ -131,6 +131,14 @@ int pk_set_cholesky_variant(pk_handle *h, int variant);
  * 2 = v = L^-1 psi held in registers, psi chunks generated on the fly (n <= 512; falls back otherwise). */
 int pk_set_predict_variant(pk_handle *h, int variant);
 
+/* pk_nll_batch pipelining experiment (the candidate loop of krige.py:429-452 has no such notion: it is
+ * strictly sequential).  0 (default): Psi -> Cholesky -> epilogue per resident chunk on one stream.
+ * 1: a population larger than the number of resident Cholesky CTAs is split in two parts and the Psi
+ * construction of the second part runs on a second stream while the first part is factorised.  Both
+ * kernels are bound by the same FP64 pipe, so this only re-orders work: measured 46.0k vs 50.5k evals/s
+ * at C3 (profiles/overlap_split_r01.txt) -- kept as a knob, off.  Results are identical either way. */
+int pk_set_overlap(pk_handle *h, int enabled);
+
 /* Phase timing for roofline accounting (bench.py): when enabled, CUDA events are recorded on the
  * handle's stream around the phases of every pk_nll_batch / pk_predict_batch call.
  * pk_phase_times() synchronises, ADDS the elapsed milliseconds since the last call into

@@ -20,7 +20,7 @@ EXPORTS = [
     "pk_version", "pk_last_error", "pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit",
     "pk_predict_batch", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
     "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
-    "pk_fp64_peak", "pk_debug_math", "pk_set_cholesky_variant", "pk_set_predict_variant",
+    "pk_fp64_peak", "pk_debug_math", "pk_set_cholesky_variant", "pk_set_predict_variant", "pk_set_overlap",
 ]
 
 _lib = None
@@ -75,6 +75,8 @@ def load():
     lib.pk_set_cholesky_variant.restype = ctypes.c_int
     lib.pk_set_predict_variant.argtypes = [hp, ctypes.c_int]
     lib.pk_set_predict_variant.restype = ctypes.c_int
+    lib.pk_set_overlap.argtypes = [hp, ctypes.c_int]
+    lib.pk_set_overlap.restype = ctypes.c_int
     for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
                  "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_set_workspace_limit"):
         getattr(lib, name).restype = ctypes.c_int
@@ -262,6 +264,10 @@ class Handle(object):
     def set_cholesky_variant(self, variant):
         """0 auto, 1 per-block-column launches, 2 persistent CTA per candidate."""
         self._check(self.lib.pk_set_cholesky_variant(self._h, int(variant)), "pk_set_cholesky_variant")
+
+    def set_overlap(self, enabled):
+        """Psi construction of the second part of a population overlaps the factorisation of the first (default on)."""
+        self._check(self.lib.pk_set_overlap(self._h, int(bool(enabled))), "pk_set_overlap")
 
     def set_predict_variant(self, variant):
         """0 auto, 1 shared-memory psi tile kernel, 2 register-resident kernel (n <= 512)."""

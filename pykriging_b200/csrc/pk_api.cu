@@ -1,5 +1,6 @@
 // C ABI of libpykriging_b200.so (see include/pykriging_b200.h for the contract of every entry point).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -137,7 +138,8 @@ int pk_create(pk_handle** out, int device) {
         return 1;
     }
     e = cudaMalloc((void**)&h->d_hp, sizeof(double) * 2 * PK_MAX_K);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_queue, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_queue, sizeof(unsigned int) * PK_QUEUE_SLOTS);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);
@@ -157,6 +159,11 @@ int pk_destroy(pk_handle* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_pipe) cudaEventDestroy(e);
+    if (h->stream2) {
+        cudaStreamSynchronize(h->stream2);
+        cudaStreamDestroy(h->stream2);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -182,6 +189,12 @@ int pk_set_pivot_tolerance(pk_handle* h, double tol) {
 int pk_set_cholesky_variant(pk_handle* h, int variant) {
     if (!h || variant < 0 || variant > 2) return 1;
     h->chol_variant = variant;
+    return 0;
+}
+
+int pk_set_overlap(pk_handle* h, int enabled) {
+    if (!h) return 1;
+    h->overlap = enabled ? 1 : 0;
     return 0;
 }
 
@@ -289,6 +302,37 @@ static int ensure_workspace(pk_handle* h, size_t per_matrix_bytes, int C, int* c
     return 0;
 }
 
+// Split a resident chunk of `cc` candidates into pipeline parts.  The persistent Cholesky kernel keeps
+// 2 CTAs per SM busy ("slots"); a population that is not a multiple of the slot count leaves a ragged
+// last wave.  The ragged part goes FIRST, so that the Psi construction of the remaining (whole-wave)
+// part fills the SMs its tail frees, and the last factorisation ends on a wave boundary.
+static void plan_parts(pk_handle* h, int cc, std::vector<int>& parts) {
+    parts.clear();
+    const int slots = 2 * h->sm_count;
+    if (const char* e = getenv("PK_SPLIT")) {  // experiment knob: comma-separated part sizes
+        int left = cc;
+        const char* q = e;
+        while (*q && left > 0) {
+            int v = atoi(q);
+            if (v <= 0) break;
+            if (v > left) v = left;
+            parts.push_back(v);
+            left -= v;
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (left > 0) parts.push_back(left);
+        return;
+    }
+    if (!h->overlap || h->profiling || h->chol_variant == 1 || cc <= slots) {
+        parts.push_back(cc);
+        return;
+    }
+    const int rem = cc % slots;
+    if (rem > 0) parts.push_back(rem);
+    parts.push_back(cc - rem);
+}
+
 int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, const double* lambda, int mode,
                  double* nll, double* mu, double* sigma2, double* lndet, int32_t* info) {
     if (!h) return 1;
@@ -315,16 +359,46 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
         if (ensure_workspace(h, s.elems() * sizeof(double), C, &chunk)) return 1;
         for (int c0 = 0; c0 < C; c0 += chunk) {
             const int cc = (C - c0 < chunk) ? (C - c0) : chunk;
-            pk::phase_begin(h, 0);
-            PK_CUDA(h, pk::launch_psi_build(h, s, cc, d_theta + (size_t)c0 * k, d_p + (size_t)c0 * k,
-                                            d_lambda ? d_lambda + c0 : nullptr, mode, h->d_ws, h->d_info + c0));
-            pk::phase_end(h);
-            pk::phase_begin(h, 1);
-            PK_CUDA(h, pk::launch_cholesky(h, s, cc, h->d_ws, h->d_info + c0));
-            pk::phase_end(h);
-            pk::phase_begin(h, 2);
-            PK_CUDA(h, pk::launch_nll_epilogue(h, s, cc, h->d_ws, h->d_out + c0, h->cap_C, h->d_info + c0));
-            pk::phase_end(h);
+            // Parts of the resident chunk: Psi of part i+1 (stream2) runs while part i is factorised (stream).
+            std::vector<int> parts;
+            plan_parts(h, cc, parts);
+            if (parts.size() > 1) {
+                while (h->ev_pipe.size() < parts.size() + 1) {
+                    cudaEvent_t ev;
+                    PK_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    h->ev_pipe.push_back(ev);
+                }
+                // stream2 starts after everything already queued on the main stream (uploads, the previous
+                // chunk's factorisations that still read the workspace)
+                PK_CUDA(h, cudaEventRecord(h->ev_pipe[0], h->stream));
+                PK_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_pipe[0], 0));
+            }
+            int o = 0;
+            for (size_t pi = 0; pi < parts.size(); ++pi) {
+                const int pc = parts[pi], a0 = c0 + o;
+                double* wsp = h->d_ws + (size_t)o * s.elems();
+                cudaStream_t main_stream = h->stream;
+                if (parts.size() > 1) h->stream = h->stream2;
+                pk::phase_begin(h, 0);
+                cudaError_t pe = pk::launch_psi_build(h, s, pc, d_theta + (size_t)a0 * k, d_p + (size_t)a0 * k,
+                                                      d_lambda ? d_lambda + a0 : nullptr, mode, wsp, h->d_info + a0);
+                pk::phase_end(h);
+                h->stream = main_stream;
+                PK_CUDA(h, pe);
+                if (parts.size() > 1) {
+                    PK_CUDA(h, cudaEventRecord(h->ev_pipe[pi + 1], h->stream2));
+                    PK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_pipe[pi + 1], 0));
+                }
+                h->queue_slot = (int)(pi % PK_QUEUE_SLOTS);
+                pk::phase_begin(h, 1);
+                PK_CUDA(h, pk::launch_cholesky(h, s, pc, wsp, h->d_info + a0));
+                pk::phase_end(h);
+                pk::phase_begin(h, 2);
+                PK_CUDA(h, pk::launch_nll_epilogue(h, s, pc, wsp, h->d_out + a0, h->cap_C, h->d_info + a0));
+                pk::phase_end(h);
+                o += pc;
+            }
+            h->queue_slot = 0;
         }
     }
     double* outs[4] = {nll, mu, sigma2, lndet};

@@ -607,7 +607,8 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    cudaError_t e = cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned int), h->stream);
+    unsigned int* queue = h->d_queue + h->queue_slot;
+    cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(unsigned int), h->stream);
     if (e != cudaSuccess) return e;
     int per_sm = 2;
     if (const char* e = getenv("PK_CHOL_CTAS_PER_SM")) per_sm = (atoi(e) == 1) ? 1 : 2;  // experiment knob
@@ -617,7 +618,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         cudaMalloc((void**)&dbg, sizeof(long long) * 8 * grid);
         cudaMemset(dbg, 0, sizeof(long long) * 8 * grid);
         cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
-                                                                            ws, info, h->d_queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0);
+                                                                            ws, info, queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0);
         cudaStreamSynchronize(h->stream);
         std::vector<long long> host(8 * (size_t)grid);
         cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
@@ -632,7 +633,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
                 sum[6] / sum[4], sum[7] / sum[4]);
     } else {
         cta::chol_cta_kernel<false><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(),
-                                                                             h->pivot_tol, ws, info, h->d_queue, nullptr, 0);
+                                                                             h->pivot_tol, ws, info, queue, nullptr, 0);
     }
     h->launches++;
     return cudaGetLastError();

@@ -9,6 +9,8 @@
 #include "../../include/pykriging_b200.h"
 #include "pk_common.cuh"
 
+constexpr int PK_QUEUE_SLOTS = 64;
+
 struct pk_handle {
     int device = 0;
     int sm_count = 148;
@@ -22,7 +24,13 @@ struct pk_handle {
     double pivot_tol = 2.0 * PK_EPS_DIAG;  // relative pivot threshold, 2 ulps (see pk_set_pivot_tolerance)
     int chol_variant = 0;                  // 0 auto, 1 one launch per block column, 2 persistent CTA per candidate
     int predict_variant = 0;               // 0 auto, 1 shared-memory psi tile kernel (any n), 2 register-resident (n <= 512)
-    unsigned int* d_queue = nullptr;       // candidate queue of the persistent Cholesky kernel
+    unsigned int* d_queue = nullptr;       // candidate queues of the persistent Cholesky kernel (PK_QUEUE_SLOTS counters)
+    int queue_slot = 0;                    // counter the next launch_cholesky_cta uses
+    // Psi construction of the NEXT part of a population overlaps the Cholesky of the current one: the Psi
+    // kernels are issued on stream2, the factorisations on stream, ordered by events (pk_nll_batch)
+    cudaStream_t stream2 = nullptr;
+    std::vector<cudaEvent_t> ev_pipe;
+    int overlap = 0;                       // 1: two-part pipeline on two streams (pk_set_overlap; measured slower, off)
 
     // model data (pk_set_data)
     int n = 0, k = 0;

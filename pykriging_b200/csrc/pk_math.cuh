@@ -4,6 +4,7 @@
 #pragma once
 #include "pk_common.cuh"
 #include "pk_exp2_table.h"
+#include "pk_exp2_4096.h"
 
 namespace pk {
 
@@ -92,6 +93,92 @@ __device__ __forceinline__ void log2_split(double d, double& L, float& res) {
     const double bb = L - lh;                    // TwoSum: (lh + t) = L + r exactly
     const double r = (lh - (L - bb)) + (t - bb);
     res = (float)r;
+}
+
+// ---- 4096-entry variants for the population Psi kernel ----------------------------------------------------
+// That kernel is ISSUE bound: an FP64 instruction holds a scheduler's dispatch port for two cycles, every
+// other instruction for one -- 2 x 151 + 140 = 442 cycles per warp and Psi entry with the 64-entry functions
+// below is exactly what ncu measured (profiles/ncu_psi_pop_r01_r.txt: sm__cycles_active / entries per
+// scheduler), so what counts is the instruction count.  With 2^(j/4096) tabulated the reduced argument is
+// |r| <= 2^-13 and (2^r - 1)/r needs a quadratic (c3 r^4 < 0.01 ulp): 8 FP64 instructions per 2^x instead of
+// 10; the exponent clamp (two integer min/max) is gone because log2_split_clamped keeps |p log2 d| < 1022 for
+// p <= 3; table index, address and scaling cost five integer instructions instead of seven.  The table is a
+// plain 32 KB shared array: the loads of a half-warp collide on its banks, but the LSU has the wavefronts to
+// spare.  Measured on the C3 population: 6.53 ms -> 5.74 ms; a bank-replicated 256-entry table with a cubic
+// (conflict free, one FP64 instruction more) measured 5.93 ms, two candidates per thread and iteration
+// (124 registers, two CTAs per SM) 5.90 ms.
+static __device__ const double g_exp2_4096[4096] = {PK_EXP2_4096_LIST};
+constexpr double MAGIC32K = 6755399441055744.0 / 32768.0;  // 1.5 * 2^37: ulp 2^-15
+constexpr double HALF_STEP_4096 = 1.0 / 8192.0;
+constexpr double L2_CLAMP = 340.0;
+static __constant__ double c_e2q[3] = {0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58fp-3, 0x1.c6b08d704a0c0p-5};
+
+__device__ __forceinline__ void fill_exp2_4096(double* tab, int tid, int nthreads) {
+    for (int i = tid; i < 4096; i += nthreads) tab[i] = g_exp2_4096[i];
+}
+
+// 2^(pd * (lh + ll)) for |pd * lh| < 1022.  `tab_saddr` = 32-bit shared address of the table, ALIGNED TO
+// 32 KB.  x = pd * lh (+ half a table step) is rounded to a multiple of 2^-15 by the magic add, so the low word
+// kl of kd holds 32768 (x + 1/8192): bits 3..14 are the table index -- as a byte offset they are OR-ed into
+// the address by the same LOP3 that masks them -- bits 15.. are the binary exponent, and kd with the low
+// three bits cleared is x rounded to the nearest 1/4096: kf.
+__device__ __forceinline__ double exp2_lean4k(double pd, double lh, double ll, unsigned tab_saddr) {
+    const double kd = fma(pd, lh, MAGIC32K + HALF_STEP_4096);
+    const int kl = __double2loint(kd);
+    const double kf = __longlong_as_double(__double_as_longlong(kd) & ~0x7LL) - MAGIC32K;
+    double r = fma(pd, lh, -kf);
+    r = fma(pd, ll, r);                          // |r| <= 2^-13 + 2^-16
+    double q = fma(r, c_e2q[2], c_e2q[1]);
+    q = fma(r, q, c_e2q[0]);
+    double T;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_saddr | (unsigned)(kl & 0x7ff8)));
+    const double v = fma(T * r, q, T);
+    int hi;
+    asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(hi) : "r"(kl >> 15), "r"(__double2hiint(v)));
+    return __hiloint2double(hi, __double2loint(v));
+}
+
+// e^(-S), S >= 0: Cody-Waite with ln2/4096 = hi (20 bits: k * hi is exact for |k| < 2^33) + lo, quadratic.
+__device__ __forceinline__ double expneg_4k(double S, unsigned tab_saddr) {
+    const double kd = fma(S, -PK_4096_OVER_LN2, MAGIC1);
+    const int ki = __double2loint(kd);
+    const double kf = kd - MAGIC1;              // k = round(-S * 4096 / ln2)
+    double r = fma(kf, -PK_LN2_4096_HI, -S);
+    r = fma(kf, -PK_LN2_4096_LO, r);            // |r| <= ln2/8192
+    double q = fma(r, 1.6666666666666666e-01, 0.5);
+    q = fma(r, q, 1.0);                         // (e^r - 1) / r up to r^2/6
+    double T;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_saddr | (unsigned)((ki & 4095) << 3)));
+    const double v = fma(T * r, q, T);
+    if (!(S < 1.0e5)) return (S != S) ? S : 0.0;  // NaN propagates, huge S underflows
+    return scale_pow2(v, ki >> 12);
+}
+
+// 2^(s + e) with full range checks and the 64-entry table read from the constant bank: the rare slow path
+// (candidates with an exponent that is exactly 1 or 2, or outside [0.25, 3])
+__device__ __forceinline__ double exp2_const(double s, double e) {
+    if (!(s > -1100.0)) return 0.0;
+    if (!(s < 1100.0)) return CUDART_INF;
+    const double kd = s + MAGIC64;
+    const int ki = __double2loint(kd);
+    const double kf = kd - MAGIC64;
+    const double r = (s - kf) + e;
+    double q = fma(r, 0x1.5d87fe78a6731p-10, 0x1.3b2ab6fba4e77p-7);
+    q = fma(r, q, 0x1.c6b08d704a0c0p-5);
+    q = fma(r, q, 0x1.ebfbdff82c58fp-3);
+    q = fma(r, q, 0x1.62e42fefa39efp-1);
+    q = q * r;
+    const double T = c_exp2_hi[ki & 63];
+    return scale_pow2(fma(T, q, T), ki >> 6);
+}
+
+// log2_split with the result clamped to [-L2_CLAMP, L2_CLAMP] (d = 0 -> -L2_CLAMP): for p <= 3 the product
+// p * log2 d then stays inside the exponent range and exp2_lean4k needs no clamp of its own; 2^(-340 p) is
+// < 1e-102 -- in a sum that is >= 0 and feeds e^-S it is indistinguishable from pow(0, p) = 0.
+__device__ __forceinline__ void log2_split_clamped(double d, double& L, float& res) {
+    log2_split(d, L, res);
+    if (!(L > -L2_CLAMP)) { L = -L2_CLAMP; res = 0.0f; }
+    if (L > L2_CLAMP) { L = L2_CLAMP; res = 0.0f; }
 }
 
 // ---- lean 2^x for the candidate loop ---------------------------------------------------------------

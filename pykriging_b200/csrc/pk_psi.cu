@@ -21,11 +21,18 @@
 namespace pk {
 
 constexpr int PSI_THREADS = 256;
-constexpr int PSI_GROUP = 64;  // candidates per CTA (amortises the log2 split of the CTA's pairs)
+constexpr int PSI_GROUP = 128;  // candidates per CTA (amortises the log2 split of the CTA's pairs and the table copy)
 
 // PPT pairs per thread: large K keeps ONE pair per thread so that the per-pair log2 tables (3 registers per
 // dimension) leave room for three resident CTAs per SM -- the per-candidate 2^x chain is latency bound and
 // needs the extra warps more than it needs wider stores.
+// bytes of the per-CTA arrays in front of the 2^x table
+template <int K, int PPT>
+__host__ __device__ constexpr unsigned psi_small_bytes() {
+    return (unsigned)(sizeof(double) * (2 * PSI_GROUP * K + (PSI_THREADS * PPT / PK_TILE + PK_TILE) * K + PSI_GROUP) +
+                      sizeof(int) * PSI_GROUP);
+}
+
 template <int K, int PPT>
 __global__ void __launch_bounds__(PSI_THREADS, (PPT == 1) ? (K <= 12 ? 3 : 2) : 1)
 psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restrict__ X,
@@ -33,12 +40,18 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                const double* __restrict__ lambda, int mode, double* __restrict__ ws) {
     constexpr int RB = PSI_THREADS * PPT / PK_TILE;  // rows of the pair block
     constexpr int SPT = PK_TILE / RB;                // row blocks per tile
-    __shared__ double tab[64 * 16];
-    __shared__ double Xr[RB * K], Xc[PK_TILE * K];
-    __shared__ double2 thp[PSI_GROUP * K];  // (theta_d, p_d) pairs: one 16-byte broadcast load per (candidate, dimension)
-    __shared__ double dg[PSI_GROUP];
-    __shared__ int spec[PSI_GROUP];  // candidate has an exponent that is exactly 1 or 2 (exact d / d*d path)
-    const int tid = threadIdx.x, bank = tid & 15;
+    extern __shared__ __align__(16) double psi_smem[];
+    double2* thp = reinterpret_cast<double2*>(psi_smem);             // (theta_d, p_d): one 16-byte broadcast load per (candidate, dimension)
+    double* Xr = reinterpret_cast<double*>(thp + PSI_GROUP * K);     // RB x K
+    double* Xc = Xr + RB * K;                                        // 64 x K
+    double* dg = Xc + PK_TILE * K;                                   // PSI_GROUP diagonal values
+    int* spec = reinterpret_cast<int*>(dg + PSI_GROUP);              // candidate takes the exact / range-checked path
+    const int tid = threadIdx.x;
+    // 2^(j/4096) (32 KB) at the first 32 KB-aligned shared address behind the arrays above (the launcher sizes the
+    // dynamic allocation for it): exp2_lean4k ORs the entry's byte offset into the address
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(psi_smem);
+    const unsigned tab_saddr = (smem_base + psi_small_bytes<K, PPT>() + 0x7fffu) & ~0x7fffu;
+    double* tab4k = psi_smem + (tab_saddr - smem_base) / sizeof(double);
     // block -> (lower tile, row block)
     const int t = blockIdx.x / SPT, sb = blockIdx.x % SPT;
     int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
@@ -49,7 +62,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
     const int g0 = blockIdx.y * PSI_GROUP;
     const int gn = min(PSI_GROUP, C - g0);
 
-    for (int i = tid; i < 64 * 16; i += PSI_THREADS) tab[i] = c_exp2_hi[i >> 4];
+    fill_exp2_4096(tab4k, tid, PSI_THREADS);
     for (int i = tid; i < RB * K; i += PSI_THREADS) {
         const int rr = i / K;
         Xr[i] = (r0 + rr < n) ? X[(size_t)(r0 + rr) * K + (i % K)] : 0.0;
@@ -66,18 +79,17 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
         int sp = 0;
         for (int d = 0; d < K; ++d) {
             const double pd = p[(size_t)(g0 + tid) * K + d];
-            sp |= (pd == 1.0 || pd == 2.0) ? 1 : 0;
+            sp |= (pd == 1.0 || pd == 2.0 || !(pd >= 0.25 && pd <= 3.0)) ? 1 : 0;
         }
         spec[tid] = sp;
     }
     __syncthreads();
-    const char* tabp = reinterpret_cast<const char*>(tab + bank);
 
     const int lr = tid / (PK_TILE / PPT);            // local row
     const int lc = (tid % (PK_TILE / PPT)) * PPT;    // first local column
     const int gr = r0 + lr;
     double lh[PPT][K];
-    float ll[PPT][K];
+    double ll[PPT][K];  // kept as doubles: a float would be re-converted (F2F.F64.F32, FP64-rate) per candidate
     bool live[PPT];
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
@@ -85,15 +97,21 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
         live[q] = (gr < n) && (gc < gr);
 #pragma unroll
         for (int d = 0; d < K; ++d) {
-            if (live[q]) log2_split(fabs(Xr[lr * K + d] - Xc[(lc + q) * K + d]), lh[q][d], ll[q][d]);
-            else { lh[q][d] = 0.0; ll[q][d] = 0.0f; }
+            if (live[q]) {
+                float lf;
+                log2_split_clamped(fabs(Xr[lr * K + d] - Xc[(lc + q) * K + d]), lh[q][d], lf);
+                ll[q][d] = (double)lf;
+            } else {
+                lh[q][d] = 0.0;
+                ll[q][d] = 0.0;
+            }
         }
     }
     bool any_live = false;
 #pragma unroll
     for (int q = 0; q < PPT; ++q) any_live |= live[q];
 
-    for (int g = 0; g < gn; ++g) {
+    auto one_candidate = [&](int g) {
         double out[PPT];
         const double2* tpg = thp + g * K;
 #pragma unroll
@@ -106,7 +124,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                 auto tw = [&](int d, double& th_d) {
                     const double2 tp = tpg[d];
                     th_d = tp.x;
-                    return exp2_lean(tp.y, lh[q][d], (double)ll[q][d], tabp);
+                    return exp2_lean4k(tp.y, lh[q][d], ll[q][d], tab_saddr);
                 };
                 double S;
                 if (K < 8) {
@@ -139,7 +157,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                         S = fma(t, wv, S);
                     }
                 }
-                v = expneg_table(S, tab, bank);
+                v = expneg_4k(S, tab_saddr);
             } else if (live[q]) {
                 // a candidate with an exponent that is exactly 1 or 2 (bounder-clipped PSO particles,
                 // krige.py:383): np.power returns d and d*d exactly there, so do the same
@@ -154,14 +172,18 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                     } else if (pd == 1.0) {
                         w = fabs(Xr[lr * K + d] - Xc[(lc + q) * K + d]);
                     } else {
-                        const double s = pd * lh[q][d];
-                        const double e = fma(pd, (double)ll[q][d], fma(pd, lh[q][d], -s));
-                        w = exp2_table(s, e, tab, bank);
+                        const double dd = fabs(Xr[lr * K + d] - Xc[(lc + q) * K + d]);
+                        double l0;
+                        float l1;
+                        log2_split(dd, l0, l1);  // unclamped: exp2_const checks the range itself
+                        const double s = pd * l0;
+                        const double e = fma(pd, (double)l1, fma(pd, l0, -s));
+                        w = exp2_const(s, e);
                     }
                     term[d] = tpg[d].x * w;
                 }
                 const double S = sum_numpy_order(K, [&](int d) { return term[d]; });
-                v = expneg_table(S, tab, bank);
+                v = expneg_4k(S, tab_saddr);
             } else if (gr >= n || gc >= n) {
                 v = (gr == gc) ? 1.0 : 0.0;   // identity padding
             } else {
@@ -178,7 +200,9 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
         } else {
             dst[0] = out[0];  // a warp still writes 256 contiguous bytes
         }
-    }
+    };
+
+    for (int g = 0; g < gn; ++g) one_candidate(g);
     (void)any_live;
 }
 
@@ -186,7 +210,12 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
 __global__ void debug_math_kernel(int64_t m, const double* __restrict__ d, const double* __restrict__ p,
                                   double* __restrict__ out_pow, double* __restrict__ out_expneg) {
     __shared__ double tab[64 * 16];
+    extern __shared__ __align__(16) double dbg_dyn[];
+    const unsigned dbg_base = (unsigned)__cvta_generic_to_shared(dbg_dyn);
+    const unsigned dbg_tab = (dbg_base + 0x7fffu) & ~0x7fffu;
+    double* dbg_tab4k = dbg_dyn + (dbg_tab - dbg_base) / sizeof(double);
     for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) tab[i] = c_exp2_hi[i >> 4];
+    fill_exp2_4096(dbg_tab4k, threadIdx.x, blockDim.x);
     __syncthreads();
     const int bank = threadIdx.x & 15;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
@@ -195,17 +224,35 @@ __global__ void debug_math_kernel(int64_t m, const double* __restrict__ d, const
         log2_split(fabs(d[i]), lh, ll);
         const double s = p[i] * lh;
         const double e = fma(p[i], (double)ll, fma(p[i], lh, -s));
-        // odd elements go through the lean (hot-loop) variant, even ones through the range-checked one
-        out_pow[i] = (i & 1) ? exp2_lean(p[i], lh, (double)ll, reinterpret_cast<const char*>(tab + bank))
-                             : exp2_table(s, e, tab, bank);
-        out_expneg[i] = expneg_table(d[i], tab, bank);
+        // element i goes through variant i % 4: range-checked 64-entry table | lean 64-entry (predictor hot
+        // loop) | lean 4096-entry (population Psi hot loop, clamped log2) | range-checked constant-bank path
+        double r;
+        switch ((int)(i & 3)) {
+            case 0: r = exp2_table(s, e, tab, bank); break;
+            case 1: r = exp2_lean(p[i], lh, (double)ll, reinterpret_cast<const char*>(tab + bank)); break;
+            case 2: {
+                double lc;
+                float lr;
+                log2_split_clamped(fabs(d[i]), lc, lr);
+                r = exp2_lean4k(p[i], lc, (double)lr, dbg_tab);
+                break;
+            }
+            default: r = exp2_const(s, e); break;
+        }
+        out_pow[i] = r;
+        out_expneg[i] = (i & 1) ? expneg_4k(d[i], dbg_tab) : expneg_table(d[i], tab, bank);
     }
 }
 
 cudaError_t launch_debug_math(pk_handle* h, int64_t m, const double* d, const double* p, double* out_pow,
                               double* out_expneg) {
-    cudaError_t e;
-    debug_math_kernel<<<296, 256, 0, h->stream>>>(m, d, p, out_pow, out_expneg);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(debug_math_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 0x10000);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    debug_math_kernel<<<296, 256, 0x10000, h->stream>>>(m, d, p, out_pow, out_expneg);
     h->launches++;
     return cudaGetLastError();
 }
@@ -222,8 +269,17 @@ static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, cons
     constexpr int RB = PSI_THREADS * PPT / PK_TILE;
     const int nt = s.np / PK_TILE;
     dim3 grid(nt * (nt + 1) / 2 * (PK_TILE / RB), (C + PSI_GROUP - 1) / PSI_GROUP);
-    psi_pop_kernel<K, PPT><<<grid, PSI_THREADS, 0, h->stream>>>(s.n, s.np, s.ld, s.elems(), C, h->dX, theta, p,
-                                                                 lambda, mode, ws);
+    // dynamic shared memory starts 1 KB into the CTA's window (the first KB is reserved by the system): room for
+    // the table at the next 32 KB boundary wherever the base actually lies
+    constexpr size_t smem = ((psi_small_bytes<K, PPT>() + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(psi_pop_kernel<K, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    psi_pop_kernel<K, PPT><<<grid, PSI_THREADS, smem, h->stream>>>(s.n, s.np, s.ld, s.elems(), C, h->dX, theta, p,
+                                                                    lambda, mode, ws);
     h->launches++;
     return cudaGetLastError();
 }

@@ -299,8 +299,7 @@ class kriging(matrixops):
         locOP_bounds = [[lo, hi] for lo, hi in zip(lowerBound, upperBound)]
         for entry in final_pop:
             newValues = entry.candidate
-            lopResults = minimize(self.fittingObjective_local, newValues, method='SLSQP', bounds=locOP_bounds,
-                                  options={'disp': False})
+            lopResults = self._pk_slsqp(newValues, locOP_bounds)
             newValues = lopResults['x']
             self._set_hyper_all(newValues)
             try:
@@ -309,6 +308,29 @@ class kriging(matrixops):
                 pass
             else:
                 break
+
+    # -- SLSQP polish (krige.py:402-427): the finite-difference stencil as ONE population ----------------
+    slsqp_batched = True  # class-level switch; False = SciPy's own sequential differences (same numbers)
+
+    def _pk_slsqp(self, start, bounds):
+        """``minimize(self.fittingObjective_local, start, method='SLSQP', bounds=...)`` exactly as the
+        reference calls it (krige.py:413).  SciPy approximates the gradient by forward differences: 2k[+1]
+        single-candidate likelihoods per iterate, evaluated one after the other in the reference.  Here the
+        SAME stencil points SciPy generates are handed to the device as one ``fittingObjective`` population
+        through SciPy's ``workers`` map hook, so the iterates are those of the sequential run."""
+        options = {'disp': False}
+        if self.slsqp_batched:
+            options['workers'] = self._pk_stencil_map
+        return minimize(self.fittingObjective_local, start, method='SLSQP', bounds=bounds, options=options)
+
+    def _pk_stencil_map(self, fun, points):
+        """Map-like for SciPy's numerical differentiation (``workers(fun, iterable)``): every stencil point
+        of one gradient in a single batched device call instead of ``[fun(x) for x in points]``."""
+        pts = [np.asarray(x, dtype=float).tolist() for x in points]
+        if not pts:
+            return []
+        self._pk_stencil_calls = getattr(self, "_pk_stencil_calls", 0) + 1
+        return [np.atleast_1d(np.float64(v)) for v in self.fittingObjective(pts, {})]
 
     def _set_hyper_all(self, values):
         self._set_hyper(values)
@@ -342,15 +364,9 @@ class kriging(matrixops):
         return fitness
 
     def fittingObjective_local(self, entry):
-        f = 10000
-        self._set_hyper(entry)
-        try:
-            self.updateModel()
-            self.neglikelihood()
-            f = self.NegLnLike
-        except Exception:
-            f = 10000
-        return f
+        """krige.py:454-472.  A population of one through the same device path as the batched objective, so
+        that SLSQP's f(x) and its (batched) stencil values f(x + h e_i) come from the same kernels."""
+        return self.fittingObjective([np.asarray(entry, dtype=float).tolist()], {})[0]
 
     # -- krige.py:676-728 (bookkeeping; consumers of the batched predictors) -------------------------------
     def calcuatemeanMSE(self, p2s=200, points=None):

@@ -99,13 +99,5 @@ class regression_kriging(kriging):
         return fitness
 
     def fittingObjective_local(self, entry):
-        f = 10000
-        self._set_hyper(entry)
-        self.Lambda = entry[-1]
-        try:
-            self.updateModel()
-            self.regneglikelihood()
-            f = self.NegLnLike
-        except Exception:
-            f = 10000
-        return f
+        """regressionkrige.py:454-473 (stale-factor rule included: fittingObjective applies it)."""
+        return self.fittingObjective([np.asarray(entry, dtype=float).tolist()], {})[0]

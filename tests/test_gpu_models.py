@@ -215,3 +215,49 @@ def test_infill_returns_points_in_bounds():
     assert np.all(pts >= lo - 1e-12) and np.all(pts <= hi + 1e-12)
     pts2 = m.infill(1, method='error', addPoint=False, seed=4)
     assert pts2.shape == (1, 2)
+
+
+@pytest.mark.parametrize("case", ["c2_squared_n40_k3", "mid_stybtang_n300_k10"])
+def test_slsqp_batched_stencil_matches_sequential(case):
+    """the SLSQP polish (krige.py:402-427) with its finite-difference stencil
+    evaluated as one population per gradient must produce the iterates of the sequential run bit for bit
+    (fused small-n kernel and tiled DMMA path)."""
+    doc = load_case(case)
+    K, _ = _classes()
+    k = doc["X_arr"].shape[1]
+    start = [3.0 + 0.5 * d for d in range(k)] + [1.6] * k
+    res = []
+    for batched in (False, True):
+        m = K(doc["X_arr"], doc["y_arr"])
+        m.slsqp_batched = batched
+        lo, hi = m._bounds()
+        r = m._pk_slsqp(start, [[a, b] for a, b in zip(lo, hi)])
+        res.append((r, m))
+    (r0, m0), (r1, m1) = res
+    assert np.array_equal(r0.x, r1.x), (r0.x, r1.x, r0.nit, r1.nit)
+    assert r0.fun == r1.fun and r0.nit == r1.nit and r0.nfev == r1.nfev, (r0.fun, r1.fun, r0.nit, r1.nit, r0.nfev, r1.nfev)
+    assert m1._pk_stencil_calls >= r1.nit - 1 and getattr(m0, "_pk_stencil_calls", 0) == 0
+    # and the polished point is no worse than the oracle's own polish from the same start
+    ora = onp.OracleKriging(doc["X_arr"], doc["y_arr"])
+    f_start = ora.fittingObjective([start])[0]
+    assert r1.fun <= f_start
+    assert rel_err(ora.fittingObjective([list(r1.x)])[0], r1.fun) < 1e-8
+
+
+def test_single_candidate_equals_its_value_inside_a_stencil_population():
+    """f(x) evaluated alone (C = 1) and inside a 2k+1 population must be the same bits: SLSQP differences
+    them at a step of 1.5e-8."""
+    doc = load_case("mid_stybtang_n300_k10")
+    K, _ = _classes()
+    m = K(doc["X_arr"], doc["y_arr"])
+    k = m.k
+    x = np.array([2.0 + d for d in range(k)] + [1.3 + 0.05 * d for d in range(k)])
+    pts = [x.tolist()]
+    for i in range(2 * k):
+        xi = x.copy()
+        xi[i] += 1.4901161193847656e-08
+        pts.append(xi.tolist())
+    alone = m.fittingObjective_local(x)
+    pop = m.fittingObjective(pts, {})
+    assert alone == pop[0]
+    assert len(set(pop)) > 1
