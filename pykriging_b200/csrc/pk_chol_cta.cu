@@ -167,8 +167,10 @@ __device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const doubl
 // cp.async pipeline never drains between passes: while a pass is being solved and stored, the first
 // chunks of the next pass are already in flight.
 // ------------------------------------------------------------------------------------------------
+// tl != nullptr (diagnostic build only): lanes 0 of warps 0 and 4 accumulate clock64() deltas of the loop's
+// sections {barrier wait, early produce, first half, late produce, second half, store} into tl[0..5] / tl[8..13].
 __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
-                                             int rows) {
+                                             int rows, long long* tl = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     double* As = pipe;
@@ -229,23 +231,38 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     // (warps 0-3 before its first half, warps 4-7 between the halves): while one computes addresses the
     // other keeps the tensor pipe fed.
     const bool early = warp < 4;
+    long long tprev = 0, tacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const bool tlw = tl != nullptr && lane == 0 && (warp & 3) == 0;
+    if (tlw) tprev = clock64();
+#define PK_TL(i)                                  \
+    if (tlw) {                                    \
+        const long long tn_ = clock64();          \
+        tacc[i] += tn_ - tprev;                   \
+        tprev = tn_;                              \
+    }
     for (int g = 0; g < total; ++g) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
+        PK_TL(0)
         const bool more = g + STAGES - 1 < total;
         if (early) {
             if (more) produce();
             cp_async_commit();
         }
+        PK_TL(1)
         const double* as = As + cs * A_STAGE;
         const double* bs = Bs + cs * B_STAGE;
         cs = (cs == STAGES - 1) ? 0 : cs + 1;
         consume_half<0>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count);
+        PK_TL(2)
         if (!early) {
             if (more) produce();
             cp_async_commit();
         }
+        PK_TL(3)
         consume_half<1>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count);
+        PK_TL(4)
+        if (tlw) tacc[6] += 1;
         if (++ck == nkt) {
             // pass complete: store the solved rows, reset the accumulators, move to the next pass
 #pragma unroll
@@ -263,7 +280,13 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
             ++cb;
             row0 = first + cb * BM;
             pass_shape(row0, wrow, mi_count);
+            PK_TL(5)
         }
+    }
+#undef PK_TL
+    if (tlw) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) tl[(warp >> 2) * 8 + i] += tacc[i];
     }
     cp_async_wait<0>();
     __syncthreads();  // stages drained; the stores of this column are visible to the whole CTA
@@ -582,7 +605,7 @@ chol_cta_kernel(int C, int nt, int rows, int ld, size_t elems, double piv_tol, d
             }
             long long t0 = 0;
             if (TIMING) t0 = clock64();
-            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE);
+            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
             if (TIMING) tmv[3] += clock64() - t0;
         }
         if (TIMING) tmv[4] += 1;
@@ -615,17 +638,25 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
     const int grid = (C < per_sm * h->sm_count) ? C : per_sm * h->sm_count;
     if (getenv("PK_CTA_TIMING")) {  // diagnostic: per-phase cycle counts of the persistent kernel, printed to stderr
         long long* dbg = nullptr;
-        cudaMalloc((void**)&dbg, sizeof(long long) * 8 * grid);
-        cudaMemset(dbg, 0, sizeof(long long) * 8 * grid);
+        cudaMalloc((void**)&dbg, sizeof(long long) * (8 * grid + 16));
+        cudaMemset(dbg, 0, sizeof(long long) * (8 * grid + 16));
         cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
                                                                             ws, info, queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0);
         cudaStreamSynchronize(h->stream);
-        std::vector<long long> host(8 * (size_t)grid);
+        std::vector<long long> host(8 * (size_t)grid + 16);
         cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
         cudaFree(dbg);
         double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int b2 = 0; b2 < grid; ++b2)
             for (int i = 0; i < 8; ++i) sum[i] += (double)host[8 * b2 + i];
+        for (int w = 0; w < 2; ++w) {
+            const long long* t = host.data() + 8 * (size_t)grid + 8 * w;
+            const double it = (double)(t[6] > 0 ? t[6] : 1);
+            fprintf(stderr,
+                    "[pk cta timeline] CTA 0 warp %d: %.0f chunks; cycles per chunk: barrier %.0f, early produce %.0f, half0 %.0f, "
+                    "late produce %.0f, half1 %.0f, pass store (per chunk) %.0f\n",
+                    4 * w, it, t[0] / it, t[1] / it, t[2] / it, t[3] / it, t[4] / it, t[5] / it);
+        }
         fprintf(stderr,
                 "[pk cta timing] grid %d, candidates %.0f; cycles per candidate: diag product %.0f, factorise 64x64 %.0f, "
                 "copy-out %.0f, panel column %.0f; factorise = 8x8 block %.0f + scale %.0f + trailing %.0f\n",
