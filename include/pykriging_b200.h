@@ -94,6 +94,16 @@ int pk_predict_batch(pk_handle *h, int64_t m, const double *Xq, const double *th
 
 /* self.Psi / self.U attribute access (matrixops.py:29-32): n x n row-major copies of the correlation
  * matrix of the last pk_fit attempt and of the upper factor U = L^T of the last successful one. */
+/* Incremental form of kriging.addPoint (krige.py:135-156: append the sample, updateData, updatePsi -- a
+ * full O(n^2 k) Psi rebuild and O(n^3) factorisation in the reference).  With a cached factor (pk_fit) of
+ * the CURRENT data and hyper-parameters, appends sample (x_new[k], y_new), both in model units, by the
+ * bordered O(n^2) update of L, L^-1, L^-1 1 and L^-1 y, and returns the new (NegLnLike, mu, SigmaSqr,
+ * LnDetPsi) in out4.  *appended = 1 on success.  *appended = 0 and nothing modified when there is no
+ * cached factor for the current data, when n + 1 would cross a 64-row tile boundary, or when the bordered
+ * pivot is not positive (*info = n + 1, dpotrf convention): the caller then takes the reference's route,
+ * pk_set_data + pk_fit.  x_new / out4 / info: host or device pointers. */
+int pk_append_point(pk_handle *h, const double *x_new, double y_new, double *out4, int32_t *info, int32_t *appended);
+
 int pk_get_psi(pk_handle *h, double *out);
 int pk_get_U(pk_handle *h, double *out);
 

@@ -18,7 +18,7 @@ MODE_REGRESSION = 1
 # every symbol include/pykriging_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "pk_version", "pk_last_error", "pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit",
-    "pk_predict_batch", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
+    "pk_predict_batch", "pk_append_point", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
     "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
     "pk_fp64_peak", "pk_debug_math", "pk_set_cholesky_variant", "pk_set_predict_variant", "pk_set_overlap",
 ]
@@ -52,6 +52,8 @@ def load():
     lib.pk_fit.argtypes = [hp, c_dp, c_dp, ctypes.c_double, ctypes.c_int, c_dp, c_dp]
     lib.pk_predict_batch.argtypes = [hp, ctypes.c_int64, c_dp, c_dp, c_dp, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_double, ctypes.c_double, ctypes.c_double, c_dp, c_dp, c_dp]
+    lib.pk_append_point.argtypes = [hp, c_dp, ctypes.c_double, c_dp, c_dp, c_dp]
+    lib.pk_append_point.restype = ctypes.c_int
     lib.pk_get_psi.argtypes = [hp, c_dp]
     lib.pk_get_U.argtypes = [hp, c_dp]
     lib.pk_psi_batch.argtypes = [hp, ctypes.c_int, c_dp, c_dp, c_dp, ctypes.c_int, c_dp]
@@ -80,28 +82,8 @@ def load():
     for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
                  "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_set_workspace_limit"):
         getattr(lib, name).restype = ctypes.c_int
-    if hasattr(lib, "pk_opt_create"):
-        _declare_opt(lib)
     _lib = lib
     return lib
-
-
-def _declare_opt(lib):
-    hp = ctypes.c_void_p
-    c_dp = ctypes.c_void_p
-    lib.pk_opt_create.restype = ctypes.c_int
-    lib.pk_opt_create.argtypes = [hp, ctypes.POINTER(hp), ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, c_dp,
-                                  ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
-    lib.pk_opt_destroy.restype = ctypes.c_int
-    lib.pk_opt_destroy.argtypes = [hp]
-    lib.pk_opt_init.restype = ctypes.c_int
-    lib.pk_opt_init.argtypes = [hp]
-    lib.pk_opt_step.restype = ctypes.c_int
-    lib.pk_opt_step.argtypes = [hp, c_dp]
-    lib.pk_opt_get.restype = ctypes.c_int
-    lib.pk_opt_get.argtypes = [hp, ctypes.c_int, c_dp]
-    lib.pk_nll_population.restype = ctypes.c_int
-    lib.pk_nll_population.argtypes = [hp, hp, ctypes.c_int, c_dp, c_dp]
 
 
 def _addr(a):
@@ -185,6 +167,19 @@ class Handle(object):
         self._check(self.lib.pk_fit(self._h, _addr(theta), _addr(p), float(lam), int(mode), _addr(out4), _addr(info)),
                     "pk_fit")
         return out4, int(info[0])
+
+    def append_point(self, x_new, y_new):
+        """Bordered O(n^2) update of the cached factor with one more sample (model units).  Returns
+        (appended, out4, info); appended False = nothing changed, take the set_data + fit route."""
+        x = _f64(x_new)
+        out4 = np.empty(4, dtype=np.float64)
+        info = np.zeros(1, dtype=np.int32)
+        app = np.zeros(1, dtype=np.int32)
+        self._check(self.lib.pk_append_point(self._h, _addr(x), float(y_new), _addr(out4), _addr(info), _addr(app)),
+                    "pk_append_point")
+        if app[0]:
+            self.n += 1
+        return bool(app[0]), out4, int(info[0])
 
     # -- predictors -----------------------------------------------------------------------------
     def predict_batch(self, Xq, theta, p, mu, sigma2, y_min=0.0, ei_weight=-1.0, var_extra=0.0,

@@ -138,6 +138,8 @@ int pk_create(pk_handle** out, int device) {
         return 1;
     }
     e = cudaMalloc((void**)&h->d_hp, sizeof(double) * 2 * PK_MAX_K);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_fit_hp, sizeof(double) * 2 * PK_MAX_K);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_try_hp, sizeof(double) * 2 * PK_MAX_K);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_queue, sizeof(unsigned int) * PK_QUEUE_SLOTS);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -155,7 +157,7 @@ int pk_destroy(pk_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
-                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue};
+                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -258,8 +260,11 @@ int pk_set_data(pk_handle* h, int n, int k, const double* X, const double* y) {
     if (n < 2 || k < 1 || k > PK_MAX_K || !X || !y) PK_FAIL(h, "pk_set_data: need n>=2, 1<=k<=%d, X, y", PK_MAX_K);
     PK_CUDA(h, cudaSetDevice(h->device));
     PK_CUDA(h, cudaStreamSynchronize(h->stream));
-    PK_CUDA(h, regrow(&h->dX, (size_t)n * k));
-    PK_CUDA(h, regrow(&h->dy, (size_t)n));
+    // capacity up to the next tile boundary, so that pk_append_point can add samples in place
+    const int cap_rows = (n / PK_TILE + 1) * PK_TILE;
+    PK_CUDA(h, regrow(&h->dX, (size_t)cap_rows * k));
+    PK_CUDA(h, regrow(&h->dy, (size_t)cap_rows));
+    h->cap_rows = cap_rows;
     PK_CUDA(h, cudaMemcpyAsync(h->dX, X, sizeof(double) * n * k, cudaMemcpyDefault, h->stream));
     PK_CUDA(h, cudaMemcpyAsync(h->dy, y, sizeof(double) * n, cudaMemcpyDefault, h->stream));
     PK_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -449,6 +454,8 @@ int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, in
     if (to_device(h, theta, h->d_theta, (size_t)k, &d_theta)) return 1;
     if (to_device(h, p, h->d_p, (size_t)k, &d_p)) return 1;
     PK_CUDA(h, cudaMemcpyAsync(h->d_lambda, &lambda, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(h->d_try_hp, d_theta, sizeof(double) * k, cudaMemcpyDeviceToDevice, h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(h->d_try_hp + PK_MAX_K, d_p, sizeof(double) * k, cudaMemcpyDeviceToDevice, h->stream));
     PK_CUDA(h, pk::launch_psi_build(h, s, 1, d_theta, d_p, h->d_lambda, mode, h->d_try, h->d_info));
     PK_CUDA(h, pk::launch_extract_psi(h, s, h->d_try, h->d_psi, 1));
     PK_CUDA(h, pk::launch_cholesky(h, s, 1, h->d_try, h->d_info));
@@ -464,6 +471,11 @@ int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, in
         double* t = h->d_fit;
         h->d_fit = h->d_try;
         h->d_try = t;
+        t = h->d_fit_hp;
+        h->d_fit_hp = h->d_try_hp;
+        h->d_try_hp = t;
+        h->fit_lambda = lambda;
+        h->fit_mode = mode;
         PK_CUDA(h, pk::launch_fit_finalize(h, s));
         h->fit_valid = true;
         h->fit_n = h->n;
@@ -471,6 +483,48 @@ int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, in
     }
     if (out4) PK_CUDA(h, cudaMemcpy(out4, host4, sizeof(host4), cudaMemcpyDefault));
     if (info) PK_CUDA(h, cudaMemcpy(info, &host_info, sizeof(int32_t), cudaMemcpyDefault));
+    return 0;
+}
+
+int pk_append_point(pk_handle* h, const double* x_new, double y_new, double* out4, int32_t* info, int32_t* appended) {
+    if (!h) return 1;
+    if (!x_new || !appended) PK_FAIL(h, "pk_append_point: bad arguments");
+    *appended = 0;
+    if (h->n == 0) PK_FAIL(h, "pk_append_point: pk_set_data has not been called");
+    // in place only with a cached factor of the current data and room inside the padded order
+    if (!h->fit_valid || h->fit_n != h->n) return 0;
+    const int n = h->n, k = h->k;
+    const pk::TiledShape s = pk::tiled_shape(n, true);
+    if (n + 1 > s.np || n + 1 > h->cap_rows || s.np != h->fit_np) return 0;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    if (ensure_candidates(h, 1)) return 1;
+    // d_try is scratch between fits: [psi | l | t] at its head, the grown Psi copy behind them
+    double* scratch = h->d_try;
+    double* psi_new = h->d_try + 2 * s.np + 8;
+    PK_CUDA(h, cudaMemcpyAsync(h->dX + (size_t)n * k, x_new, sizeof(double) * k, cudaMemcpyDefault, h->stream));
+    const double diag = 1.0 + (h->fit_mode == PK_MODE_REGRESSION ? h->fit_lambda : PK_EPS_DIAG);
+    PK_CUDA(h, pk::launch_append_point(h, s, h->dX + (size_t)n * k, y_new, diag, scratch, h->d_info));
+    int32_t host_info = 0;
+    PK_CUDA(h, cudaMemcpyAsync(&host_info, h->d_info, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (info) PK_CUDA(h, cudaMemcpy(info, &host_info, sizeof(int32_t), cudaMemcpyDefault));
+    if (host_info != 0) return 0;  // not positive definite: nothing was modified (the sample row is beyond n)
+    PK_CUDA(h, cudaMemcpyAsync(h->dy + n, &y_new, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PK_CUDA(h, pk::launch_append_psi_copy(h, n, diag, h->d_psi, scratch, psi_new));
+    PK_CUDA(h, cudaMemcpyAsync(h->d_psi, psi_new, sizeof(double) * (size_t)(n + 1) * (n + 1), cudaMemcpyDeviceToDevice,
+                               h->stream));
+    h->n = n + 1;
+    h->fit_n = n + 1;
+    h->w_valid = false;
+    const pk::TiledShape s1 = pk::tiled_shape(n + 1, true);
+    PK_CUDA(h, pk::launch_nll_epilogue(h, s1, 1, h->d_fit, h->d_out, h->cap_C, h->d_info));
+    double host4[4];
+    for (int i = 0; i < 4; ++i)
+        PK_CUDA(h, cudaMemcpyAsync(&host4[i], h->d_out + (size_t)i * h->cap_C, sizeof(double), cudaMemcpyDeviceToHost,
+                                   h->stream));
+    PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (out4) PK_CUDA(h, cudaMemcpy(out4, host4, sizeof(host4), cudaMemcpyDefault));
+    *appended = 1;
     return 0;
 }
 

@@ -61,6 +61,11 @@ struct pk_handle {
     double* d_linv = nullptr; // fit_np x fit_np row-major L^-1 (lower)
     double* d_ad = nullptr;   // 2 x fit_np : a = L^-1 1, d = L^-1 y
     double* d_w = nullptr;    // fit_np : w = L^-T (d - mu a)
+    double* d_fit_hp = nullptr;  // 2 x PK_MAX_K: (theta | p) of the cached factor (pk_append_point)
+    double* d_try_hp = nullptr;  // ... of the attempt
+    double fit_lambda = 0.0;
+    int fit_mode = 0;
+    int cap_rows = 0;            // sample capacity of dX / dy (rows)
     double w_mu = 0.0;
     bool w_valid = false;
     bool fit_valid = false;
@@ -113,6 +118,9 @@ cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const doub
                            double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
                            double* ei);
 cudaError_t launch_extract_U(pk_handle* h, const TiledShape& s, double* out);
+cudaError_t launch_append_point(pk_handle* h, const TiledShape& s, const double* xnew_dev, double y_new, double diag,
+                                double* scratch, int32_t* info);
+cudaError_t launch_append_psi_copy(pk_handle* h, int n, double diag, const double* old, const double* psi, double* out);
 cudaError_t measure_fp64_peak(pk_handle* h, double* dmma, double* dfma);
 
 // phase timing helpers (no-ops unless h->profiling)

@@ -63,6 +63,121 @@ __global__ void extract_psi_kernel(int n, int ld, size_t elems, const double* __
     if (c < n) o[(size_t)r * n + c] = (c <= r) ? M[(size_t)r * ld + c] : M[(size_t)c * ld + r];
 }
 
+// ---- incremental append of one sample to a cached factor (pk_append_point) ---------------------------
+// Replaces the full rebuild kriging.addPoint triggers (krige.py:135-156 -> updateData -> updatePsi:
+// O(n^2 k) pow + n^3/3 flop) by the bordered update of L, L^-1, a = L^-1 1 and d = L^-1 y:
+//     psi = corr(X, x_new);  l = L^-1 psi;  t = sqrt(diag - |l|^2)   (diag = 1 + eps | 1 + lambda)
+//     L <- [L 0; l^T t],  L^-1 <- [L^-1 0; -(l^T L^-1)/t  1/t],  a_n = (1 - l.a)/t,  d_n = (y_new - l.d)/t
+// O(n^2) flop and bytes.  The padded order np is unchanged (the caller refits when n crosses a tile boundary).
+__global__ void append_psi_kernel(int n, int k, const double* __restrict__ X, const double* __restrict__ xnew,
+                                  const double* __restrict__ hp, double* __restrict__ psi) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) psi[r] = exp(-corr_exponent(X + (size_t)r * k, xnew, hp, hp + PK_MAX_K, k));
+}
+
+// l[c] = sum_{r <= c} Linv[c][r] psi[r], one warp per row c (Linv row-major, lower)
+__global__ void append_solve_kernel(int n, int np, const double* __restrict__ linv, const double* __restrict__ psi,
+                                    double* __restrict__ l) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n) return;
+    const double* row = linv + (size_t)c * np;
+    double acc = 0.0;
+    for (int r = lane; r <= c; r += 32) acc = fma(row[r], psi[r], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) l[c] = acc;
+}
+
+// one CTA: pivot test, then row n of L, the new entries of a and d.  info[0] = n + 1 on failure (dpotrf's
+// "leading minor of order n+1"), in which case nothing is modified.
+__global__ void append_pivot_kernel(int n, int np, int ld, double diag, double piv_tol, double y_new,
+                                    const double* __restrict__ l, double* __restrict__ M, double* __restrict__ ad,
+                                    double* __restrict__ scal, int32_t* __restrict__ info) {
+    __shared__ double scratch[32];
+    const int tid = threadIdx.x;
+    double sll = 0.0, sla = 0.0, sld = 0.0;
+    for (int c = tid; c < n; c += blockDim.x) {
+        const double lc = l[c];
+        sll = fma(lc, lc, sll);
+        sla = fma(lc, ad[c], sla);
+        sld = fma(lc, ad[np + c], sld);
+    }
+    sll = block_sum(sll, scratch);
+    sla = block_sum(sla, scratch);
+    sld = block_sum(sld, scratch);
+    const double piv = diag - sll;
+    if (!(piv > piv_tol * diag)) {
+        if (tid == 0) info[0] = n + 1;
+        return;
+    }
+    const double t = sqrt(piv);
+    for (int c = tid; c < n; c += blockDim.x) M[(size_t)n * ld + c] = l[c];
+    if (tid == 0) {
+        info[0] = 0;
+        M[(size_t)n * ld + n] = t;
+        const double an = (1.0 - sla) / t, dn = (y_new - sld) / t;
+        M[(size_t)np * ld + n] = an;
+        M[(size_t)(np + 1) * ld + n] = dn;
+        ad[n] = an;
+        ad[np + n] = dn;
+        scal[0] = t;
+    }
+}
+
+// new row n of L^-1: Linv[n][r] = -(1/t) sum_{c >= r} l[c] Linv[c][r], Linv[n][n] = 1/t; mirrored into the
+// inverse rows of M (R = L^-T: R[r][n]).  One thread per column r (coalesced over r for every c).
+__global__ void append_inverse_kernel(int n, int np, int ld, const double* __restrict__ l, double* __restrict__ linv,
+                                      double* __restrict__ M, const double* __restrict__ scal,
+                                      const int32_t* __restrict__ info) {
+    if (info[0] != 0) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    const double t = scal[0];
+    double v;
+    if (r == n) {
+        v = 1.0 / t;
+    } else {
+        double acc = 0.0;
+        for (int c = r; c < n; ++c) acc = fma(l[c], linv[(size_t)c * np + r], acc);
+        v = -acc / t;
+    }
+    linv[(size_t)n * np + r] = v;
+    M[(size_t)(np + PK_AUG_ROWS + r) * ld + n] = v;
+}
+
+// Psi copy (dense, row-major) grown from n x n to (n+1) x (n+1): border = psi_new, corner = diag
+__global__ void append_psi_copy_kernel(int n, double diag, const double* __restrict__ old, const double* __restrict__ psi,
+                                       double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c > n) return;
+    double v;
+    if (r < n && c < n) v = old[(size_t)r * n + c];
+    else if (r == n && c == n) v = diag;
+    else v = psi[(r == n) ? c : r];
+    out[(size_t)r * (n + 1) + c] = v;
+}
+
+cudaError_t launch_append_point(pk_handle* h, const TiledShape& s, const double* xnew_dev, double y_new, double diag,
+                                double* scratch /* >= 2 np + 8 doubles */, int32_t* info) {
+    const int n = s.n, np = s.np, k = h->k;
+    double* psi = scratch;
+    double* l = scratch + np;
+    double* scal = scratch + 2 * np;
+    append_psi_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, k, h->dX, xnew_dev, h->d_fit_hp, psi);
+    append_solve_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(n, np, h->d_linv, psi, l);
+    append_pivot_kernel<<<1, 256, 0, h->stream>>>(n, np, s.ld, diag, h->pivot_tol, y_new, l, h->d_fit, h->d_ad, scal, info);
+    append_inverse_kernel<<<(n + 256) / 256, 256, 0, h->stream>>>(n, np, s.ld, l, h->d_linv, h->d_fit, scal, info);
+    h->launches += 4;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_append_psi_copy(pk_handle* h, int n, double diag, const double* old, const double* psi, double* out) {
+    dim3 grid((n + 256) / 256, n + 1);
+    append_psi_copy_kernel<<<grid, 256, 0, h->stream>>>(n, diag, old, psi, out);
+    h->launches++;
+    return cudaGetLastError();
+}
+
 // ---- fused predictor -------------------------------------------------------------------------------
 constexpr int PKC = 16;           // K chunk of the L^-1 pipeline
 constexpr int PSLD = PKC + 4;     // 20

@@ -125,6 +125,8 @@ class kriging(matrixops):
         return X
 
     # -- krige.py:135-178 -------------------------------------------------------------------------------
+    incremental_addpoint = True  # bordered O(n^2) factor update when possible; False = always rebuild
+
     def addPoint(self, newX, newy, norm=True):
         if norm:
             newX = self.normX(newX)
@@ -132,6 +134,8 @@ class kriging(matrixops):
         self.X = np.append(self.X, [newX], axis=0)
         self.y = np.append(self.y, newy)
         self.n = self.X.shape[0]
+        if self.incremental_addpoint and self._pk_try_append(newX, newy, self._pk_mode):
+            return
         self.updateData()
         while True:
             try:

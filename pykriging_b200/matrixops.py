@@ -82,6 +82,7 @@ class matrixops(object):
         self._U_host = None
         self._psi_ever = False
         self._pending_factor = None  # (theta, pl, Lambda, mode): factor to restore lazily
+        self._factor_params = None   # (theta, pl, Lambda, mode) of the factor cached on the device
 
     def _pk_ensure_factor(self):
         """After a batched fittingObjective the reference's self.U is the factor of the last
@@ -92,7 +93,8 @@ class matrixops(object):
         if pend is not None:
             self._pending_factor = None
             th, pl, lam, mode = pend
-            self._pk_handle().fit(th, pl, lam, mode)
+            _, info = self._pk_handle().fit(th, pl, lam, mode)
+            self._factor_params = (th.copy(), pl.copy(), float(lam), mode) if info == 0 else None
             self._U_host = None
             self._psi_host = None
 
@@ -145,6 +147,7 @@ class matrixops(object):
         self._pk_handle().set_data(np.ascontiguousarray(self.X, dtype=float),
                                    np.ascontiguousarray(self.y, dtype=float))
         self._pending_factor = None
+        self._factor_params = None  # the device drops its cached factor with the old data
 
     # -- matrixops.py:24-32 / 34-42 ---------------------------------------------------------------
     def _pk_factorise(self, mode):
@@ -161,6 +164,31 @@ class matrixops(object):
         self._has_U = True
         self._U_host = None
         self._fit_vals = out4
+        self._factor_params = (np.array(self.theta, dtype=float), np.array(self.pl, dtype=float), lam, mode)
+
+    def _pk_try_append(self, newX, newy, mode):
+        """addPoint without the rebuild: when the device holds the factor of the
+        CURRENT theta / pl / Lambda for the data before the append, border it with the new sample (O(n^2))
+        instead of updateData + updatePsi (O(n^2 k) pow + n^3/3 flop).  True = done: the state is what
+        updateData(); updatePsi() would have left (U current, mu / SigmaSqr still those of the old model, as in
+        the reference).  False = nothing happened, take the reference's route."""
+        fp = self._factor_params
+        if fp is None or not self._has_U or self._pending_factor is not None:
+            return False
+        lam = float(self.Lambda) if mode == _lib.MODE_REGRESSION else 0.0
+        if fp[3] != mode or fp[2] != lam or not np.array_equal(fp[0], np.asarray(self.theta, dtype=float)) \
+                or not np.array_equal(fp[1], np.asarray(self.pl, dtype=float)):
+            return False
+        appended, out4, _ = self._pk_handle().append_point(np.asarray(newX, dtype=float), float(newy))
+        if not appended:
+            return False
+        self.one = np.ones(self.n)
+        self.psi = np.zeros((self.n, 1))
+        self._psi_host = None
+        self._U_host = None
+        self._fit_vals = out4
+        self.__dict__["_pk_appends"] = self.__dict__.get("_pk_appends", 0) + 1
+        return True
 
     def updatePsi(self):
         self._pk_factorise(_lib.MODE_INTERP)

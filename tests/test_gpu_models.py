@@ -236,7 +236,7 @@ def test_slsqp_batched_stencil_matches_sequential(case):
     (r0, m0), (r1, m1) = res
     assert np.array_equal(r0.x, r1.x), (r0.x, r1.x, r0.nit, r1.nit)
     assert r0.fun == r1.fun and r0.nit == r1.nit and r0.nfev == r1.nfev, (r0.fun, r1.fun, r0.nit, r1.nit, r0.nfev, r1.nfev)
-    assert m1._pk_stencil_calls >= r1.nit - 1 and getattr(m0, "_pk_stencil_calls", 0) == 0
+    assert m1._pk_stencil_calls == r1.njev and getattr(m0, "_pk_stencil_calls", 0) == 0  # one population per gradient
     # and the polished point is no worse than the oracle's own polish from the same start
     ora = onp.OracleKriging(doc["X_arr"], doc["y_arr"])
     f_start = ora.fittingObjective([start])[0]
@@ -261,3 +261,48 @@ def test_single_candidate_equals_its_value_inside_a_stencil_population():
     pop = m.fittingObjective(pts, {})
     assert alone == pop[0]
     assert len(set(pop)) > 1
+
+
+@pytest.mark.parametrize("regression", [False, True])
+@pytest.mark.parametrize("n0", [30, 60, 150])
+def test_incremental_addpoint_matches_rebuild(n0, regression):
+    """addPoint through the bordered O(n^2) factor update must leave the model in
+    the state the reference's rebuild (updateData + updatePsi, krige.py:135-156) leaves it in -- several
+    appends in a row, across a 64-row tile boundary (n0 = 60: the library falls back to the rebuild there),
+    interpolating and regression models."""
+    K, R = _classes()
+    cls = R if regression else K
+    k = 3
+    X = onp.rlh(n0, k, 21)
+    y = onp.f_squared(X)
+    hyper = [4.0, 2.5, 6.0, 1.9, 1.85, 1.95] + ([0.01] if regression else [])
+    new_pts = onp.rlh(7, k, 99) * 0.9 + 0.05
+    models = []
+    for incremental in (True, False):
+        m = cls(X, y)
+        m.incremental_addpoint = incremental
+        m.update(hyper)
+        (m.regneglikelihood if regression else m.neglikelihood)()
+        mu_before = m.mu
+        for q in new_pts:
+            m.addPoint(q, float(onp.f_squared(q[None, :])[0]))
+            assert m.mu == mu_before  # addPoint refreshes U, not mu / SigmaSqr (SURVEY App. A.5)
+        (m.regneglikelihood if regression else m.neglikelihood)()
+        models.append(m)
+    inc, full = models
+    assert inc.n == full.n == n0 + 7
+    # the bordered path really ran (n0 = 60: the append that crosses n = 64 is a rebuild)
+    assert inc.__dict__.get("_pk_appends", 0) == (6 if n0 == 60 else 7) and "_pk_appends" not in full.__dict__
+    assert rel_err(inc.NegLnLike, full.NegLnLike) < 1e-10
+    assert rel_err(inc.mu, full.mu) < 1e-10 and rel_err(inc.SigmaSqr, full.SigmaSqr) < 1e-10
+    assert np.allclose(inc.U, full.U, rtol=1e-9, atol=1e-12)
+    assert np.allclose(inc.Psi, full.Psi, rtol=0, atol=1e-15)
+    q = np.array([0.37, 0.52, 0.61])
+    assert rel_err(inc.predict(q), full.predict(q)) < 1e-9
+    assert abs(inc.predict_var(q) - full.predict_var(q)) < 1e-8 * max(1.0, float(full.SigmaSqr) ** 0.5)
+    assert abs(inc.expimp(inc.normX(q.copy())) - full.expimp(full.normX(q.copy()))) < 1e-8
+    # and against the CPU oracle on the grown data set
+    ora = onp.OracleKriging(inc.X, inc.y, regression=regression, normalize=False)
+    ora.update(hyper)
+    ora.neglikelihood()
+    assert rel_err(inc.NegLnLike, ora.NegLnLike) < 1e-9
