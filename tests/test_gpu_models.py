@@ -306,3 +306,34 @@ def test_incremental_addpoint_matches_rebuild(n0, regression):
     ora.update(hyper)
     ora.neglikelihood()
     assert rel_err(inc.NegLnLike, ora.NegLnLike) < 1e-9
+
+
+def test_cross_validation_scvr_matches_direct_prediction():
+    """the leave-one-out driver (CrossValidation.py:57-123) on the device path.
+    Whatever hyper-parameters the n trainings select, every left-out prediction must equal the oracle's
+    predictor evaluated with THAT model's theta / p on the (n-1)-point data set."""
+    from pykriging_b200.CrossValidation import Cross_Validation
+
+    K, _ = _classes()
+    X = onp.rlh(14, 2, 8)
+    y = onp.f_branin(X)
+    base = K(X, y)
+    cv = Cross_Validation(base, name="cv", seed=11, pop_size=24, max_evaluations=600)
+    pred, var, scvr = cv.calculate_SCVR(optimiser='ga')
+    assert len(pred) == len(var) == len(scvr) == 14 and len(cv.models) == 14
+    for i, m in enumerate(cv.models):
+        assert m.n == 13
+        m.neglikelihood()  # predictions after train() use the mu / SigmaSqr train() left behind (App. A.5)
+    ynorm = (base.y - base.y.min()) / (base.y.max() - base.y.min())
+    for i, m in enumerate(cv.models):
+        xq = m.normX(np.array(base.X[i], dtype=float))
+        ref = onp.predict_batch_fast(m.X, m.y, m.theta, m.pl, onp.EPS_DIAG, np.array([xq]))
+        assert rel_err(m.predict_normalized(xq), ref["yhat"][0]) < 1e-8
+        assert np.isfinite(scvr[i]) and np.isfinite(pred[i]) and var[i] >= 0.0
+    # a smooth function sampled on a 14-point plan: the cross-validated predictions track the samples
+    resid = np.array([m.normy(p) for m, p in zip(cv.models, pred)]) - ynorm
+    assert np.sqrt(np.mean(resid ** 2)) < 0.35
+    rmse, r2 = cv.calculate_RMSE_Rsquared('ga', 6)
+    assert rmse.startswith('RMSE = ') and r2.startswith('Rsquared = ')
+    avg, std = cv.leave_n_out(q=3)
+    assert np.isfinite(avg) and np.isfinite(std)

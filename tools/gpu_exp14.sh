@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_models.py -m gpu -x -q 2>&1 | grep -v "site-packages" | tail -25
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | grep -v "site-packages" | tail -25
