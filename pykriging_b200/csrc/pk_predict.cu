@@ -346,33 +346,32 @@ constexpr int PR_QT = 32;
 constexpr int PR_KC = 16;
 constexpr int PR_ALD = PR_KC + 4;
 
+// One 16-sample chunk of v += psi_chunk * Linv_chunk^T for this warp's column blocks LO .. NTW-1.  The B
+// operand comes from the warp's private shared-memory stage: block ni = 8 rows x 16 k (1 KB), 16-byte pieces
+// XOR-swizzled with the row so that the fragment loads are conflict free without padding
+// (boff[ks] = (fc & 1) + 2 * ((2 ks) ^ (fc >> 1) ^ fr), precomputed per lane).
 template <int NTW, int LO>
-__device__ __forceinline__ void pred_consume(double (&acc)[4][NTW][2], double (&breg)[2][NTW], const double* As,
-                                             const double* __restrict__ brow, size_t ni_stride, int kcol,
-                                             bool prefetch_next_chunk, unsigned valid_mask, int lane) {
+__device__ __forceinline__ void pred_consume(double (&acc)[4][NTW][2], const double* As, const double* Bw,
+                                             const int (&boff)[4], int lane) {
     const int fr = lane >> 2, fc = lane & 3;
     const double* a_s = As + fr * PR_ALD + fc;
+    const double* b_s = Bw + fr * 16;
 #pragma unroll
     for (int ks = 0; ks < PR_KC / 4; ++ks) {
-        // prefetch the B fragments of the next k-step (next chunk's first step from the last one)
-        if (ks < PR_KC / 4 - 1 || prefetch_next_chunk) {
-#pragma unroll
-            for (int ni = LO; ni < NTW; ++ni)
-                breg[(ks + 1) & 1][ni] =
-                    ((valid_mask >> ni) & 1u) ? __ldg(brow + ni * ni_stride + kcol + 4 * (ks + 1)) : 0.0;
-        }
-        double a[4];
+        double a[4], b[NTW];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[mi * 8 * PR_ALD + 4 * ks];
 #pragma unroll
+        for (int ni = LO; ni < NTW; ++ni) b[ni] = b_s[ni * 128 + boff[ks]];
+#pragma unroll
         for (int ni = LO; ni < NTW; ++ni) {
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], breg[ks & 1][ni]);
+            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
     }
 }
 
-constexpr int PR_XS_MAX = 4096;  // sample coordinates staged in shared memory when n * k fits (32 KB)
+constexpr int PR_XS_MAX = 3072;  // sample coordinates staged in shared memory when n * k fits (24 KB)
 
 // KK > 0: number of design variables known at compile time (theta, p, the query point in registers, a
 // straight-line psi chain); KK == 0: any k <= PK_MAX_K.
@@ -390,7 +389,10 @@ predict_reg_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X
     double2* thp = reinterpret_cast<double2*>(xq + PR_QT * PK_MAX_K);  // PK_MAX_K
     double (*ypart)[PR_QT] = reinterpret_cast<double (*)[PR_QT]>(thp + PK_MAX_K);
     double (*qpart)[PR_QT + 1] = reinterpret_cast<double (*)[PR_QT + 1]>(ypart + PR_WARPS);
-    double* Xs = reinterpret_cast<double*>(qpart + PR_WARPS);       // n x k when it fits
+    // B stages: 2 x (16 warps x NTW blocks x 128 doubles), every warp owns its slice
+    double* Bst = reinterpret_cast<double*>(qpart + PR_WARPS);
+    Bst += (16 - ((size_t)(Bst - pr_smem) & 15)) & 15;              // 128-byte aligned rows
+    double* Xs = Bst + 2 * PR_WARPS * NTW * 128;                    // n x k when it fits
     const bool x_staged = (n * k <= PR_XS_MAX);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fc = lane & 3;
@@ -460,42 +462,71 @@ predict_reg_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int ni = 0; ni < NTW; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    double breg[2][NTW];
-    // B fragment base: row (8 warp + fr) of the first 128-column group, k offset fc; block ni adds 128 rows
-    const double* brow = linv + (size_t)(8 * warp + fr) * np + fc;
-    const size_t ni_stride = (size_t)(8 * PR_WARPS) * np;
+    // L^-1 operand: rows (columns of v) 128 ni + 8 warp .. + 7, 16 samples per chunk, streamed from L2 into this
+    // warp's shared stage one whole chunk ahead (cp.async, 8 pieces of 16 bytes per lane and chunk): the
+    // L2 latency hides behind a chunk of DMMAs instead of a single k-step.  Blocks left of the chunk (zero part
+    // of the triangular L^-1) are neither loaded nor multiplied: the first live block is dispatched through a
+    // warp-uniform switch (a predicated-off DMMA would still occupy the tensor pipe).
     unsigned valid_mask = 0;
 #pragma unroll
     for (int ni = 0; ni < NTW; ++ni)
         if (8 * PR_WARPS * ni + 8 * warp < np) valid_mask |= 1u << ni;
-    if (need_s) {
+    double* Bw = Bst + warp * NTW * 128;
+    constexpr int BSTAGE = PR_WARPS * NTW * 128;
+    int boff[4];
 #pragma unroll
-        for (int ni = 0; ni < NTW; ++ni) breg[0][ni] = ((valid_mask >> ni) & 1u) ? __ldg(brow + ni * ni_stride) : 0.0;
+    for (int ks = 0; ks < 4; ++ks) boff[ks] = (fc & 1) + 2 * ((2 * ks) ^ (fc >> 1) ^ fr);
+    auto first_live = [&](int kc) {
+        // block ni covers columns 128 ni + 8 warp .. + 7 and is needed iff that reaches 16 kc
+        const int num = PR_KC * kc - 8 * warp - 7;
+        return (num <= 0) ? 0 : ((num + 8 * PR_WARPS - 1) / (8 * PR_WARPS));
+    };
+    auto load_B = [&](int kc) {
+        const int lo = first_live(kc);
+        double* dst = Bw + (kc & 1) * BSTAGE;
+        const double* src = linv + (size_t)(8 * warp) * np + PR_KC * kc;
+#pragma unroll
+        for (int i = 0; i < 2 * NTW; ++i) {
+            const int idx = i * 32 + lane, ni = idx >> 6, row = (idx >> 3) & 7, piece = idx & 7;
+            if (ni >= lo && ((valid_mask >> ni) & 1u))
+                cp_async16(dst + ni * 128 + row * 16 + 2 * (piece ^ row),
+                           src + (size_t)(8 * PR_WARPS * ni + row) * np + 2 * piece);
+        }
+    };
+    if (need_s) {
+        // blocks beyond the padded order are never loaded: they must read as zeros in both stages
+#pragma unroll
+        for (int ni = 0; ni < NTW; ++ni)
+            if (!((valid_mask >> ni) & 1u))
+                for (int i = lane; i < 128; i += 32) Bw[ni * 128 + i] = Bw[BSTAGE + ni * 128 + i] = 0.0;
+        __syncwarp();
+        load_B(0);
     }
+    cp_async_commit();
     make_psi(0, As[0]);
     for (int kc = 0; kc < nch; ++kc) {
-        __syncthreads();  // chunk kc of psi is complete; the other A stage is free again
+        if (need_s && kc + 1 < nch) load_B(kc + 1);  // the stage it overwrites was consumed by this warp in chunk kc - 1
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();  // chunk kc of psi is complete (and every lane's B pieces have landed); the other A stage is free
         if (kc + 1 < nch) make_psi(kc + 1, As[(kc + 1) & 1]);
         if (need_s) {
-            // first live block: block ni covers columns 128 ni + 8 warp .. + 7 and is needed iff that reaches 16 kc
-            const int num = PR_KC * kc - 8 * warp - 7;
-            const int lo = (num <= 0) ? 0 : ((num + 8 * PR_WARPS - 1) / (8 * PR_WARPS));
-            const bool pf = kc + 1 < nch;
             const double* as = As[kc & 1];
-            const int kcol = PR_KC * kc;
-            switch (lo) {
-                case 0: pred_consume<NTW, 0>(acc, breg, as, brow, ni_stride, kcol, pf, valid_mask, lane); break;
+            const double* bw = Bw + (kc & 1) * BSTAGE;
+            switch (first_live(kc)) {
+                case 0: pred_consume<NTW, 0>(acc, as, bw, boff, lane); break;
                 case 1:
-                    if (NTW > 1) pred_consume<NTW, (NTW > 1 ? 1 : 0)>(acc, breg, as, brow, ni_stride, kcol, pf, valid_mask, lane);
+                    if (NTW > 1) pred_consume<NTW, (NTW > 1 ? 1 : 0)>(acc, as, bw, boff, lane);
                     break;
                 case 2:
-                    if (NTW > 2) pred_consume<NTW, (NTW > 2 ? 2 : 0)>(acc, breg, as, brow, ni_stride, kcol, pf, valid_mask, lane);
+                    if (NTW > 2) pred_consume<NTW, (NTW > 2 ? 2 : 0)>(acc, as, bw, boff, lane);
                     break;
                 case 3:
-                    if (NTW > 3) pred_consume<NTW, (NTW > 3 ? 3 : 0)>(acc, breg, as, brow, ni_stride, kcol, pf, valid_mask, lane);
+                    if (NTW > 3) pred_consume<NTW, (NTW > 3 ? 3 : 0)>(acc, as, bw, boff, lane);
                     break;
                 default: break;
             }
+            __syncwarp();  // all lanes are done with this stage before the next load_B overwrites it
         }
     }
     // ---- reductions: yhat partials over the 16 sample slots, |v|^2 over columns -------------------
@@ -583,7 +614,8 @@ static cudaError_t launch_predict_reg_k(pk_handle* h, int64_t m, const double* X
     const int need_s = (sout != nullptr || ei != nullptr) ? 1 : 0;
     const int64_t blocks = (m + PR_QT - 1) / PR_QT;
     constexpr size_t smem = sizeof(double) * (64 * 16 + 3 * 64 * 16 + 2 * PR_QT * PR_ALD + PR_QT * PK_MAX_K +
-                                              2 * PK_MAX_K + PR_WARPS * PR_QT + PR_WARPS * (PR_QT + 1) + PR_XS_MAX);
+                                              2 * PK_MAX_K + PR_WARPS * PR_QT + PR_WARPS * (PR_QT + 1) + 16 +
+                                              2 * PR_WARPS * NTW * 128 + PR_XS_MAX);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e =
