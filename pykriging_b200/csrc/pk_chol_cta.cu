@@ -19,6 +19,8 @@
 //
 // Two CTAs are resident per SM (256 threads, 128 registers, ~99 KB shared memory each): while one
 // sits in the latency-bound 64x64 factorisation the other keeps the FP64 tensor pipe busy.
+#include <cuda.h>
+
 #include <cstdio>
 #include <cstdlib>
 
@@ -29,39 +31,62 @@ namespace pk {
 namespace cta {
 
 constexpr int THREADS = 256;
-constexpr int KC = 16;             // K chunk per pipeline stage
-constexpr int SLD = KC + 4;        // 20: conflict-free fragment loads (row stride == 4 mod 16 doubles)
-constexpr int STAGES = 3;
+constexpr int KC = 16;             // K chunk per pipeline stage: one row of a stage = 16 doubles = 128 bytes
+constexpr int STAGES = 4;
 constexpr int BM = 128;            // rows per panel pass (8 warps x 16 rows)
-constexpr int A_STAGE = BM * SLD;
-constexpr int B_STAGE = PK_TILE * SLD;
+// A stage = two TMA boxes of 64 rows x 128 bytes, B stage = one; dense rows, 32-byte atoms XOR-swizzled with the
+// row (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): element (r, c) of a box lives at r * 16 + (((c >> 2) ^ (r & 3)) << 2)
+// + (c & 3).  A DMMA fragment load reads, per half-warp, 4 consecutive k of 4 consecutive rows: with the 32-byte
+// atom of row r rotated by r & 3 those are 16 different 8-byte bank pairs (the 16-byte swizzle of plain
+// SWIZZLE_128B maps rows r and r ^ 1 onto the same 32 bytes: measured 1.1e9 bank conflicts per launch).
+constexpr int BOX_ROWS = PK_TILE;
+constexpr int BOX_DOUBLES = BOX_ROWS * KC;  // 8 KB
+constexpr int A_STAGE = BM * KC;
+constexpr int B_STAGE = PK_TILE * KC;
 constexpr int PIPE_DOUBLES = STAGES * (A_STAGE + B_STAGE);
 constexpr int TS = PK_TILE + 4;    // 68: stride of the diagonal tile while it is factorised in smem
 constexpr int DLD = 12;            // row stride of the inverted 8x8 diagonal blocks
 constexpr int D_DOUBLES = 8 * 8 * DLD;
-constexpr int SMEM_DOUBLES = PIPE_DOUBLES + D_DOUBLES + PK_TILE + 2;  // + diag0[64] + control words
+constexpr int SMEM_DOUBLES = PIPE_DOUBLES + D_DOUBLES + PK_TILE + 2 + STAGES;  // + diag0[64] + control words + mbarriers
+constexpr int SMEM_ALIGN = 1024;   // the swizzle pattern is a function of the shared address: stages on 1 KB boundaries
 static_assert((PK_TILE + 32) * TS <= STAGES * A_STAGE, "the diagonal tile reuses the pipeline buffers");
 
 __device__ __forceinline__ double negd(double x) {
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));  // sign flip on the ALU pipe
 }
 
-// acc(8*MI x 64 per warp) -= A(8*MI x 16) * B(64 x 16)^T for one stage.  MI (rows of 8 this warp owns in
+// acc(8*MI x 64 per warp) += A(8*MI x 16) * B(64 x 16)^T for one stage (the products are accumulated with a
+// PLUS sign and subtracted from the original tile in one go when it arrives with the solve chunks: no sign
+// flips in the hot loop -- every non-DMMA instruction costs the scheduler's dispatch port a cycle the tensor
+// pipe does not get).  MI (rows of 8 this warp owns in
 // the pass) is a template parameter, selected by a warp-uniform branch: a DMMA that is merely
 // predicated off still occupies its issue slots on the tensor pipe (measured: profiles/).
+// Per-lane swizzled column offsets of the four k-steps of a chunk: lane (fr, fc) reads column 4i + fc of a row
+// whose index is fr mod 8:  soff[i] = ((i ^ (fr & 3)) << 2) + fc.
+struct Frag {
+    int soff[4];
+};
+__device__ __forceinline__ Frag make_frag(int lane) {
+    const int fr = lane >> 2, fc = lane & 3;
+    Frag f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f.soff[i] = ((i ^ (fr & 3)) << 2) + fc;
+    return f;
+}
+
 template <int MI, int HALF>
 __device__ __forceinline__ void gemm_consume(double (&acc)[2][8][2], const double* As, const double* Bs, int wrow,
-                                             int lane) {
-    const int fr = lane >> 2, fc = lane & 3;
-    const double* a_s = As + (wrow + fr) * SLD + fc;
-    const double* b_s = Bs + fr * SLD + fc;
+                                             int lane, const Frag& fg) {
+    const int fr = lane >> 2;
+    const double* a_s = As + (wrow + fr) * KC;
+    const double* b_s = Bs + fr * KC;
 #pragma unroll
-    for (int kk = HALF * (KC / 2); kk < (HALF + 1) * (KC / 2); kk += 4) {
+    for (int i = 2 * HALF; i < 2 * HALF + 2; ++i) {
         double a[MI], b[8];
 #pragma unroll
-        for (int mi = 0; mi < MI; ++mi) a[mi] = negd(a_s[mi * 8 * SLD + kk]);
+        for (int mi = 0; mi < MI; ++mi) a[mi] = a_s[mi * 8 * KC + fg.soff[i]];
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) b[ni] = b_s[ni * 8 * SLD + kk];
+        for (int ni = 0; ni < 8; ++ni) b[ni] = b_s[ni * 8 * KC + fg.soff[i]];
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi) {
 #pragma unroll
@@ -83,9 +108,11 @@ __device__ __forceinline__ void acc_to_afrag(double v0, double v1, int lane, dou
 }
 
 // Triangular solve, pipeline chunk T (columns 16T .. 16T+15 of L_jj are in Bs): for the two 8-column
-// blocks cb of the chunk  X_cb = T_cb * D_cb^T,  then  T_gb -= X_cb * L_jj[gb, cb]^T  for gb > cb.
+// blocks cb of the chunk  X_cb = T_cb * D_cb^T,  then  P_gb += X_cb * L_jj[gb, cb]^T  for gb > cb (P_gb = the
+// still positive product sum of block gb; it becomes T_gb = tile - P_gb when its own solve chunk arrives).
 template <int T, int MI, int half>
-__device__ __forceinline__ void trsm_consume(double (&acc)[2][8][2], const double* Bs, const double* Dsm, int lane) {
+__device__ __forceinline__ void trsm_consume(double (&acc)[2][8][2], const double* Bs, const double* Dsm, int lane,
+                                             const Frag& fg) {
     const int fr = lane >> 2, q = lane & 3;
     constexpr int cb = 2 * T + half;
     const double d0 = Dsm[(cb * 8 + fr) * DLD + q], d1 = Dsm[(cb * 8 + fr) * DLD + 4 + q];
@@ -99,14 +126,12 @@ __device__ __forceinline__ void trsm_consume(double (&acc)[2][8][2], const doubl
         dmma884(x0, x1, a1, d1);
         acc[mi][cb][0] = x0;
         acc[mi][cb][1] = x1;
-        acc_to_afrag(x0, x1, lane, a0, a1);
-        ax[mi][0] = negd(a0);
-        ax[mi][1] = negd(a1);
+        acc_to_afrag(x0, x1, lane, ax[mi][0], ax[mi][1]);
     }
 #pragma unroll
     for (int gb = cb + 1; gb < 8; ++gb) {
-        const double b0 = Bs[(gb * 8 + fr) * SLD + half * 8 + q];
-        const double b1 = Bs[(gb * 8 + fr) * SLD + half * 8 + 4 + q];
+        const double b0 = Bs[(gb * 8 + fr) * KC + fg.soff[2 * half]];
+        const double b1 = Bs[(gb * 8 + fr) * KC + fg.soff[2 * half + 1]];
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi) {
             dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][0], b0);
@@ -117,44 +142,48 @@ __device__ __forceinline__ void trsm_consume(double (&acc)[2][8][2], const doubl
 
 // The original tile enters through the pipeline as well: the A stage of solve chunk T holds columns
 // 16T .. 16T+15 of M[rows, j] (still Psi / identity / right-hand sides), which are added to the two
-// accumulator blocks that chunk is about to solve.  No accumulator pre-load from global memory.
+// accumulator blocks that chunk is about to solve (tile - accumulated products).  No accumulator pre-load from
+// global memory.
 template <int T, int MI, int half>
 __device__ __forceinline__ void add_tile_chunk(double (&acc)[2][8][2], const double* As, int wrow, int lane) {
     const int fr = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
-        const double2 v = *reinterpret_cast<const double2*>(As + (wrow + mi * 8 + fr) * SLD + half * 8 + 2 * q);
-        acc[mi][2 * T + half][0] += v.x;
-        acc[mi][2 * T + half][1] += v.y;
+        const double2 v =
+            *reinterpret_cast<const double2*>(As + (wrow + mi * 8 + fr) * KC + (((half * 2 + (q >> 1)) ^ (fr & 3)) << 2) +
+                                              2 * (q & 1));
+        acc[mi][2 * T + half][0] = v.x - acc[mi][2 * T + half][0];
+        acc[mi][2 * T + half][1] = v.y - acc[mi][2 * T + half][1];
     }
 }
 
 // one half (8 columns) of solve chunk T
 template <int T, int half>
 __device__ __forceinline__ void solve_half(double (&acc)[2][8][2], const double* As, const double* Bs,
-                                           const double* Dsm, int wrow, int lane, int mi_count) {
+                                           const double* Dsm, int wrow, int lane, int mi_count, const Frag& fg) {
     if (mi_count == 2) {
         add_tile_chunk<T, 2, half>(acc, As, wrow, lane);
-        trsm_consume<T, 2, half>(acc, Bs, Dsm, lane);
+        trsm_consume<T, 2, half>(acc, Bs, Dsm, lane, fg);
     } else if (mi_count == 1) {
         add_tile_chunk<T, 1, half>(acc, As, wrow, lane);
-        trsm_consume<T, 1, half>(acc, Bs, Dsm, lane);
+        trsm_consume<T, 1, half>(acc, Bs, Dsm, lane, fg);
     }
 }
 
 // half a pipeline chunk of a pass: product chunk (ck < nk_gemm) or solve chunk ck - nk_gemm
 template <int HALF>
 __device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const double* as, const double* bs,
-                                             const double* Dsm, int ck, int nk_gemm, int wrow, int lane, int mi_count) {
+                                             const double* Dsm, int ck, int nk_gemm, int wrow, int lane, int mi_count,
+                                             const Frag& fg) {
     if (ck < nk_gemm) {
-        if (mi_count == 2) gemm_consume<2, HALF>(acc, as, bs, wrow, lane);
-        else if (mi_count == 1) gemm_consume<1, HALF>(acc, as, bs, wrow, lane);
+        if (mi_count == 2) gemm_consume<2, HALF>(acc, as, bs, wrow, lane, fg);
+        else if (mi_count == 1) gemm_consume<1, HALF>(acc, as, bs, wrow, lane, fg);
     } else {
         switch (ck - nk_gemm) {
-            case 0: solve_half<0, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count); break;
-            case 1: solve_half<1, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count); break;
-            case 2: solve_half<2, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count); break;
-            default: solve_half<3, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count); break;
+            case 0: solve_half<0, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count, fg); break;
+            case 1: solve_half<1, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count, fg); break;
+            case 2: solve_half<2, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count, fg); break;
+            default: solve_half<3, HALF>(acc, as, bs, Dsm, wrow, lane, mi_count, fg); break;
         }
     }
 }
@@ -170,7 +199,8 @@ __device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const doubl
 // tl != nullptr (diagnostic build only): lanes 0 of warps 0 and 4 accumulate clock64() deltas of the loop's
 // sections {barrier wait, early produce, first half, late produce, second half, store} into tl[0..5] / tl[8..13].
 __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
-                                             int rows, long long* tl = nullptr) {
+                                             int rows, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
+                                             unsigned& seq, const Frag& fg, long long* tl = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     double* As = pipe;
@@ -181,36 +211,33 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     const int nkt = nk_gemm + PK_TILE / KC;
     const int nblk = (rows - first + BM - 1) / BM;
     const int total = nblk * nkt;
-    // Producer: every thread owns one 16-byte column slot (lc) of rows lr, lr+32, .. of a stage; its global
-    // source pointers are carried along (advance by KC per chunk, by BM rows per pass), so issuing a stage
-    // costs a handful of instructions -- the tensor pipe idles while the CTA is busy with anything else.
-    const int lr = tid >> 3, lc = (tid & 7) * 2;
-    const size_t ld32 = (size_t)32 * ld;
-    const double* gB = M + (size_t)(brow0 + lr) * ld + lc;
-    const double* gA = M + (size_t)(first + lr) * ld + lc;
-    int p_row0 = first, p_rows = min(BM, rows - first), pk = 0, ps = 0;
+    // Producer: ONE thread.  A chunk is three TMA tile copies (two 64-row boxes of A, one of B, 16 columns
+    // each) described by a 3-D tensor map over (column, row, candidate); completion is counted in bytes on the
+    // stage's mbarrier.  With per-thread 16-byte cp.async every one of the 8 warps spent about 50 instructions per
+    // chunk on the copies, and every non-DMMA instruction costs the scheduler's dispatch port a cycle the tensor
+    // pipe does not get.
+    int p_row0 = first, p_rows = min(BM, rows - first), pk = 0;
+    unsigned pseq = seq;
     auto produce = [&]() {
-        double* as = As + ps * A_STAGE + lr * SLD + lc;
-        double* bs = Bs + ps * B_STAGE + lr * SLD + lc;
-        const double* ga = gA + pk * KC;
-        const double* gb = gB + pk * KC;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (lr + 32 * i < p_rows) cp_async16(as + i * 32 * SLD, ga + i * ld32);
-        cp_async16(bs, gb);
-        cp_async16(bs + 32 * SLD, gb + ld32);
-        ps = (ps == STAGES - 1) ? 0 : ps + 1;
+        const int ps = (int)(pseq % STAGES);
+        unsigned long long* bar = bars + ps;
+        const int nbox = (p_rows > BOX_ROWS) ? 2 : 1;
+        mbar_arrive_expect_tx(bar, (unsigned)((nbox + 1) * BOX_DOUBLES * sizeof(double)));
+        double* as = As + ps * A_STAGE;
+        tma_load_3d(as, tmap, pk * KC, p_row0, cidx, bar);
+        if (nbox == 2) tma_load_3d(as + BOX_DOUBLES, tmap, pk * KC, p_row0 + BOX_ROWS, cidx, bar);
+        tma_load_3d(Bs + ps * B_STAGE, tmap, pk * KC, brow0, cidx, bar);
+        ++pseq;
         if (++pk == nkt) {
             pk = 0;
             p_row0 += BM;
-            gA += (size_t)BM * ld;
             p_rows = min(BM, rows - p_row0);
         }
     };
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < total) produce();
-        cp_async_commit();
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (s < total) produce();
     }
     double acc[2][8][2];
 #pragma unroll
@@ -224,13 +251,10 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         wrow = warp * (full ? 16 : 8);
         mic = full ? 2 : 1;
     };
-    int cb = 0, ck = 0, cs = 0;
+    int cb = 0, ck = 0, cs = (int)(seq % STAGES);
+    unsigned cpar = (seq / STAGES) & 1u;
     int row0 = first, wrow, mi_count;
     pass_shape(row0, wrow, mi_count);
-    // The two warps of a scheduler issue their share of the next stage at different points of the chunk
-    // (warps 0-3 before its first half, warps 4-7 between the halves): while one computes addresses the
-    // other keeps the tensor pipe fed.
-    const bool early = warp < 4;
     long long tprev = 0, tacc[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool tlw = tl != nullptr && lane == 0 && (warp & 3) == 0;
     if (tlw) tprev = clock64();
@@ -241,26 +265,21 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         tprev = tn_;                              \
     }
     for (int g = 0; g < total; ++g) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
+        mbar_wait(bars + cs, cpar);  // chunk g has landed
+        __syncthreads();             // every warp is done with chunk g - 1: its stage may be refilled
         PK_TL(0)
-        const bool more = g + STAGES - 1 < total;
-        if (early) {
-            if (more) produce();
-            cp_async_commit();
-        }
+        if (tid == 0 && g + STAGES - 1 < total) produce();
         PK_TL(1)
         const double* as = As + cs * A_STAGE;
         const double* bs = Bs + cs * B_STAGE;
-        cs = (cs == STAGES - 1) ? 0 : cs + 1;
-        consume_half<0>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count);
-        PK_TL(2)
-        if (!early) {
-            if (more) produce();
-            cp_async_commit();
+        if (++cs == STAGES) {
+            cs = 0;
+            cpar ^= 1u;
         }
+        consume_half<0>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count, fg);
+        PK_TL(2)
         PK_TL(3)
-        consume_half<1>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count);
+        consume_half<1>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count, fg);
         PK_TL(4)
         if (tlw) tacc[6] += 1;
         if (++ck == nkt) {
@@ -288,8 +307,9 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
 #pragma unroll
         for (int i = 0; i < 7; ++i) tl[(warp >> 2) * 8 + i] += tacc[i];
     }
-    cp_async_wait<0>();
-    __syncthreads();  // stages drained; the stores of this column are visible to the whole CTA
+    seq += (unsigned)total;
+    fence_proxy_async();  // the stores above are read by bulk copies (async proxy) in the columns to come
+    __syncthreads();      // stages drained; the stores of this column are visible to the whole CTA
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -393,22 +413,23 @@ __device__ __forceinline__ void trailing_update(double* T, int kb, int warp, int
 // ------------------------------------------------------------------------------------------------
 template <int NI, bool AUG, int HALF>
 __device__ __forceinline__ void diag_consume(double (&acc)[8][2], double (&accA)[2][2], const double* Bs,
-                                             const double* Aaug, int br, int lane) {
-    const int fr = lane >> 2, fc = lane & 3;
-    const double* a_s = Bs + (br * 8 + fr) * SLD + fc;
-    const double* b_s = Bs + fr * SLD + fc;
+                                             const double* Aaug, int br, int lane, const Frag& fg) {
+    const int fr = lane >> 2;
+    const double* a_s = Bs + (br * 8 + fr) * KC;
+    const double* b_s = Bs + fr * KC;
 #pragma unroll
-    for (int kk = HALF * (KC / 2); kk < (HALF + 1) * (KC / 2); kk += 4) {
-        const double a = negd(a_s[kk]);
+    for (int i = 2 * HALF; i < 2 * HALF + 2; ++i) {
+        const int kk = fg.soff[i];
+        const double a = a_s[kk];
         double b[NI];
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) b[ni] = b_s[ni * 8 * SLD + kk];
+        for (int ni = 0; ni < NI; ++ni) b[ni] = b_s[ni * 8 * KC + kk];
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) dmma884(acc[ni][0], acc[ni][1], a, b[ni]);
         if (AUG) {
             // the 8 augmented rows (1^T, y^T, ...) x column blocks 2*br, 2*br+1 (br == warp < 4 here)
-            const double aa = negd(Aaug[fr * SLD + fc + kk]);
-            const double b0 = b_s[(2 * br) * 8 * SLD + kk], b1 = b_s[(2 * br + 1) * 8 * SLD + kk];
+            const double aa = Aaug[fr * KC + kk];
+            const double b0 = b_s[(2 * br) * 8 * KC + kk], b1 = b_s[(2 * br + 1) * 8 * KC + kk];
             dmma884(accA[0][0], accA[0][1], aa, b0);
             dmma884(accA[1][0], accA[1][1], aa, b1);
         }
@@ -416,110 +437,97 @@ __device__ __forceinline__ void diag_consume(double (&acc)[8][2], double (&accA)
 }
 
 __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j,
-                                          int np) {
+                                          int np, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
+                                          unsigned& seq, const Frag& fg) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     const int br = (warp < 4) ? warp : 11 - warp;
     double* Bs = pipe + STAGES * A_STAGE;
     const int row0 = j * PK_TILE;
     const int nk = j * (PK_TILE / KC);
-    const int lr = tid >> 3, lc = (tid & 7) * 2;
-    const size_t ld32 = (size_t)32 * ld;
-    const double* gB = M + (size_t)(row0 + lr) * ld + lc;
-    const double* gAug = M + (size_t)(np + (lr & 7)) * ld + lc;  // threads 0..63: the 8 augmented rows
-    int ps = 0;
+    // producer: one thread, two TMA boxes per chunk (L[j, :] and the box that starts at the 8 augmented rows;
+    // its 56 rows beyond the matrix are zero-filled by the TMA unit)
+    unsigned pseq = seq;
+    int pk = 0;
     auto produce = [&]() {
-        double* bs = Bs + ps * B_STAGE + lr * SLD + lc;
-        cp_async16(bs, gB);
-        cp_async16(bs + 32 * SLD, gB + ld32);
-        if (tid < 64) cp_async16(pipe + ps * A_STAGE + lr * SLD + lc, gAug);
-        gB += KC;
-        gAug += KC;
-        ps = (ps == STAGES - 1) ? 0 : ps + 1;
+        const int ps = (int)(pseq % STAGES);
+        unsigned long long* bar = bars + ps;
+        mbar_arrive_expect_tx(bar, (unsigned)(2 * BOX_DOUBLES * sizeof(double)));
+        tma_load_3d(Bs + ps * B_STAGE, tmap, pk * KC, row0, cidx, bar);
+        tma_load_3d(pipe + ps * A_STAGE, tmap, pk * KC, np, cidx, bar);
+        ++pk;
+        ++pseq;
     };
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) produce();
-        cp_async_commit();
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (s < nk) produce();
     }
-    int cs = 0;
+    int cs = (int)(seq % STAGES);
+    unsigned cpar = (seq / STAGES) & 1u;
     double acc[8][2];
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
+    double accA[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int it = 0; it < nk; ++it) {
+        mbar_wait(bars + cs, cpar);
+        __syncthreads();
+        if (tid == 0 && it + STAGES - 1 < nk) produce();
+        const double* bs = Bs + cs * B_STAGE;
+        const double* aa = pipe + cs * A_STAGE;
+        if (++cs == STAGES) {
+            cs = 0;
+            cpar ^= 1u;
+        }
+#define PK_DIAG_HALF(HH)                                                                        \
+        switch (warp) {                                                                         \
+            case 0: diag_consume<1, true, HH>(acc, accA, bs, aa, br, lane, fg); break;              \
+            case 1: diag_consume<2, true, HH>(acc, accA, bs, aa, br, lane, fg); break;              \
+            case 2: diag_consume<3, true, HH>(acc, accA, bs, aa, br, lane, fg); break;              \
+            case 3: diag_consume<4, true, HH>(acc, accA, bs, aa, br, lane, fg); break;              \
+            case 4: diag_consume<8, false, HH>(acc, accA, bs, aa, br, lane, fg); break;             \
+            case 5: diag_consume<7, false, HH>(acc, accA, bs, aa, br, lane, fg); break;             \
+            case 6: diag_consume<6, false, HH>(acc, accA, bs, aa, br, lane, fg); break;             \
+            default: diag_consume<5, false, HH>(acc, accA, bs, aa, br, lane, fg); break;            \
+        }
+        PK_DIAG_HALF(0)
+        PK_DIAG_HALF(1)
+#undef PK_DIAG_HALF
+    }
+    seq += (unsigned)nk;
+    __syncthreads();  // the stages are drained: T (aliasing the A stages) may be written
+    // T = original tile - accumulated products
 #pragma unroll
     for (int ni = 0; ni < 8; ++ni) {
         if (ni <= br) {
             const double2 v =
                 *reinterpret_cast<const double2*>(M + (size_t)(row0 + br * 8 + fr) * ld + row0 + ni * 8 + 2 * q);
-            acc[ni][0] = v.x;
-            acc[ni][1] = v.y;
-        } else {
-            acc[ni][0] = acc[ni][1] = 0.0;
+            *reinterpret_cast<double2*>(T + (br * 8 + fr) * TS + ni * 8 + 2 * q) =
+                make_double2(v.x - acc[ni][0], v.y - acc[ni][1]);
         }
     }
-    double accA[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     if (warp < 4) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const double2 v =
                 *reinterpret_cast<const double2*>(M + (size_t)(np + fr) * ld + row0 + (2 * warp + i) * 8 + 2 * q);
-            accA[i][0] = v.x;
-            accA[i][1] = v.y;
-        }
-    }
-    for (int it = 0; it < nk; ++it) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        const bool more = it + STAGES - 1 < nk;
-        if (warp < 4) {
-            if (more) produce();
-            cp_async_commit();
-        }
-        const double* bs = Bs + cs * B_STAGE;
-        const double* aa = pipe + cs * A_STAGE;
-        cs = (cs == STAGES - 1) ? 0 : cs + 1;
-#define PK_DIAG_HALF(HH)                                                                        \
-        switch (warp) {                                                                         \
-            case 0: diag_consume<1, true, HH>(acc, accA, bs, aa, br, lane); break;              \
-            case 1: diag_consume<2, true, HH>(acc, accA, bs, aa, br, lane); break;              \
-            case 2: diag_consume<3, true, HH>(acc, accA, bs, aa, br, lane); break;              \
-            case 3: diag_consume<4, true, HH>(acc, accA, bs, aa, br, lane); break;              \
-            case 4: diag_consume<8, false, HH>(acc, accA, bs, aa, br, lane); break;             \
-            case 5: diag_consume<7, false, HH>(acc, accA, bs, aa, br, lane); break;             \
-            case 6: diag_consume<6, false, HH>(acc, accA, bs, aa, br, lane); break;             \
-            default: diag_consume<5, false, HH>(acc, accA, bs, aa, br, lane); break;            \
-        }
-        PK_DIAG_HALF(0)
-        if (warp >= 4) {
-            if (more) produce();
-            cp_async_commit();
-        }
-        PK_DIAG_HALF(1)
-#undef PK_DIAG_HALF
-    }
-    cp_async_wait<0>();
-    __syncthreads();  // the stages are drained: T (aliasing the A stages) may be written
-#pragma unroll
-    for (int ni = 0; ni < 8; ++ni) {
-        if (ni <= br)
-            *reinterpret_cast<double2*>(T + (br * 8 + fr) * TS + ni * 8 + 2 * q) = make_double2(acc[ni][0], acc[ni][1]);
-    }
-    if (warp < 4) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
             *reinterpret_cast<double2*>(T + (PK_TILE + fr) * TS + (2 * warp + i) * 8 + 2 * q) =
-                make_double2(accA[i][0], accA[i][1]);
+                make_double2(v.x - accA[i][0], v.y - accA[i][1]);
+        }
     }
 }
 
 // Diagonal tile of block column j.  Returns 0 or the tile-local failing column (CTA uniform).
 __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag0, int* ctl, double* __restrict__ M,
-                                         int ld, int j, int np, double piv_tol, long long* tm) {
+                                         int ld, int j, int np, double piv_tol, const CUtensorMap* tmap, int cidx,
+                                         unsigned long long* bars, unsigned& seq, const Frag& fg, long long* tm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = j * PK_TILE;
     if (tid < PK_TILE) diag0[tid] = M[(size_t)(row0 + tid) * ld + row0 + tid];
     double* T = pipe;
     long long t0 = 0;
     if (tm) t0 = clock64();
-    diag_gemm(T, pipe, M, ld, j, np);
+    diag_gemm(T, pipe, M, ld, j, np, tmap, cidx, bars, seq, fg);
     if (tid == 0) ctl[1] = 0;
     __syncthreads();
     if (tm) {
@@ -570,6 +578,9 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
         *reinterpret_cast<double2*>(M + (size_t)(np + rr) * ld + row0 + c2) =
             *reinterpret_cast<const double2*>(T + (PK_TILE + rr) * TS + c2);
     }
+    // T (written through the generic proxy) is about to be overwritten by bulk copies, and L_jj / the solved
+    // augmented rows are about to be READ by them: order both before the async proxy
+    fence_proxy_async();
     __syncthreads();  // L_jj is in global memory and D in shared memory for every thread of the CTA
     if (tm) tm[2] += clock64() - t0;
     return 0;
@@ -579,33 +590,46 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
 // panel column, candidates} into dbg[8 * blockIdx.x ..] (diagnostic build of the same kernel).
 template <bool TIMING>
 __global__ void __launch_bounds__(THREADS, 2)
-chol_cta_kernel(int C, int nt, int rows, int ld, size_t elems, double piv_tol, double* __restrict__ ws,
-                int32_t* __restrict__ info, unsigned int* __restrict__ queue, long long* __restrict__ dbg, int alias) {
+chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int rows, int ld, size_t elems, double piv_tol,
+                double* __restrict__ ws, int32_t* __restrict__ info, unsigned int* __restrict__ queue,
+                long long* __restrict__ dbg, int alias) {
     long long tmv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long* tm = TIMING ? tmv : nullptr;
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(16) double smem_raw[];
+    // stages on a 1 KB boundary (the launcher allocates the slack): the TMA swizzle is a function of the address
+    double* smem = smem_raw + ((SMEM_ALIGN - ((unsigned)__cvta_generic_to_shared(smem_raw) & (SMEM_ALIGN - 1))) &
+                               (SMEM_ALIGN - 1)) / sizeof(double);
     double* pipe = smem;
     double* Dsm = pipe + PIPE_DOUBLES;
     double* diag0 = Dsm + D_DOUBLES;
     int* ctl = reinterpret_cast<int*>(diag0 + PK_TILE);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(diag0 + PK_TILE + 2);  // one mbarrier per stage
     const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+        mbar_fence_init();
+    }
+    const Frag fg = make_frag(tid & 31);
+    unsigned seq = 0;  // pipeline chunks issued == consumed so far (stage = seq % STAGES, parity = seq / STAGES & 1)
     for (;;) {
+        fence_proxy_async();  // a failed factorisation leaves generic-proxy writes in the stage buffers
         __syncthreads();
         if (tid == 0) ctl[0] = (int)atomicAdd(queue, 1u);
         __syncthreads();
         const int cand = ctl[0];
         if (cand >= C) break;
         if (info[cand] != 0) continue;
-        double* M = ws + (size_t)(alias ? (cand & 7) : cand) * elems;  // alias: timing experiment only (results are garbage)
+        const int cidx = alias ? (cand & 7) : cand;  // alias: timing experiment only (results are garbage)
+        double* M = ws + (size_t)cidx * elems;
         for (int j = 0; j < nt; ++j) {
-            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, tm);
+            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cidx, bars, seq, fg, tm);
             if (bad && !alias) {
                 if (tid == 0) info[cand] = j * PK_TILE + bad;  // dpotrf convention: order of the failing minor
                 break;
             }
             long long t0 = 0;
             if (TIMING) t0 = clock64();
-            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
+            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, seq, fg, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
             if (TIMING) tmv[3] += clock64() - t0;
         }
         if (TIMING) tmv[4] += 1;
@@ -617,10 +641,41 @@ chol_cta_kernel(int C, int nt, int rows, int ld, size_t elems, double piv_tol, d
 
 }  // namespace cta
 
+// 3-D tensor map over the candidate workspace: (column, row, candidate), boxes of 16 columns x 64 rows,
+// 128-byte swizzle span with 32-byte atoms.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query (no
+// link against libcuda).
+static cudaError_t make_ws_tensor_map(CUtensorMap* tmap, double* ws, const TiledShape& s, int C) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)s.ld, (cuuint64_t)s.rows, (cuuint64_t)C};
+    const cuuint64_t gstride[2] = {(cuuint64_t)s.ld * sizeof(double), (cuuint64_t)s.elems() * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)cta::KC, (cuuint32_t)cta::BOX_ROWS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ws, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     if (s.with_inverse || s.rows != s.np + PK_AUG_ROWS) return cudaErrorInvalidValue;  // population shape only
     const int nt = s.np / PK_TILE;
-    const size_t smem = sizeof(double) * (size_t)cta::SMEM_DOUBLES;
+    const size_t smem = sizeof(double) * (size_t)cta::SMEM_DOUBLES + cta::SMEM_ALIGN;
+    CUtensorMap tmap;
+    {
+        cudaError_t e = make_ws_tensor_map(&tmap, ws, s, C);
+        if (e != cudaSuccess) return e;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e =
@@ -640,7 +695,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         long long* dbg = nullptr;
         cudaMalloc((void**)&dbg, sizeof(long long) * (8 * grid + 16));
         cudaMemset(dbg, 0, sizeof(long long) * (8 * grid + 16));
-        cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
+        cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
                                                                             ws, info, queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0);
         cudaStreamSynchronize(h->stream);
         std::vector<long long> host(8 * (size_t)grid + 16);
@@ -663,7 +718,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
                 grid, sum[4], sum[0] / sum[4], sum[1] / sum[4], sum[2] / sum[4], sum[3] / sum[4], sum[5] / sum[4],
                 sum[6] / sum[4], sum[7] / sum[4]);
     } else {
-        cta::chol_cta_kernel<false><<<grid, cta::THREADS, smem, h->stream>>>(C, nt, s.rows, s.ld, s.elems(),
+        cta::chol_cta_kernel<false><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(),
                                                                              h->pivot_tol, ws, info, queue, nullptr, 0);
     }
     h->launches++;
