@@ -47,7 +47,7 @@ constexpr int PIPE_DOUBLES = STAGES * (A_STAGE + B_STAGE);
 constexpr int TS = PK_TILE + 4;    // 68: stride of the diagonal tile while it is factorised in smem
 constexpr int DLD = 12;            // row stride of the inverted 8x8 diagonal blocks
 constexpr int D_DOUBLES = 8 * 8 * DLD;
-constexpr int SMEM_DOUBLES = PIPE_DOUBLES + D_DOUBLES + PK_TILE + 2 + STAGES;  // + diag0[64] + control words + mbarriers
+constexpr int SMEM_DOUBLES = PIPE_DOUBLES + D_DOUBLES + PK_TILE + 2 + 2 * STAGES;  // + diag0[64] + control words + mbarriers (full | empty)
 constexpr int SMEM_ALIGN = 1024;   // the swizzle pattern is a function of the shared address: stages on 1 KB boundaries
 static_assert((PK_TILE + 32) * TS <= STAGES * A_STAGE, "the diagonal tile reuses the pipeline buffers");
 
@@ -221,6 +221,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     auto produce = [&]() {
         const int ps = (int)(pseq % STAGES);
         unsigned long long* bar = bars + ps;
+        mbar_wait(bars + STAGES + ps, ((pseq / STAGES) & 1u) ^ 1u);  // every warp has released the stage's previous chunk
         const int nbox = (p_rows > BOX_ROWS) ? 2 : 1;
         mbar_arrive_expect_tx(bar, (unsigned)((nbox + 1) * BOX_DOUBLES * sizeof(double)));
         double* as = As + ps * A_STAGE;
@@ -264,14 +265,17 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         tacc[i] += tn_ - tprev;                   \
         tprev = tn_;                              \
     }
+    // No CTA barrier in this loop: a warp waits for its data (full[stage]) and releases the stage when its
+    // fragment loads are done (empty[stage], one arrival per warp); the producer thread refills a stage -- after
+    // its own warp's work on the current chunk -- once all eight warps have released it.  Warps on different
+    // schedulers may be up to STAGES - 2 chunks apart.
     for (int g = 0; g < total; ++g) {
         mbar_wait(bars + cs, cpar);  // chunk g has landed
-        __syncthreads();             // every warp is done with chunk g - 1: its stage may be refilled
         PK_TL(0)
-        if (tid == 0 && g + STAGES - 1 < total) produce();
         PK_TL(1)
         const double* as = As + cs * A_STAGE;
         const double* bs = Bs + cs * B_STAGE;
+        unsigned long long* ebar = bars + STAGES + cs;
         if (++cs == STAGES) {
             cs = 0;
             cpar ^= 1u;
@@ -280,6 +284,9 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         PK_TL(2)
         PK_TL(3)
         consume_half<1>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count, fg);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ebar);
+        if (tid == 0 && g + STAGES - 1 < total) produce();
         PK_TL(4)
         if (tlw) tacc[6] += 1;
         if (++ck == nkt) {
@@ -452,6 +459,7 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
     auto produce = [&]() {
         const int ps = (int)(pseq % STAGES);
         unsigned long long* bar = bars + ps;
+        mbar_wait(bars + STAGES + ps, ((pseq / STAGES) & 1u) ^ 1u);
         mbar_arrive_expect_tx(bar, (unsigned)(2 * BOX_DOUBLES * sizeof(double)));
         tma_load_3d(Bs + ps * B_STAGE, tmap, pk * KC, row0, cidx, bar);
         tma_load_3d(pipe + ps * A_STAGE, tmap, pk * KC, np, cidx, bar);
@@ -471,10 +479,9 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
     double accA[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     for (int it = 0; it < nk; ++it) {
         mbar_wait(bars + cs, cpar);
-        __syncthreads();
-        if (tid == 0 && it + STAGES - 1 < nk) produce();
         const double* bs = Bs + cs * B_STAGE;
         const double* aa = pipe + cs * A_STAGE;
+        unsigned long long* ebar = bars + STAGES + cs;
         if (++cs == STAGES) {
             cs = 0;
             cpar ^= 1u;
@@ -492,8 +499,11 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
         }
         PK_DIAG_HALF(0)
         PK_DIAG_HALF(1)
-#undef PK_DIAG_HALF
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ebar);
+        if (tid == 0 && it + STAGES - 1 < nk) produce();
     }
+#undef PK_DIAG_HALF
     seq += (unsigned)nk;
     __syncthreads();  // the stages are drained: T (aliasing the A stages) may be written
     // T = original tile - accumulated products
@@ -606,7 +616,10 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(diag0 + PK_TILE + 2);  // one mbarrier per stage
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + s, 1);                       // full: the producer's arrive.expect_tx + the bytes
+            mbar_init(bars + STAGES + s, THREADS / 32);   // empty: one arrival per warp
+        }
         mbar_fence_init();
     }
     const Frag fg = make_frag(tid & 31);
