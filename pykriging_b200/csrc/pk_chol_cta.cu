@@ -47,7 +47,7 @@ constexpr int PIPE_DOUBLES = STAGES * (A_STAGE + B_STAGE);
 constexpr int TS = PK_TILE + 4;    // 68: stride of the diagonal tile while it is factorised in smem
 constexpr int DLD = 12;            // row stride of the inverted 8x8 diagonal blocks
 constexpr int D_DOUBLES = 8 * 8 * DLD;
-constexpr int SMEM_DOUBLES = PIPE_DOUBLES + D_DOUBLES + PK_TILE + 2 + 2 * STAGES;  // + diag0[64] + control words + mbarriers (full | empty)
+constexpr int SMEM_DOUBLES = PIPE_DOUBLES + D_DOUBLES + PK_TILE + 2 + STAGES + STAGES / 2;  // + diag0[64] + control words + mbarriers + release counters
 constexpr int SMEM_ALIGN = 1024;   // the swizzle pattern is a function of the shared address: stages on 1 KB boundaries
 static_assert((PK_TILE + 32) * TS <= STAGES * A_STAGE, "the diagonal tile reuses the pipeline buffers");
 
@@ -200,7 +200,7 @@ __device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const doubl
 // sections {barrier wait, early produce, first half, late produce, second half, store} into tl[0..5] / tl[8..13].
 __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
                                              int rows, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
-                                             unsigned& seq, const Frag& fg, long long* tl = nullptr) {
+                                             int* rel, unsigned& seq, const Frag& fg, long long* tl = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     double* As = pipe;
@@ -211,35 +211,26 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     const int nkt = nk_gemm + PK_TILE / KC;
     const int nblk = (rows - first + BM - 1) / BM;
     const int total = nblk * nkt;
-    // Producer: ONE thread.  A chunk is three TMA tile copies (two 64-row boxes of A, one of B, 16 columns
-    // each) described by a 3-D tensor map over (column, row, candidate); completion is counted in bytes on the
-    // stage's mbarrier.  With per-thread 16-byte cp.async every one of the 8 warps spent about 50 instructions per
-    // chunk on the copies, and every non-DMMA instruction costs the scheduler's dispatch port a cycle the tensor
-    // pipe does not get.
-    int p_row0 = first, p_rows = min(BM, rows - first), pk = 0;
-    unsigned pseq = seq;
-    auto produce = [&]() {
-        const int ps = (int)(pseq % STAGES);
+    // Producer: ONE thread per chunk.  A chunk is three TMA tile copies (two 64-row boxes of A, one of B, 16
+    // columns each) described by a 3-D tensor map over (column, row, candidate); completion is counted in bytes on
+    // the stage's mbarrier.  Chunk c of the column goes to stage (seq + c) % STAGES; the first STAGES chunks are
+    // issued here, chunk c + STAGES by whichever warp is the LAST to release chunk c (a counter per stage):
+    // nobody ever waits for a stage to become free.
+    auto issue = [&](int c, int k_idx, int r0) {
+        const int ps = (int)((seq + (unsigned)c) % STAGES);
         unsigned long long* bar = bars + ps;
-        mbar_wait(bars + STAGES + ps, ((pseq / STAGES) & 1u) ^ 1u);  // every warp has released the stage's previous chunk
-        const int nbox = (p_rows > BOX_ROWS) ? 2 : 1;
+        const int nbox = (rows - r0 > BOX_ROWS) ? 2 : 1;
         mbar_arrive_expect_tx(bar, (unsigned)((nbox + 1) * BOX_DOUBLES * sizeof(double)));
         double* as = As + ps * A_STAGE;
-        tma_load_3d(as, tmap, pk * KC, p_row0, cidx, bar);
-        if (nbox == 2) tma_load_3d(as + BOX_DOUBLES, tmap, pk * KC, p_row0 + BOX_ROWS, cidx, bar);
-        tma_load_3d(Bs + ps * B_STAGE, tmap, pk * KC, brow0, cidx, bar);
-        ++pseq;
-        if (++pk == nkt) {
-            pk = 0;
-            p_row0 += BM;
-            p_rows = min(BM, rows - p_row0);
-        }
+        tma_load_3d(as, tmap, k_idx * KC, r0, cidx, bar);
+        if (nbox == 2) tma_load_3d(as + BOX_DOUBLES, tmap, k_idx * KC, r0 + BOX_ROWS, cidx, bar);
+        tma_load_3d(Bs + ps * B_STAGE, tmap, k_idx * KC, brow0, cidx, bar);
     };
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s)
-            if (s < total) produce();
+        for (int c = 0; c < STAGES && c < total; ++c) issue(c, c % nkt, first + (c / nkt) * BM);
     }
+    // position of the chunk STAGES ahead of the one being consumed (tracked by every warp: any of them may issue it)
+    int pk = STAGES % nkt, p_row0 = first + (STAGES / nkt) * BM;
     double acc[2][8][2];
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
@@ -266,16 +257,15 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         tprev = tn_;                              \
     }
     // No CTA barrier in this loop: a warp waits for its data (full[stage]) and releases the stage when its
-    // fragment loads are done (empty[stage], one arrival per warp); the producer thread refills a stage -- after
-    // its own warp's work on the current chunk -- once all eight warps have released it.  Warps on different
-    // schedulers may be up to STAGES - 2 chunks apart.
+    // fragment loads are done (one count per warp on the stage's release counter); the last warp to release a
+    // stage refills it.  Warps on different schedulers may be up to STAGES - 1 chunks apart.
     for (int g = 0; g < total; ++g) {
         mbar_wait(bars + cs, cpar);  // chunk g has landed
         PK_TL(0)
         PK_TL(1)
         const double* as = As + cs * A_STAGE;
         const double* bs = Bs + cs * B_STAGE;
-        unsigned long long* ebar = bars + STAGES + cs;
+        int* rcnt = rel + cs;
         if (++cs == STAGES) {
             cs = 0;
             cpar ^= 1u;
@@ -285,8 +275,14 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         PK_TL(3)
         consume_half<1>(acc, as, bs, Dsm, ck, nk_gemm, wrow, lane, mi_count, fg);
         __syncwarp();
-        if (lane == 0) mbar_arrive(ebar);
-        if (tid == 0 && g + STAGES - 1 < total) produce();
+        if (lane == 0 && atomicAdd(rcnt, 1) == THREADS / 32 - 1) {  // last warp to release this stage: refill it
+            *rcnt = 0;
+            if (g + STAGES < total) issue(g + STAGES, pk, p_row0);
+        }
+        if (++pk == nkt) {
+            pk = 0;
+            p_row0 += BM;
+        }
         PK_TL(4)
         if (tlw) tacc[6] += 1;
         if (++ck == nkt) {
@@ -445,31 +441,24 @@ __device__ __forceinline__ void diag_consume(double (&acc)[8][2], double (&accA)
 
 __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j,
                                           int np, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
-                                          unsigned& seq, const Frag& fg) {
+                                          int* rel, unsigned& seq, const Frag& fg) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     const int br = (warp < 4) ? warp : 11 - warp;
     double* Bs = pipe + STAGES * A_STAGE;
     const int row0 = j * PK_TILE;
     const int nk = j * (PK_TILE / KC);
-    // producer: one thread, two TMA boxes per chunk (L[j, :] and the box that starts at the 8 augmented rows;
-    // its 56 rows beyond the matrix are zero-filled by the TMA unit)
-    unsigned pseq = seq;
-    int pk = 0;
-    auto produce = [&]() {
-        const int ps = (int)(pseq % STAGES);
+    // two TMA boxes per chunk (L[j, :] and the box that starts at the 8 augmented rows; its 56 rows beyond the
+    // matrix are zero-filled by the TMA unit); issued like the panel's chunks (see panel_column)
+    auto issue = [&](int c) {
+        const int ps = (int)((seq + (unsigned)c) % STAGES);
         unsigned long long* bar = bars + ps;
-        mbar_wait(bars + STAGES + ps, ((pseq / STAGES) & 1u) ^ 1u);
         mbar_arrive_expect_tx(bar, (unsigned)(2 * BOX_DOUBLES * sizeof(double)));
-        tma_load_3d(Bs + ps * B_STAGE, tmap, pk * KC, row0, cidx, bar);
-        tma_load_3d(pipe + ps * A_STAGE, tmap, pk * KC, np, cidx, bar);
-        ++pk;
-        ++pseq;
+        tma_load_3d(Bs + ps * B_STAGE, tmap, c * KC, row0, cidx, bar);
+        tma_load_3d(pipe + ps * A_STAGE, tmap, c * KC, np, cidx, bar);
     };
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s)
-            if (s < nk) produce();
+        for (int c = 0; c < STAGES && c < nk; ++c) issue(c);
     }
     int cs = (int)(seq % STAGES);
     unsigned cpar = (seq / STAGES) & 1u;
@@ -481,7 +470,7 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
         mbar_wait(bars + cs, cpar);
         const double* bs = Bs + cs * B_STAGE;
         const double* aa = pipe + cs * A_STAGE;
-        unsigned long long* ebar = bars + STAGES + cs;
+        int* rcnt = rel + cs;
         if (++cs == STAGES) {
             cs = 0;
             cpar ^= 1u;
@@ -500,8 +489,10 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
         PK_DIAG_HALF(0)
         PK_DIAG_HALF(1)
         __syncwarp();
-        if (lane == 0) mbar_arrive(ebar);
-        if (tid == 0 && it + STAGES - 1 < nk) produce();
+        if (lane == 0 && atomicAdd(rcnt, 1) == THREADS / 32 - 1) {
+            *rcnt = 0;
+            if (it + STAGES < nk) issue(it + STAGES);
+        }
     }
 #undef PK_DIAG_HALF
     seq += (unsigned)nk;
@@ -530,14 +521,15 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
 // Diagonal tile of block column j.  Returns 0 or the tile-local failing column (CTA uniform).
 __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag0, int* ctl, double* __restrict__ M,
                                          int ld, int j, int np, double piv_tol, const CUtensorMap* tmap, int cidx,
-                                         unsigned long long* bars, unsigned& seq, const Frag& fg, long long* tm) {
+                                         unsigned long long* bars, int* rel, unsigned& seq, const Frag& fg,
+                                         long long* tm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = j * PK_TILE;
     if (tid < PK_TILE) diag0[tid] = M[(size_t)(row0 + tid) * ld + row0 + tid];
     double* T = pipe;
     long long t0 = 0;
     if (tm) t0 = clock64();
-    diag_gemm(T, pipe, M, ld, j, np, tmap, cidx, bars, seq, fg);
+    diag_gemm(T, pipe, M, ld, j, np, tmap, cidx, bars, rel, seq, fg);
     if (tid == 0) ctl[1] = 0;
     __syncthreads();
     if (tm) {
@@ -614,11 +606,12 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
     double* diag0 = Dsm + D_DOUBLES;
     int* ctl = reinterpret_cast<int*>(diag0 + PK_TILE);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(diag0 + PK_TILE + 2);  // one mbarrier per stage
+    int* rel = reinterpret_cast<int*>(bars + STAGES);                                      // one release counter per stage
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bars + s, 1);                       // full: the producer's arrive.expect_tx + the bytes
-            mbar_init(bars + STAGES + s, THREADS / 32);   // empty: one arrival per warp
+            mbar_init(bars + s, 1);  // the issuing thread's arrive.expect_tx + the bytes of the chunk
+            rel[s] = 0;
         }
         mbar_fence_init();
     }
@@ -635,14 +628,14 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
         const int cidx = alias ? (cand & 7) : cand;  // alias: timing experiment only (results are garbage)
         double* M = ws + (size_t)cidx * elems;
         for (int j = 0; j < nt; ++j) {
-            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cidx, bars, seq, fg, tm);
+            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cidx, bars, rel, seq, fg, tm);
             if (bad && !alias) {
                 if (tid == 0) info[cand] = j * PK_TILE + bad;  // dpotrf convention: order of the failing minor
                 break;
             }
             long long t0 = 0;
             if (TIMING) t0 = clock64();
-            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, seq, fg, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
+            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, rel, seq, fg, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
             if (TIMING) tmv[3] += clock64() - t0;
         }
         if (TIMING) tmv[4] += 1;
