@@ -387,23 +387,29 @@ __device__ __forceinline__ void panel_scale_blocks(double* T, const double* Dsm,
     *reinterpret_cast<double2*>(row + 2 * q) = make_double2(x0, x1);
 }
 
-// trailing update after panel kb: T[bi, bl] -= L[bi, kb] L[bl, kb]^T for kb < bl <= bi, 8x8 blocks
-// spread over the warps, two DMMAs each.
-__device__ __forceinline__ void trailing_update(double* T, int kb, int warp, int lane) {
+// one 8x8 block of the trailing update after panel kb: T[bi, bl] -= L[bi, kb] L[bl, kb]^T (two DMMAs)
+__device__ __forceinline__ void trailing_block(double* T, int kb, int bi, int bl, int lane) {
     const int fr = lane >> 2, q = lane & 3;
+    double2* cp = reinterpret_cast<double2*>(T + (bi * 8 + fr) * TS + bl * 8 + 2 * q);
+    double2 c = *cp;
+    const double a0 = negd(T[(bi * 8 + fr) * TS + kb * 8 + q]);
+    const double a1 = negd(T[(bi * 8 + fr) * TS + kb * 8 + 4 + q]);
+    const double b0 = T[(bl * 8 + fr) * TS + kb * 8 + q];
+    const double b1 = T[(bl * 8 + fr) * TS + kb * 8 + 4 + q];
+    dmma884(c.x, c.y, a0, b0);
+    dmma884(c.x, c.y, a1, b1);
+    *cp = c;
+}
+
+// trailing update after panel kb, WITHOUT the next diagonal block (kb+1, kb+1): that one belongs to warp 0, which
+// updates and factorises it while warps 1..7 work through the rest (block row 8 = the augmented rows)
+__device__ __forceinline__ void trailing_update_rest(double* T, int kb, int warp, int lane) {
     int cnt = 0;
-    for (int bi = kb + 1; bi < 9; ++bi) {  // block row 8 = the augmented rows
-        for (int bl = kb + 1; bl <= min(bi, 7); ++bl, ++cnt) {
-            if ((cnt & 7) != warp) continue;
-            double2* cp = reinterpret_cast<double2*>(T + (bi * 8 + fr) * TS + bl * 8 + 2 * q);
-            double2 c = *cp;
-            const double a0 = negd(T[(bi * 8 + fr) * TS + kb * 8 + q]);
-            const double a1 = negd(T[(bi * 8 + fr) * TS + kb * 8 + 4 + q]);
-            const double b0 = T[(bl * 8 + fr) * TS + kb * 8 + q];
-            const double b1 = T[(bl * 8 + fr) * TS + kb * 8 + 4 + q];
-            dmma884(c.x, c.y, a0, b0);
-            dmma884(c.x, c.y, a1, b1);
-            *cp = c;
+    for (int bi = kb + 1; bi < 9; ++bi) {
+        for (int bl = kb + 1; bl <= min(bi, 7); ++bl) {
+            if (bi == kb + 1) continue;  // (kb+1, kb+1)
+            if (cnt++ % 7 + 1 != warp) continue;
+            trailing_block(T, kb, bi, bl, lane);
         }
     }
 }
@@ -537,20 +543,18 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
         tm[0] += t1 - t0;
         t0 = t1;
     }
+    // Panel kb: (a) its 8x8 diagonal block is factorised by warp 0 -- a chain of 8 dependent pivots, latency
+    // bound; (b) all warps scale the blocks below; (c) trailing update.  (a) of panel kb+1 runs DURING (c) of
+    // panel kb: warp 0 updates block (kb+1, kb+1) first and walks its chain while warps 1..7 do the rest.
+    if (warp == 0) {
+        const int bad = diag_block_factor(T, Dsm, diag0, 0, piv_tol, lane);
+        if (bad && lane == 0) ctl[1] = bad;
+    }
+    __syncthreads();
+    if (ctl[1]) return ctl[1];
     for (int kb = 0; kb < 8; ++kb) {
         long long ta = 0;
         if (tm) ta = clock64();
-        if (warp == 0) {
-            const int bad = diag_block_factor(T, Dsm, diag0, kb, piv_tol, lane);
-            if (bad && lane == 0) ctl[1] = bad;
-        }
-        __syncthreads();
-        if (tm) {
-            const long long tb = clock64();
-            tm[5] += tb - ta;
-            ta = tb;
-        }
-        if (ctl[1]) return ctl[1];
         panel_scale_blocks(T, Dsm, kb, warp, lane);
         __syncthreads();
         if (tm) {
@@ -559,10 +563,18 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
             ta = tb;
         }
         if (kb < 7) {
-            trailing_update(T, kb, warp, lane);
+            if (warp == 0) {
+                trailing_block(T, kb, kb + 1, kb + 1, lane);
+                __syncwarp();
+                const int bad = diag_block_factor(T, Dsm, diag0, kb + 1, piv_tol, lane);
+                if (bad && lane == 0) ctl[1] = bad;
+            } else {
+                trailing_update_rest(T, kb, warp, lane);
+            }
             __syncthreads();
+            if (ctl[1]) return ctl[1];
         }
-        if (tm) tm[7] += clock64() - ta;
+        if (tm) tm[5] += clock64() - ta;
     }
     if (tm) {
         const long long t1 = clock64();
