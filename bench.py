@@ -361,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": 4 * C * 8 + 4 * C, "api": "pk_nll_batch (C ABI) with pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "cta::chol_cta_kernel (persistent blocked Cholesky, one CTA per candidate, "
-                                   "DMMA 8x8x4)" if args.chol_variant != 1 else "chol_first_kernel + chol_step_kernel",
+                                   "DMMA 8x8x4, TMA-fed stages)" if args.chol_variant != 1 else "chol_first_kernel + chol_step_kernel",
                          "bound": "tensor", "achieved": chol_tf, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
                          "frac": (chol_tf / peak["dmma_tflops"]) if chol_tf else None,
                          "traffic": (traffic or {}).get("chol_cta_kernel_dram_bytes_per_launch"),
