@@ -157,7 +157,7 @@ int pk_destroy(pk_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
-                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp};
+                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -538,7 +538,6 @@ int pk_predict_batch(pk_handle* h, int64_t m, const double* Xq, const double* th
     PK_CUDA(h, cudaSetDevice(h->device));
     const int k = h->k;
     const pk::TiledShape sh = pk::tiled_shape(h->n, true);
-    if (sh.np > 2944) PK_FAIL(h, "pk_predict_batch: n=%d exceeds the fused predictor's limit (2944)", h->n);
     PK_CUDA(h, cudaMemcpyAsync(h->d_hp, theta, sizeof(double) * k, cudaMemcpyDefault, h->stream));
     PK_CUDA(h, cudaMemcpyAsync(h->d_hp + PK_MAX_K, p, sizeof(double) * k, cudaMemcpyDefault, h->stream));
     if (!h->w_valid || !(h->w_mu == mu)) {

@@ -76,6 +76,8 @@ struct pk_handle {
     double* d_qout = nullptr; // 3 x chunk
     int64_t cap_q = 0;
     double* d_hp = nullptr;   // 2 x PK_MAX_K (theta | p) for predict
+    double* d_pscratch = nullptr;  // psi slabs of predict_big_kernel (np > 2944): grid x 32 x (np + 4)
+    size_t cap_pscratch = 0;
 };
 
 namespace pk {

@@ -329,6 +329,137 @@ predict_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X, co
 }
 
 
+// ---- fused predictor, any n (np > 3072: a psi tile no longer fits in shared memory) --------------------
+// Same arithmetic as predict_kernel<32>, but the psi tile of a CTA (32 queries x np) lives in a per-CTA slab of a
+// global scratch buffer (L2 resident: 32 x 4100 doubles = 1 MB per CTA) and its 32 x 16 chunks ride through the
+// cp.async stages together with the 64 x 16 chunks of L^-1.  Persistent: a CTA walks query tiles with stride
+// gridDim.x, so the scratch is grid-sized, not m-sized.  Config C4 (regression kriging, n = 4096).
+constexpr int PB_QT = 32;
+__global__ void __launch_bounds__(PRED_THREADS)
+predict_big_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X, const double* __restrict__ Xq,
+                   const double* __restrict__ hp, const double* __restrict__ linv, const double* __restrict__ w,
+                   double mu, double sigma2, double y_min, double ei_weight, double var_extra, int need_s,
+                   double* __restrict__ psi_scratch, double* __restrict__ yhat_out, double* __restrict__ s_out,
+                   double* __restrict__ ei_out) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int QT = PB_QT;
+    const int psl = np + 4;
+    double* As = smem;                                   // PSTAGES x QT x PSLD
+    double* Bs = As + PSTAGES * QT * PSLD;               // PSTAGES x 64 x PSLD
+    double* xq = Bs + PSTAGES * PK_TILE * PSLD;          // QT x k
+    double* th = xq + QT * k;                            // k
+    double* pp = th + k;                                 // k
+    double* ysum = pp + k;                               // QT
+    double* qsum = ysum + QT;                            // QT x 8
+    double* psi = psi_scratch + (size_t)blockIdx.x * QT * psl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < k) {
+        th[tid] = hp[tid];
+        pp[tid] = hp[PK_MAX_K + tid];
+    }
+    const int64_t ntiles = (m + QT - 1) / QT;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t q0 = tile * QT;
+        const int qv = (int)min((int64_t)QT, m - q0);
+        __syncthreads();  // previous tile: outputs written, xq / ysum / qsum / stages free
+        for (int i = tid; i < QT * k; i += PRED_THREADS) {
+            const int q = i / k;
+            xq[i] = (q < qv) ? Xq[q0 * k + i] : 0.0;
+        }
+        __syncthreads();
+        for (int q = warp; q < QT; q += PRED_THREADS / 32) {
+            double ys = 0.0;
+            for (int r = lane; r < np; r += 32) {
+                double v = 0.0;
+                if (r < n && q < qv) {
+                    v = exp(-corr_exponent(X + (size_t)r * k, xq + q * k, th, pp, k));
+                    ys += v * w[r];
+                }
+                psi[(size_t)q * psl + r] = v;
+            }
+            ys = warp_sum(ys);
+            if (lane == 0) ysum[q] = ys;
+        }
+        __syncthreads();  // the slab (global memory, written by this CTA) is complete for every thread of the CTA
+
+        if (need_s) {
+            // warps: 2 along the queries (16 each) x 4 along the 64 columns of a tile (16 each)
+            const int wm = warp & 1, wn = warp >> 1;
+            const int fr = lane >> 2, fc = lane & 3;
+            const int nct = np / PK_TILE;
+            double qpart[2] = {0.0, 0.0};
+            for (int ct = 0; ct < nct; ++ct) {
+                double acc[2][2][2];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+                const double* Bg = linv + (size_t)(ct * PK_TILE) * np;
+                const int nk = (ct + 1) * PK_TILE / PKC;  // Linv[c][r] == 0 for r > c
+                auto load_stage = [&](int s, int k0) {
+                    for (int i = tid; i < (PK_TILE + QT) * 8; i += PRED_THREADS) {
+                        const int r = i >> 3, ch = i & 7;
+                        if (r < PK_TILE)
+                            cp_async16(Bs + s * PK_TILE * PSLD + r * PSLD + ch * 2, Bg + (size_t)r * np + k0 + ch * 2);
+                        else
+                            cp_async16(As + s * QT * PSLD + (r - PK_TILE) * PSLD + ch * 2,
+                                       psi + (size_t)(r - PK_TILE) * psl + k0 + ch * 2);
+                    }
+                };
+#pragma unroll
+                for (int s = 0; s < PSTAGES - 1; ++s) {
+                    if (s < nk) load_stage(s, s * PKC);
+                    cp_async_commit();
+                }
+                for (int it = 0; it < nk; ++it) {
+                    cp_async_wait<PSTAGES - 2>();
+                    __syncthreads();
+                    const int nxt = it + PSTAGES - 1;
+                    if (nxt < nk) load_stage(nxt % PSTAGES, nxt * PKC);
+                    cp_async_commit();
+                    const double* a_s = As + (it % PSTAGES) * QT * PSLD + (wm * 16 + fr) * PSLD + fc;
+                    const double* b_s = Bs + (it % PSTAGES) * PK_TILE * PSLD + (wn * 16 + fr) * PSLD + fc;
+#pragma unroll
+                    for (int kk = 0; kk < PKC; kk += 4) {
+                        const double a0 = a_s[kk], a1 = a_s[8 * PSLD + kk];
+                        const double b0 = b_s[kk], b1 = b_s[8 * PSLD + kk];
+                        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+                        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+                        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+                        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+                    }
+                }
+                cp_async_wait<0>();
+                __syncthreads();
+#pragma unroll
+                for (int x = 0; x < 2; ++x)
+#pragma unroll
+                    for (int z = 0; z < 2; ++z)
+                        qpart[x] += acc[x][z][0] * acc[x][z][0] + acc[x][z][1] * acc[x][z][1];
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                double v = qpart[x];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (fc == 0) qsum[(wm * 16 + x * 8 + fr) * 8 + wn] = v;
+            }
+            __syncthreads();
+        }
+        if (tid < qv) {
+            const double yhat = mu + ysum[tid];
+            if (yhat_out) yhat_out[q0 + tid] = yhat;
+            if (need_s) {
+                const double qs = (qsum[tid * 8] + qsum[tid * 8 + 1]) + (qsum[tid * 8 + 2] + qsum[tid * 8 + 3]);
+                const double ssqr = sigma2 * (1.0 + var_extra - qs);
+                const double S = sqrt(fabs(ssqr));
+                if (s_out) s_out[q0 + tid] = S;
+                if (ei_out) ei_out[q0 + tid] = expected_improvement(yhat, S, y_min, ei_weight);
+            }
+        }
+    }
+}
+
 // ---- fused predictor, register-resident variant (n <= 512) ------------------------------------------
 // v = L^-1 psi for a tile of 32 query points is held ENTIRELY in accumulator registers: the 16 warps of a
 // CTA split the columns of v in 8-column blocks, block b -> warp b % 16 (so every warp owns a slice of every
@@ -381,52 +512,67 @@ predict_reg_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X
                    const double* __restrict__ hp, const double* __restrict__ linv, const double* __restrict__ w,
                    double mu, double sigma2, double y_min, double ei_weight, double var_extra, int need_s,
                    double* __restrict__ yhat_out, double* __restrict__ s_out, double* __restrict__ ei_out) {
+    // PERSISTENT: one CTA per SM walks query tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The tables, the staged
+    // sample coordinates and the hyper-parameters are set up once per CTA, and the chunk pipeline runs straight
+    // through tile boundaries: psi chunk 0 / the first L^-1 chunk of the NEXT tile are produced under the last
+    // DMMA chunk of the current one, and a tile's final reduction (yhat, s, EI: 32 threads) happens after the next
+    // tile's first barrier -- no prologue, epilogue or pipeline fill is exposed between tiles.
     extern __shared__ __align__(16) double pr_smem[];
     double* tab = pr_smem;                                          // 64 x 16 : 2^(j/64), bank replicated
     double* ltab = tab + 64 * 16;                                   // 3 x 64 x 16 : log2 split tables
     double (*As)[PR_QT * PR_ALD] = reinterpret_cast<double (*)[PR_QT * PR_ALD]>(ltab + 3 * 64 * 16);
-    double* xq = reinterpret_cast<double*>(As + 2);                 // 32 x PK_MAX_K
-    double2* thp = reinterpret_cast<double2*>(xq + PR_QT * PK_MAX_K);  // PK_MAX_K
-    double (*ypart)[PR_QT] = reinterpret_cast<double (*)[PR_QT]>(thp + PK_MAX_K);
-    double (*qpart)[PR_QT + 1] = reinterpret_cast<double (*)[PR_QT + 1]>(ypart + PR_WARPS);
+    const int xst = k;                                              // row stride of a staged query point
+    double* xqs0 = reinterpret_cast<double*>(As + 2);               // 2 (tile parity) x 32 x k
+    double* xqs[2] = {xqs0, xqs0 + PR_QT * xst};
+    double2* thp = reinterpret_cast<double2*>(xqs0 + 2 * PR_QT * ((xst + 1) & ~1));  // PK_MAX_K
+    double (*ypart)[PR_WARPS][PR_QT] = reinterpret_cast<double (*)[PR_WARPS][PR_QT]>(thp + PK_MAX_K);  // per tile parity
+    double (*qpart)[PR_WARPS][PR_QT + 1] = reinterpret_cast<double (*)[PR_WARPS][PR_QT + 1]>(ypart + 2);
     // B stages: 2 x (16 warps x NTW blocks x 128 doubles), every warp owns its slice
-    double* Bst = reinterpret_cast<double*>(qpart + PR_WARPS);
+    double* Bst = reinterpret_cast<double*>(qpart + 2);
     Bst += (16 - ((size_t)(Bst - pr_smem) & 15)) & 15;              // 128-byte aligned rows
     double* Xs = Bst + 2 * PR_WARPS * NTW * 128;                    // n x k when it fits
     const bool x_staged = (n * k <= PR_XS_MAX);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fc = lane & 3;
-    const int64_t q0 = (int64_t)blockIdx.x * PR_QT;
-    const int qv = (int)min((int64_t)PR_QT, m - q0);
+    const int64_t ntiles = (m + PR_QT - 1) / PR_QT;
 
     fill_exp2_table(tab, tid, PR_THREADS);
     fill_log2_tables(ltab, tid, PR_THREADS);
-    for (int i = tid; i < PR_QT * k; i += PR_THREADS) {
-        const int q = i / k;
-        xq[q * PK_MAX_K + (i - q * k)] = (q < qv) ? Xq[q0 * k + i] : 0.0;
-    }
     if (tid < k) thp[tid] = make_double2(hp[tid], hp[PK_MAX_K + tid]);
     if (x_staged)
         for (int i = tid; i < n * k; i += PR_THREADS) Xs[i] = X[i];
+    // query points of a tile into the shared buffer of its parity (generic-k path and the final reduction's qv)
+    auto stage_queries = [&](int64_t tile, int par) {
+        const int64_t q0 = tile * PR_QT;
+        const int qv = (int)min((int64_t)PR_QT, m - q0);
+        for (int i = tid; i < PR_QT * k; i += PR_THREADS) {
+            const int q = i / k;
+            xqs[par][i] = (q < qv) ? Xq[q0 * k + i] : 0.0;
+        }
+    };
+    int64_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    stage_queries(tile, 0);
     __syncthreads();
     const char* tabp = reinterpret_cast<const char*>(tab + (tid & 15));
     const double* Xsrc = x_staged ? Xs : X;
     // compile-time k: hyper-parameters and this thread's query point live in registers
-    double th_r[KK > 0 ? KK : 1], p_r[KK > 0 ? KK : 1], xq_r[KK > 0 ? KK : 1];
+    double th_r[KK > 0 ? KK : 1], p_r[KK > 0 ? KK : 1], xq_r[KK > 0 ? KK : 1], xq_n[KK > 0 ? KK : 1];
     bool special = false;  // some exponent is exactly 1 or 2 (exact d / d*d path, CTA uniform)
     if (KK > 0) {
 #pragma unroll
         for (int d = 0; d < KK; ++d) {
             th_r[d] = thp[d].x;
             p_r[d] = thp[d].y;
-            xq_r[d] = xq[lane * PK_MAX_K + d];
+            xq_r[d] = xqs[0][lane * xst + d];
+            xq_n[d] = 0.0;
             special |= (p_r[d] == 1.0 || p_r[d] == 2.0);
         }
     }
 
     // psi producer: this thread owns query `lane` and sample slot `warp` of every chunk
-    double ys = 0.0;
-    auto make_psi = [&](int kc, double* dst) {
+    auto make_psi = [&](int kc, double* dst, const double (&xr_q)[KK > 0 ? KK : 1], const double* xqq, int qv,
+                        double& ys) {
         const int r = kc * PR_KC + warp;
         double v = 0.0;
         if (r < n && lane < qv) {
@@ -439,12 +585,11 @@ predict_reg_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X
                 for (int d = 0; d < KK; ++d) {
                     double lh;
                     float ll;
-                    log2_split_smem(fabs(xr[d] - xq_r[d]), ltab, tid & 15, lh, ll);
+                    log2_split_smem(fabs(xr[d] - xr_q[d]), ltab, tid & 15, lh, ll);
                     term[d] = th_r[d] * exp2_lean(p_r[d], lh, (double)ll, tabp);
                 }
                 S = sum_numpy_order(KK, [&](int d) { return term[d]; });
             } else {
-                const double* xqq = xq + lane * PK_MAX_K;
                 S = sum_numpy_order(k, [&](int d) {
                     const double2 tp = thp[d];
                     return tp.x * pow_abs_lean(fabs(xr[d] - xqq[d]), tp.y, tabp, ltab, tid & 15);
@@ -481,9 +626,9 @@ predict_reg_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X
         const int num = PR_KC * kc - 8 * warp - 7;
         return (num <= 0) ? 0 : ((num + 8 * PR_WARPS - 1) / (8 * PR_WARPS));
     };
-    auto load_B = [&](int kc) {
+    auto load_B = [&](int kc, int stage) {
         const int lo = first_live(kc);
-        double* dst = Bw + (kc & 1) * BSTAGE;
+        double* dst = Bw + stage * BSTAGE;
         const double* src = linv + (size_t)(8 * warp) * np + PR_KC * kc;
 #pragma unroll
         for (int i = 0; i < 2 * NTW; ++i) {
@@ -493,6 +638,27 @@ predict_reg_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X
                            src + (size_t)(8 * PR_WARPS * ni + row) * np + 2 * piece);
         }
     };
+    // final reduction of a finished tile (partials of parity `par`): yhat partials over the 16 sample slots, |v|^2
+    // over the column blocks, then s and EI.  Runs on the first 32 threads after a CTA barrier.
+    auto finish_tile = [&](int64_t t, int par) {
+        const int64_t q0 = t * PR_QT;
+        const int qv = (int)min((int64_t)PR_QT, m - q0);
+        if (tid < qv) {
+            double ysum = 0.0, qs = 0.0;
+#pragma unroll
+            for (int z = 0; z < PR_WARPS; ++z) ysum += ypart[par][z][tid];
+            const double yhat = mu + ysum;
+            if (yhat_out) yhat_out[q0 + tid] = yhat;
+            if (need_s) {
+#pragma unroll
+                for (int z = 0; z < PR_WARPS; ++z) qs += qpart[par][z][tid];
+                const double ssqr = sigma2 * (1.0 + var_extra - qs);
+                const double S = sqrt(fabs(ssqr));
+                if (s_out) s_out[q0 + tid] = S;
+                if (ei_out) ei_out[q0 + tid] = expected_improvement(yhat, S, y_min, ei_weight);
+            }
+        }
+    };
     if (need_s) {
         // blocks beyond the padded order are never loaded: they must read as zeros in both stages
 #pragma unroll
@@ -500,64 +666,92 @@ predict_reg_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X
             if (!((valid_mask >> ni) & 1u))
                 for (int i = lane; i < 128; i += 32) Bw[ni * 128 + i] = Bw[BSTAGE + ni * 128 + i] = 0.0;
         __syncwarp();
-        load_B(0);
+        load_B(0, 0);
     }
     cp_async_commit();
-    make_psi(0, As[0]);
-    for (int kc = 0; kc < nch; ++kc) {
-        if (need_s && kc + 1 < nch) load_B(kc + 1);  // the stage it overwrites was consumed by this warp in chunk kc - 1
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();  // chunk kc of psi is complete (and every lane's B pieces have landed); the other A stage is free
-        if (kc + 1 < nch) make_psi(kc + 1, As[(kc + 1) & 1]);
-        if (need_s) {
-            const double* as = As[kc & 1];
-            const double* bw = Bw + (kc & 1) * BSTAGE;
-            switch (first_live(kc)) {
-                case 0: pred_consume<NTW, 0>(acc, as, bw, boff, lane); break;
-                case 1:
-                    if (NTW > 1) pred_consume<NTW, (NTW > 1 ? 1 : 0)>(acc, as, bw, boff, lane);
-                    break;
-                case 2:
-                    if (NTW > 2) pred_consume<NTW, (NTW > 2 ? 2 : 0)>(acc, as, bw, boff, lane);
-                    break;
-                case 3:
-                    if (NTW > 3) pred_consume<NTW, (NTW > 3 ? 3 : 0)>(acc, as, bw, boff, lane);
-                    break;
-                default: break;
+    double ys = 0.0, ys_n = 0.0;
+    int qv = (int)min((int64_t)PR_QT, m - tile * PR_QT);
+    make_psi(0, As[0], xq_r, xqs[0] + lane * xst, qv, ys);
+    unsigned g = 0;    // chunks consumed so far by this CTA: stage of chunk g = g & 1
+    int tpar = 0;      // parity of the current tile (query buffer, partials)
+    int64_t done_tile = -1;  // tile whose partials wait for their final reduction
+    for (;;) {
+        const int64_t next_tile = tile + gridDim.x;
+        const bool has_next = next_tile < ntiles;
+        int qv_n = 0;
+        if (has_next) {
+            // the next tile's query points: shared buffer of the other parity (visible after this tile's barriers)
+            // and, for compile-time k, straight into registers
+            stage_queries(next_tile, tpar ^ 1);
+            qv_n = (int)min((int64_t)PR_QT, m - next_tile * PR_QT);
+            if (KK > 0) {
+#pragma unroll
+                for (int d = 0; d < KK; ++d)
+                    xq_n[d] = (lane < qv_n) ? __ldg(Xq + (next_tile * PR_QT + lane) * KK + d) : 0.0;
             }
-            __syncwarp();  // all lanes are done with this stage before the next load_B overwrites it
         }
-    }
-    // ---- reductions: yhat partials over the 16 sample slots, |v|^2 over columns -------------------
-    ypart[warp][lane] = ys;
-    if (need_s) {
+        for (int kc = 0; kc < nch; ++kc, ++g) {
+            const bool last = (kc + 1 == nch);
+            const int st = (int)(g & 1u);
+            if (need_s && (!last || has_next)) load_B(last ? 0 : kc + 1, st ^ 1);  // that stage was consumed by this warp in chunk g - 1
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();  // chunk g of psi is complete (and every lane's B pieces have landed); the other A stage is free
+            if (done_tile >= 0) {  // partials of the previous tile are complete as of this barrier
+                finish_tile(done_tile, tpar ^ 1);
+                done_tile = -1;
+            }
+            if (!last) make_psi(kc + 1, As[st ^ 1], xq_r, xqs[tpar] + lane * xst, qv, ys);
+            else if (has_next) make_psi(0, As[st ^ 1], xq_n, xqs[tpar ^ 1] + lane * xst, qv_n, ys_n);
+            if (need_s) {
+                const double* as = As[st];
+                const double* bw = Bw + st * BSTAGE;
+                switch (first_live(kc)) {
+                    case 0: pred_consume<NTW, 0>(acc, as, bw, boff, lane); break;
+                    case 1:
+                        if (NTW > 1) pred_consume<NTW, (NTW > 1 ? 1 : 0)>(acc, as, bw, boff, lane);
+                        break;
+                    case 2:
+                        if (NTW > 2) pred_consume<NTW, (NTW > 2 ? 2 : 0)>(acc, as, bw, boff, lane);
+                        break;
+                    case 3:
+                        if (NTW > 3) pred_consume<NTW, (NTW > 3 ? 3 : 0)>(acc, as, bw, boff, lane);
+                        break;
+                    default: break;
+                }
+                __syncwarp();  // all lanes are done with this stage before the next load_B overwrites it
+            }
+        }
+        // ---- partials of this tile; the final reduction follows the next CTA barrier -------------------
+        ypart[tpar][warp][lane] = ys;
+        if (need_s) {
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            double v = 0.0;
+            for (int mi = 0; mi < 4; ++mi) {
+                double v = 0.0;
 #pragma unroll
-            for (int ni = 0; ni < NTW; ++ni) v += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (fc == 0) qpart[warp][mi * 8 + fr] = v;
+                for (int ni = 0; ni < NTW; ++ni) {
+                    v += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+                    acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                }
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (fc == 0) qpart[tpar][warp][mi * 8 + fr] = v;
+            }
+        }
+        done_tile = tile;
+        if (!has_next) break;
+        tile = next_tile;
+        tpar ^= 1;
+        qv = qv_n;
+        ys = ys_n;
+        ys_n = 0.0;
+        if (KK > 0) {
+#pragma unroll
+            for (int d = 0; d < KK; ++d) xq_r[d] = xq_n[d];
         }
     }
     __syncthreads();
-    if (tid < qv) {
-        double ysum = 0.0, qs = 0.0;
-#pragma unroll
-        for (int z = 0; z < PR_WARPS; ++z) ysum += ypart[z][tid];
-        const double yhat = mu + ysum;
-        if (yhat_out) yhat_out[q0 + tid] = yhat;
-        if (need_s) {
-#pragma unroll
-            for (int z = 0; z < PR_WARPS; ++z) qs += qpart[z][tid];
-            const double ssqr = sigma2 * (1.0 + var_extra - qs);
-            const double S = sqrt(fabs(ssqr));
-            if (s_out) s_out[q0 + tid] = S;
-            if (ei_out) ei_out[q0 + tid] = expected_improvement(yhat, S, y_min, ei_weight);
-        }
-    }
+    finish_tile(done_tile, tpar);
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
@@ -607,19 +801,52 @@ static cudaError_t launch_predict_t(pk_handle* h, int64_t m, const double* Xq, c
     return cudaGetLastError();
 }
 
+static cudaError_t launch_predict_big(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu,
+                                      double sigma2, double y_min, double ei_weight, double var_extra, double* yhat,
+                                      double* sout, double* ei) {
+    const int np = h->fit_np, k = h->k;
+    const size_t smem = sizeof(double) * ((size_t)PSTAGES * (PB_QT + PK_TILE) * PSLD + (size_t)PB_QT * k + 2 * k +
+                                          PB_QT + PB_QT * 8);
+    const int64_t ntiles = (m + PB_QT - 1) / PB_QT;
+    const int grid = (int)((ntiles < 2 * (int64_t)h->sm_count) ? ntiles : 2 * (int64_t)h->sm_count);
+    const size_t need = (size_t)grid * PB_QT * (np + 4);
+    if (need > h->cap_pscratch) {
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return e;
+        if (h->d_pscratch) cudaFree(h->d_pscratch);
+        h->d_pscratch = nullptr;
+        h->cap_pscratch = 0;
+        e = cudaMalloc((void**)&h->d_pscratch, need * sizeof(double));
+        if (e != cudaSuccess) return e;
+        h->cap_pscratch = need;
+    }
+    cudaError_t e = cudaFuncSetAttribute(predict_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int need_s = (sout != nullptr || ei != nullptr) ? 1 : 0;
+    predict_big_kernel<<<grid, PRED_THREADS, smem, h->stream>>>(h->n, np, k, m, h->dX, Xq, hp, h->d_linv, h->d_w, mu,
+                                                                sigma2, y_min, ei_weight, var_extra, need_s,
+                                                                h->d_pscratch, yhat, sout, ei);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+
 template <int NTW, int KK>
 static cudaError_t launch_predict_reg_k(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu,
                                         double sigma2, double y_min, double ei_weight, double var_extra, double* yhat,
                                         double* sout, double* ei) {
     const int need_s = (sout != nullptr || ei != nullptr) ? 1 : 0;
-    const int64_t blocks = (m + PR_QT - 1) / PR_QT;
-    constexpr size_t smem = sizeof(double) * (64 * 16 + 3 * 64 * 16 + 2 * PR_QT * PR_ALD + PR_QT * PK_MAX_K +
-                                              2 * PK_MAX_K + PR_WARPS * PR_QT + PR_WARPS * (PR_QT + 1) + 16 +
-                                              2 * PR_WARPS * NTW * 128 + PR_XS_MAX);
+    const int64_t ntiles = (m + PR_QT - 1) / PR_QT;
+    const int64_t blocks = (ntiles < (int64_t)h->sm_count) ? ntiles : (int64_t)h->sm_count;  // persistent: one CTA per SM
+    const int k = h->k;
+    const size_t xs = ((size_t)h->n * k <= (size_t)PR_XS_MAX) ? (size_t)h->n * k : 0;  // staged sample coordinates
+    const size_t smem = sizeof(double) * (64 * 16 + 3 * 64 * 16 + 2 * PR_QT * PR_ALD + 2 * PR_QT * ((k + 1) & ~1) +
+                                          2 * PK_MAX_K + 2 * PR_WARPS * PR_QT + 2 * PR_WARPS * (PR_QT + 1) + 16 +
+                                          2 * PR_WARPS * NTW * 128 + xs);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e =
-            cudaFuncSetAttribute(predict_reg_kernel<NTW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(predict_reg_kernel<NTW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -656,8 +883,8 @@ cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const doub
     }
     if (np <= 512) return launch_predict_t<32>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
     if (np <= 1280) return launch_predict_t<16>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
-    if (np <= 3072) return launch_predict_t<8>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
-    return cudaErrorInvalidValue;
+    if (np <= 2944) return launch_predict_t<8>(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
+    return launch_predict_big(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
 }
 
 }  // namespace pk

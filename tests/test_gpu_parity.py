@@ -325,6 +325,44 @@ def test_regression_n4096_matches_oracle(handle):
         assert rel_err(out["sigma2"][i], s2) < tol, i
 
 
+@pytest.mark.parametrize("n,k", [(2900, 3), (3000, 3), (4096, 6)])
+def test_regression_fit_predict_large_n_matches_oracle(handle, n, k):
+    """pk_fit + pk_predict_batch beyond the shared-memory psi tile (np > 2944: predict_big_kernel, psi slab in a
+    global scratch) and right at its edge; n = 4096, k = 6 is config C4 (regression kriging, lambda on the
+    diagonal, predict_var without lambda as regressionkrige.py:195 -> matrixops.py:79-95)."""
+    X = onp.rlh(n, k, 11)
+    rng = np.random.default_rng(12)
+    y = onp.f_squared(X) + rng.normal(0.0, 0.05, n)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    theta = 10.0 ** rng.uniform(-1.0, 1.0, k)
+    p = rng.uniform(1.81231, 2.0, k)
+    lam = 1e-2
+    out4, info = handle.fit(theta, p, lam, mode=1)
+    assert info == 0
+    m = 333  # ragged: not a multiple of the 32-query tile
+    Xq = rng.uniform(0, 1, (m, k))
+    Xq[:40] = Xn[::n // 40][:40]
+    y_min = float(np.min(yn))
+    ref = onp.predict_batch_fast(Xn, yn, theta, p, lam, Xq, y_min=y_min)
+    cond = min(1e9, (n + 2.0) / lam)  # the nugget bounds cond(Psi)
+    tol = tol_for_cond(cond)
+    assert rel_err(out4[1], ref["mu"]) < tol and rel_err(out4[2], ref["sigma2"]) < tol
+    got = handle.predict_batch(Xq, theta, p, out4[1], out4[2], y_min=y_min)
+    ytol = max(1e-9, 50.0 * cond * 2.2e-16)
+    vtol = out4[2] * max(1e-12, 100.0 * cond * 2.2e-16)
+    assert np.max(np.abs(got["yhat"] - ref["yhat"])) < ytol
+    assert np.max(np.abs(got["s"] ** 2 - ref["s"] ** 2)) < vtol
+    ds = np.abs(got["s"] - ref["s"])
+    sig = np.sqrt(out4[2])
+    assert np.all(np.abs(got["ei"] - ref["ei"]) <= 1e-9 * sig + 0.5 * ds + 1e-9 * np.abs(ref["ei"]))
+    # more tiles than CTAs of the persistent grid: every tile must come out the same as in the small call
+    big = np.tile(Xq, (40, 1))
+    got2 = handle.predict_batch(big, theta, p, out4[1], out4[2], y_min=y_min)
+    assert np.array_equal(got2["s"].reshape(40, m), np.tile(got["s"], (40, 1)))
+    assert np.array_equal(got2["yhat"].reshape(40, m), np.tile(got["yhat"], (40, 1)))
+
+
 def test_predict_device_and_host_paths_agree(handle):
     """The chunked host-buffer path and the single device-pointer launch must give identical results
     (size-independent property used at the 16 Mi-point scale of config C5)."""

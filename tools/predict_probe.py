@@ -23,4 +23,22 @@ for _ in range(2):
     h.predict_batch_raw(m, Xq, np.array([5.0, 5.0]), np.array([1.8, 1.8]), float(model.mu), float(model.SigmaSqr), 0.0, -1.0,
                         0.0, out[0], out[1], out[2])
 h.synchronize()
+if os.environ.get("PK_PROBE_TIME"):
+    # timing: 16 Mi-point grid (config C5) on the handle's stream
+    g = torch.linspace(0, 1, 4096, dtype=torch.float64, device="cuda")
+    grid = torch.stack(torch.meshgrid(g, g, indexing="ij"), dim=-1).reshape(-1, 2).contiguous()
+    mg = grid.shape[0]
+    o = torch.empty(3, mg, dtype=torch.float64, device="cuda")
+    args = (mg, grid, np.array([5.0, 5.0]), np.array([1.8, 1.8]), float(model.mu), float(model.SigmaSqr), 0.0, -1.0, 0.0,
+            o[0], o[1], o[2])
+    h.predict_batch_raw(*args)
+    h.synchronize()
+    import time
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        h.predict_batch_raw(*args)
+        h.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    print("predictions/s %.4g  (%.2f ms per 16 Mi points)" % (mg / best, best * 1e3))
 print("ok", float(out[2].max()))
