@@ -137,8 +137,11 @@ int pk_set_cholesky_variant(pk_handle *h, int variant);
 
 /* Tuning / test knob for the fused predictor behind pk_predict_batch (predict_normalized /
  * predicterr_normalized / expimp loops, matrixops.py:68-95, krige.py:201-258): 0 = automatic,
- * 1 = psi tile in shared memory + L^-1 streamed through shared memory (any n up to 2944),
- * 2 = v = L^-1 psi held in registers, psi chunks generated on the fly (n <= 512; falls back otherwise). */
+ * 1 = psi tile in shared memory + L^-1 streamed through shared memory (n up to 2944; beyond that the psi tile
+ *     lives in a per-CTA slab of a global scratch),
+ * 2 = v = L^-1 psi held in registers, psi chunks generated on the fly (n <= 512; falls back otherwise),
+ * 3 = split pipeline: psi rows + yhat in one FP64-ALU kernel (through an HBM scratch), |L^-1 psi|^2, s and EI in a
+ *     TMA-fed DMMA kernel (any n; what 0 selects for 4096 query points or more). */
 int pk_set_predict_variant(pk_handle *h, int variant);
 
 /* pk_nll_batch pipelining experiment (the candidate loop of krige.py:429-452 has no such notion: it is

@@ -189,7 +189,7 @@ int pk_set_pivot_tolerance(pk_handle* h, double tol) {
 }
 
 int pk_set_cholesky_variant(pk_handle* h, int variant) {
-    if (!h || variant < 0 || variant > 2) return 1;
+    if (!h || variant < 0 || variant > 3) return 1;
     h->chol_variant = variant;
     return 0;
 }
@@ -201,7 +201,7 @@ int pk_set_overlap(pk_handle* h, int enabled) {
 }
 
 int pk_set_predict_variant(pk_handle* h, int variant) {
-    if (!h || variant < 0 || variant > 2) return 1;
+    if (!h || variant < 0 || variant > 3) return 1;
     h->predict_variant = variant;
     return 0;
 }
@@ -558,8 +558,12 @@ int pk_predict_batch(pk_handle* h, int64_t m, const double* Xq, const double* th
     if (chunk * k > h->cap_q) {
         PK_CUDA(h, cudaStreamSynchronize(h->stream));
         PK_CUDA(h, regrow(&h->d_q, (size_t)chunk * k));
-        PK_CUDA(h, regrow(&h->d_qout, (size_t)chunk * 3));
         h->cap_q = chunk * k;
+    }
+    if (chunk > h->cap_qout) {  // sized on its own: k may have changed since the query buffer last grew
+        PK_CUDA(h, cudaStreamSynchronize(h->stream));
+        PK_CUDA(h, regrow(&h->d_qout, (size_t)chunk * 3));
+        h->cap_qout = chunk;
     }
     for (int64_t q0 = 0; q0 < m; q0 += chunk) {
         const int64_t mc = (m - q0 < chunk) ? (m - q0) : chunk;

@@ -23,7 +23,7 @@ struct pk_handle {
     size_t ev_used = 0;
     double pivot_tol = 2.0 * PK_EPS_DIAG;  // relative pivot threshold, 2 ulps (see pk_set_pivot_tolerance)
     int chol_variant = 0;                  // 0 auto, 1 one launch per block column, 2 persistent CTA per candidate
-    int predict_variant = 0;               // 0 auto, 1 shared-memory psi tile kernel (any n), 2 register-resident (n <= 512)
+    int predict_variant = 0;               // 0 auto, 1 shared-memory psi tile kernel, 2 register-resident (n <= 512), 3 split (psi rows kernel + TMA-fed DMMA kernel)
     unsigned int* d_queue = nullptr;       // candidate queues of the persistent Cholesky kernel (PK_QUEUE_SLOTS counters)
     int queue_slot = 0;                    // counter the next launch_cholesky_cta uses
     // Psi construction of the NEXT part of a population overlaps the Cholesky of the current one: the Psi
@@ -74,7 +74,8 @@ struct pk_handle {
     // staging for predict
     double* d_q = nullptr;    // query chunk
     double* d_qout = nullptr; // 3 x chunk
-    int64_t cap_q = 0;
+    int64_t cap_q = 0;      // doubles in d_q
+    int64_t cap_qout = 0;   // query points d_qout has room for (3 outputs each)
     double* d_hp = nullptr;   // 2 x PK_MAX_K (theta | p) for predict
     double* d_pscratch = nullptr;  // psi slabs of predict_big_kernel (np > 2944): grid x 32 x (np + 4)
     size_t cap_pscratch = 0;
@@ -119,6 +120,9 @@ cudaError_t launch_compute_w(pk_handle* h, const TiledShape& s, double mu);
 cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
                            double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
                            double* ei);
+cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
+                                 double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
+                                 double* ei);
 cudaError_t launch_extract_U(pk_handle* h, const TiledShape& s, double* out);
 cudaError_t launch_append_point(pk_handle* h, const TiledShape& s, const double* xnew_dev, double y_new, double diag,
                                 double* scratch, int32_t* info);

@@ -1,0 +1,468 @@
+// Prediction path, split variant: two kernels per block of query points.
+//
+// Replaces the same reference code as pk_predict.cu (matrixops.predict_normalized / predicterr_normalized,
+// matrixops.py:68-95, and kriging.expimp / weightedexpimp, krige.py:201-234), for LARGE query sets:
+//
+//   psi_rows_kernel   psi[q, r] = exp(-sum_d theta_d |X_rd - xq_d|^p_d)  for a block of queries, written row-major
+//                     (q, np) into an HBM scratch, together with yhat_q = mu + psi_q . w.  Pure FP64-ALU kernel:
+//                     a warp owns a query, its lanes walk the samples (coalesced 256-byte stores), two samples
+//                     per lane in flight.
+//   trinorm_kernel    |L^-1 psi_q|^2 for 64 queries x 256 columns of v at a time: a TMA-fed DMMA GEMM of the psi
+//                     tile against the rows of the cached L^-1 (lower triangular: chunks right of the diagonal
+//                     are neither loaded nor multiplied), followed by s = sqrt|sigma2 (1 + extra - |v|^2)| and EI.
+//
+// Why two kernels: in the fused predictors a warp alternates between a ~100-deep dependent FP64 chain (psi) and a
+// burst of DMMAs; both run on the same FP64 pipe, the chain's instructions queue behind the other warps' 16-cycle
+// DMMAs and the pipe idles 42 % of the time (profiles/ncu_predict_reg_r01_z.txt).  Apart, each kernel keeps
+// the pipe busy on its own; the price -- psi through HBM, 2 x 8 np bytes per query -- is 136 GB for the 16 Mi-point
+// grid of config C5, 21 ms of HBM time hidden under 200 ms of arithmetic.
+#include <cuda.h>
+
+#include "pk_internal.h"
+#include "pk_math.cuh"
+
+namespace pk {
+
+// expected_improvement: same formula as pk_predict.cu (krige.py:207-217 / 227-233, operation order kept)
+__device__ __forceinline__ double expected_improvement2(double yhat, double S, double y_min, double w) {
+    if (S <= 0.0) return 0.0;
+    const double u = y_min - yhat;
+    const double one = u * (0.5 + 0.5 * erf((1.0 / sqrt(2.0)) * (u / S)));
+    const double two = (S * (1.0 / sqrt(2.0 * CUDART_PI))) * exp(-(1.0 / 2.0) * ((u * u) / (S * S)));
+    if (w < 0.0) return one + two;
+    return w * one + (1.0 - w) * two;
+}
+
+// ---- kernel A: psi rows + yhat -----------------------------------------------------------------------
+constexpr int PA_THREADS = 768;
+constexpr int PA_WARPS = PA_THREADS / 32;
+constexpr int PA_XT_MAX = 12288;  // staged (transposed) sample coordinates: k * np doubles <= 96 KB
+
+// bytes in front of the 32 KB-aligned 2^x table: log2 tables + hyper-parameters + per-dimension mode + X^T
+__host__ __device__ inline unsigned pa_small_bytes(int xt_doubles) {
+    return (unsigned)(sizeof(double) * (3 * 64 * 16 + 2 * PK_MAX_K + xt_doubles) + sizeof(int) * PK_MAX_K);
+}
+
+// theta_d |d|^p_d for one dimension.  mode: 0 = table-driven 2^(p log2 d) (p in [0.25, 3], not 1 or 2),
+// 1 = p == 1 (exact d), 2 = p == 2 (exact d*d, as np.power), 3 = any other exponent (range-checked path)
+__device__ __forceinline__ double pa_term(double dd, double th, double p, int mode, const double* ltab, int bank,
+                                          unsigned tab_saddr) {
+    if (mode == 0) {
+        double lh;
+        float lf;
+        log2_split_smem(dd, ltab, bank, lh, lf);
+        double ll = (double)lf;
+        if (!(lh > -L2_CLAMP)) { lh = -L2_CLAMP; ll = 0.0; }
+        if (lh > L2_CLAMP) { lh = L2_CLAMP; ll = 0.0; }
+        return th * exp2_lean4k(p, lh, ll, tab_saddr);
+    }
+    if (mode == 2) return th * (dd * dd);
+    if (mode == 1) return th * dd;
+    double l0;
+    float l1;
+    log2_split(dd, l0, l1);
+    const double s = p * l0;
+    const double e = fma(p, (double)l1, fma(p, l0, -s));
+    return th * exp2_const(s, e);
+}
+
+template <int KK>
+__global__ void __launch_bounds__(PA_THREADS, 1)
+psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, const double* __restrict__ Xq,
+                const double* __restrict__ hp, const double* __restrict__ w, double mu, int xt_staged,
+                double* __restrict__ psi_out, double* __restrict__ yhat_out) {
+    extern __shared__ __align__(16) double pa_smem[];
+    double* ltab = pa_smem;                                   // 3 x 64 x 16
+    double* th_s = ltab + 3 * 64 * 16;                        // PK_MAX_K
+    double* p_s = th_s + PK_MAX_K;                            // PK_MAX_K
+    int* mode_s = reinterpret_cast<int*>(p_s + PK_MAX_K);     // PK_MAX_K
+    double* Xt = reinterpret_cast<double*>(mode_s + PK_MAX_K);  // k x np (transposed: conflict-free per-lane reads)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(pa_smem);
+    const unsigned tab_saddr = (smem_base + pa_small_bytes(xt_staged ? k * np : 0) + 0x7fffu) & ~0x7fffu;
+    double* tab4k = pa_smem + (tab_saddr - smem_base) / sizeof(double);
+    fill_exp2_4096(tab4k, tid, PA_THREADS);
+    fill_log2_tables(ltab, tid, PA_THREADS);
+    if (tid < k) {
+        const double pd = hp[PK_MAX_K + tid];
+        th_s[tid] = hp[tid];
+        p_s[tid] = pd;
+        mode_s[tid] = (pd == 1.0) ? 1 : (pd == 2.0) ? 2 : (pd >= 0.25 && pd <= 3.0) ? 0 : 3;
+    }
+    if (xt_staged) {
+        for (int i = tid; i < k * np; i += PA_THREADS) {
+            const int d = i / np, r = i - d * np;
+            Xt[i] = (r < n) ? X[(size_t)r * k + d] : 0.0;
+        }
+    }
+    __syncthreads();
+    const int bank = tid & 15;
+    double th_r[KK > 0 ? KK : 1], p_r[KK > 0 ? KK : 1];
+    if (KK > 0) {
+#pragma unroll
+        for (int d = 0; d < KK; ++d) {
+            th_r[d] = th_s[d];
+            p_r[d] = p_s[d];
+        }
+    }
+    bool lean = true;  // every exponent takes the table-driven path: straight-line code, two chains interleaved
+    for (int d = 0; d < k; ++d) lean &= (mode_s[d] == 0);
+    const int nit = np / 32;  // even: np is a multiple of 64
+    for (int64_t q = (int64_t)blockIdx.x * PA_WARPS + warp; q < mc; q += (int64_t)gridDim.x * PA_WARPS) {
+        double xq_r[KK > 0 ? KK : 1];
+        if constexpr (KK > 0) {
+#pragma unroll
+            for (int d = 0; d < KK; ++d) xq_r[d] = __ldg(Xq + q * KK + d);
+        }
+        const double* xqg = Xq + q * k;
+        // S(r) = sum_d theta_d |X_rd - xq_d|^p_d in NumPy's summation order; r < n (clamped by the caller)
+        auto S_lean = [&](int r) {
+            if constexpr (KK > 0) {
+                double term[KK > 0 ? KK : 1];
+#pragma unroll
+                for (int d = 0; d < KK; ++d) {
+                    const double xr = xt_staged ? Xt[d * np + r] : __ldg(X + (size_t)r * KK + d);
+                    term[d] = pa_term(fabs(xr - xq_r[d]), th_r[d], p_r[d], 0, ltab, bank, tab_saddr);
+                }
+                return sum_numpy_order(KK, [&](int d) { return term[d]; });
+            } else {
+                return sum_numpy_order(k, [&](int d) {
+                    const double xr = xt_staged ? Xt[d * np + r] : __ldg(X + (size_t)r * k + d);
+                    return pa_term(fabs(xr - __ldg(xqg + d)), th_s[d], p_s[d], 0, ltab, bank, tab_saddr);
+                });
+            }
+        };
+        auto S_any = [&](int r) {
+            return sum_numpy_order(k, [&](int d) {
+                const double xr = xt_staged ? Xt[d * np + r] : __ldg(X + (size_t)r * k + d);
+                return pa_term(fabs(xr - __ldg(xqg + d)), th_s[d], p_s[d], mode_s[d], ltab, bank, tab_saddr);
+            });
+        };
+        double ys0 = 0.0, ys1 = 0.0;
+        double* prow = psi_out ? psi_out + (size_t)q * np : nullptr;
+        for (int it = 0; it < nit; it += 2) {
+            const int r0 = it * 32 + lane, r1 = r0 + 32;
+            const int c0 = min(r0, n - 1), c1 = min(r1, n - 1);  // padding rows: computed on a valid sample, then zeroed
+            double S0, S1;
+            if (lean) {
+                S0 = S_lean(c0);
+                S1 = S_lean(c1);
+            } else {
+                S0 = S_any(c0);
+                S1 = S_any(c1);
+            }
+            double v0 = expneg_4k(S0, tab_saddr), v1 = expneg_4k(S1, tab_saddr);
+            v0 = (r0 < n) ? v0 : 0.0;
+            v1 = (r1 < n) ? v1 : 0.0;
+            ys0 = fma(v0, __ldg(w + c0), ys0);
+            ys1 = fma(v1, __ldg(w + c1), ys1);
+            if (prow) {
+                prow[r0] = v0;
+                prow[r1] = v1;
+            }
+        }
+        const double ys = warp_sum(ys0 + ys1);
+        if (lane == 0 && yhat_out) yhat_out[q] = mu + ys;
+    }
+}
+
+// ---- kernel B: |L^-1 psi|^2 (TMA-fed DMMA), s, EI ------------------------------------------------------
+namespace tn {
+constexpr int THREADS = 512;
+constexpr int WARPS = THREADS / 32;
+constexpr int KC = 16;                       // samples per pipeline chunk: one stage row = 128 bytes
+constexpr int QT = 64;                       // queries per CTA tile
+constexpr int CB = 256;                      // columns of v per pass
+constexpr int STAGES = 4;
+constexpr int BOX_DOUBLES = 64 * KC;         // one TMA box: 64 rows x 16 doubles = 8 KB
+constexpr int A_STAGE = QT * KC;
+constexpr int B_STAGE = CB * KC;
+constexpr int STAGE_DOUBLES = A_STAGE + B_STAGE;   // 40 KB
+constexpr int SMEM_ALIGN = 1024;
+// + per-tile partial sums qsm[2][8][64] + mbarriers + release counters
+constexpr int SMEM_DOUBLES = STAGES * STAGE_DOUBLES + 2 * 8 * QT + STAGES + STAGES;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
+// acc(32 x 32 per warp: 4 x 4 DMMA tiles, column blocks LO .. HI-1 only) += A(32 x 16) * B(32 x 16)^T for one
+// stage.  Stage rows are 128 bytes with the 32-byte atoms XOR-swizzled by the row (SWIZZLE_128B_ATOM_32B):
+// lane (fr, fc) reads column 4i + fc of a row congruent to fr mod 8 at soff[i] = ((i ^ (fr & 3)) << 2) + fc.
+template <int LO, int HI>
+__device__ __forceinline__ void consume(double (&acc)[4][4][2], const double* a_s, const double* b_s,
+                                        const int (&soff)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[mi * 8 * KC + soff[i]];
+#pragma unroll
+        for (int ni = LO; ni < HI; ++ni) b[ni] = b_s[ni * 64 * KC + soff[i]];
+#pragma unroll
+        for (int ni = LO; ni < HI; ++ni)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+trinorm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int np, int64_t mc,
+               double sigma2, double y_min, double ei_weight, double var_extra, const double* __restrict__ yhat,
+               double* __restrict__ s_out, double* __restrict__ ei_out) {
+    extern __shared__ __align__(16) double tn_raw[];
+    double* smem = tn_raw + ((SMEM_ALIGN - ((unsigned)__cvta_generic_to_shared(tn_raw) & (SMEM_ALIGN - 1))) &
+                             (SMEM_ALIGN - 1)) / sizeof(double);
+    double* pipe = smem;
+    double (*qsm)[8][QT] = reinterpret_cast<double (*)[8][QT]>(pipe + STAGES * STAGE_DOUBLES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(qsm + 2);
+    int* rel = reinterpret_cast<int*>(bars + STAGES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int wq = warp & 1, cg = warp >> 1;  // query half (32 rows), column group: 8-column blocks cg, cg + 8, ...
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + s, 1);
+            rel[s] = 0;
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int soff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) soff[i] = ((i ^ (fr & 3)) << 2) + fc;
+
+    const int64_t ntiles = (mc + QT - 1) / QT;
+    const int ncb = (np + CB - 1) / CB;
+    // chunks of one tile: column pass cb needs the samples r < min(np, (cb + 1) * 256)
+    // position of a chunk in the CTA's flat sequence: (tile, cb, kc)
+    struct Pos {
+        int64_t tile;
+        int cb, kc;
+    };
+    auto nk_of = [&](int cb) { return min(np, (cb + 1) * CB) / KC; };
+    auto advance = [&](Pos& p) {
+        if (++p.kc == nk_of(p.cb)) {
+            p.kc = 0;
+            if (++p.cb == ncb) {
+                p.cb = 0;
+                p.tile += gridDim.x;
+            }
+        }
+    };
+    auto issue = [&](const Pos& p, unsigned g) {
+        const int ps = (int)(g % STAGES);
+        unsigned long long* bar = bars + ps;
+        const int c0 = p.cb * CB;
+        const int nbox = min(4, (np - c0) / 64);
+        mbar_arrive_expect_tx(bar, (unsigned)((1 + nbox) * BOX_DOUBLES * sizeof(double)));
+        double* st = pipe + ps * STAGE_DOUBLES;
+        tma_load_2d(st, &tmapA, p.kc * KC, (int)(p.tile * QT), bar);
+        for (int b = 0; b < nbox; ++b) tma_load_2d(st + A_STAGE + b * BOX_DOUBLES, &tmapB, p.kc * KC, c0 + 64 * b, bar);
+    };
+    Pos cons{(int64_t)blockIdx.x, 0, 0};
+    if (cons.tile >= ntiles) return;
+    Pos prod = cons;
+    if (tid == 0) {
+        Pos p = prod;
+        for (int c = 0; c < STAGES && p.tile < ntiles; ++c) {
+            issue(p, (unsigned)c);
+            advance(p);
+        }
+    }
+    for (int c = 0; c < STAGES; ++c) advance(prod);  // every warp tracks the chunk STAGES ahead of its own
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    double qpart[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned g = 0;
+    int tpar = 0;
+    while (cons.tile < ntiles) {
+        const int ps = (int)(g % STAGES);
+        mbar_wait(bars + ps, (g / STAGES) & 1u);
+        const double* st = pipe + ps * STAGE_DOUBLES;
+        const double* a_s = st + (wq * 32 + fr) * KC;
+        const double* b_s = st + A_STAGE + (cg * 8 + fr) * KC;
+        const int c0 = cons.cb * CB;
+        // live column blocks of this warp: ni with c0 + 64 ni + 8 cg + 7 >= 16 kc (lower triangle) and < np
+        const int num = KC * cons.kc - c0 - 8 * cg - 7;
+        const int lo = (num <= 0) ? 0 : ((num + 63) >> 6);
+        const int hi = min(4, (np - c0) >> 6);
+        switch (lo * 4 + hi - 1) {
+            case 0: consume<0, 1>(acc, a_s, b_s, soff); break;
+            case 1: consume<0, 2>(acc, a_s, b_s, soff); break;
+            case 2: consume<0, 3>(acc, a_s, b_s, soff); break;
+            case 3: consume<0, 4>(acc, a_s, b_s, soff); break;
+            case 5: consume<1, 2>(acc, a_s, b_s, soff); break;
+            case 6: consume<1, 3>(acc, a_s, b_s, soff); break;
+            case 7: consume<1, 4>(acc, a_s, b_s, soff); break;
+            case 10: consume<2, 3>(acc, a_s, b_s, soff); break;
+            case 11: consume<2, 4>(acc, a_s, b_s, soff); break;
+            case 15: consume<3, 4>(acc, a_s, b_s, soff); break;
+            default: break;
+        }
+        __syncwarp();
+        if (lane == 0 && atomicAdd(rel + ps, 1) == WARPS - 1) {  // last warp to release this stage: refill it
+            rel[ps] = 0;
+            if (prod.tile < ntiles) issue(prod, g + STAGES);
+        }
+        advance(prod);
+        ++g;
+        const bool pass_end = (cons.kc + 1 == nk_of(cons.cb));
+        const bool tile_end = pass_end && (cons.cb + 1 == ncb);
+        if (pass_end) {
+            // |v|^2 of this pass' columns, accumulators back to zero
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                double v = qpart[mi];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    v = fma(acc[mi][ni][0], acc[mi][ni][0], v);
+                    v = fma(acc[mi][ni][1], acc[mi][ni][1], v);
+                    acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                }
+                qpart[mi] = v;
+            }
+        }
+        if (tile_end) {
+            const int64_t q0 = cons.tile * QT;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                double v = qpart[mi];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (fc == 0) qsm[tpar][cg][wq * 32 + mi * 8 + fr] = v;
+                qpart[mi] = 0.0;
+            }
+            __syncthreads();  // once per tile (48 chunks at np = 512); the TMA queue keeps running underneath
+            if (tid < QT && q0 + tid < mc) {
+                double qs = 0.0;
+#pragma unroll
+                for (int z = 0; z < 8; ++z) qs += qsm[tpar][z][tid];
+                const double ssqr = sigma2 * (1.0 + var_extra - qs);
+                const double S = sqrt(fabs(ssqr));
+                if (s_out) s_out[q0 + tid] = S;
+                if (ei_out) ei_out[q0 + tid] = expected_improvement2(yhat[q0 + tid], S, y_min, ei_weight);
+            }
+            tpar ^= 1;
+        }
+        advance(cons);
+    }
+}
+
+static cudaError_t encode_2d(CUtensorMap* tmap, const double* base, uint64_t cols, uint64_t rows) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, 64};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
+}
+}  // namespace tn
+
+template <int KK>
+static cudaError_t launch_psi_rows(pk_handle* h, int64_t mc, const double* Xq, const double* hp, double mu,
+                                   double* psi_out, double* yhat_out) {
+    const int k = h->k, np = h->fit_np;
+    const int xt = (k * np <= PA_XT_MAX) ? 1 : 0;
+    // the dynamic window starts 1 KB into the CTA's shared memory: leave room for the 32 KB-aligned table wherever
+    // the base lies (same sizing rule as psi_pop_kernel)
+    const size_t smem = ((pa_small_bytes(xt ? k * np : 0) + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(psi_rows_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int64_t want = (mc + PA_WARPS - 1) / PA_WARPS;
+    const int grid = (int)((want < (int64_t)h->sm_count) ? want : (int64_t)h->sm_count);
+    psi_rows_kernel<KK><<<grid, PA_THREADS, smem, h->stream>>>(h->n, np, k, mc, h->dX, Xq, hp, h->d_w, mu, xt, psi_out,
+                                                               yhat_out);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+// yhat / s / ei may each be null; all pointers are device pointers.
+cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
+                                 double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
+                                 double* ei) {
+    const int np = h->fit_np, k = h->k;
+    const bool need_s = (sout != nullptr || ei != nullptr);
+    // queries per block: psi scratch of at most 1 GiB, at least one wave of 64-query tiles
+    int64_t mcap = ((int64_t)1 << 30) / ((int64_t)np * 8);
+    mcap = (mcap / 64) * 64;
+    if (mcap < 64 * (int64_t)h->sm_count) mcap = 64 * (int64_t)h->sm_count;
+    if (mcap > m) mcap = ((m + 63) / 64) * 64;
+    const size_t need = need_s ? (size_t)mcap * np + (size_t)mcap : 0;  // psi rows + yhat (when the caller wants none)
+    if (need > h->cap_pscratch) {
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return e;
+        if (h->d_pscratch) cudaFree(h->d_pscratch);
+        h->d_pscratch = nullptr;
+        h->cap_pscratch = 0;
+        e = cudaMalloc((void**)&h->d_pscratch, need * sizeof(double));
+        if (e != cudaSuccess) return e;
+        h->cap_pscratch = need;
+    }
+    double* psi = h->d_pscratch;
+    double* ytmp = need_s ? h->d_pscratch + (size_t)mcap * np : nullptr;
+    CUtensorMap tmapB;
+    const size_t smemB = sizeof(double) * (size_t)tn::SMEM_DOUBLES + tn::SMEM_ALIGN;
+    if (need_s) {
+        cudaError_t e = tn::encode_2d(&tmapB, h->d_linv, (uint64_t)np, (uint64_t)np);
+        if (e != cudaSuccess) return e;
+        static bool attr_done = false;
+        if (!attr_done) {
+            e = cudaFuncSetAttribute(tn::trinorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+    }
+    for (int64_t q0 = 0; q0 < m; q0 += mcap) {
+        const int64_t mc = (m - q0 < mcap) ? (m - q0) : mcap;
+        double* yh = yhat ? yhat + q0 : ytmp;
+        cudaError_t e;
+        switch (k) {
+#define PK_PA(KK_) case KK_: e = launch_psi_rows<KK_>(h, mc, Xq + q0 * k, hp, mu, need_s ? psi : nullptr, yh); break;
+            PK_PA(1) PK_PA(2) PK_PA(3)
+#undef PK_PA
+            default: e = launch_psi_rows<0>(h, mc, Xq + q0 * k, hp, mu, need_s ? psi : nullptr, yh); break;
+        }
+        if (e != cudaSuccess) return e;
+        if (!need_s) continue;
+        CUtensorMap tmapA;
+        e = tn::encode_2d(&tmapA, psi, (uint64_t)np, (uint64_t)mc);
+        if (e != cudaSuccess) return e;
+        const int64_t ntiles = (mc + tn::QT - 1) / tn::QT;
+        const int grid = (int)((ntiles < (int64_t)h->sm_count) ? ntiles : (int64_t)h->sm_count);
+        tn::trinorm_kernel<<<grid, tn::THREADS, smemB, h->stream>>>(tmapA, tmapB, np, mc, sigma2, y_min, ei_weight, var_extra,
+                                                                    yh, sout ? sout + q0 : nullptr, ei ? ei + q0 : nullptr);
+        h->launches++;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace pk

@@ -238,9 +238,11 @@ def test_small_and_tiled_paths_agree(handle):
             assert rel_err(out["mu"][i], mu) < 1e-9
 
 
-@pytest.mark.parametrize("variant,n", [(1, 200), (2, 200), (2, 64), (2, 512), (1, 700)])
+@pytest.mark.parametrize("variant,n", [(1, 200), (2, 200), (2, 64), (2, 512), (1, 700), (3, 200), (3, 64), (3, 512),
+                                       (3, 700), (3, 1000), (0, 512)])
 def test_predict_large_batch_matches_oracle(handle, variant, n):
-    """Both fused predictors (shared-memory psi tile / register-resident v) against the oracle."""
+    """The fused predictors (shared-memory psi tile / register-resident v) and the split pipeline (psi rows kernel +
+    TMA-fed DMMA kernel, the default for large query sets) against the oracle."""
     handle.set_predict_variant(variant)
     try:
         _predict_large_batch(handle, n)
@@ -272,6 +274,45 @@ def _predict_large_batch(handle, n):
     assert np.all(np.abs(got["ei"] - ref["ei"]) <= 1e-9 * sig + 0.5 * ds + 1e-9 * np.abs(ref["ei"]))
     only = handle.predict_batch(Xq, theta, p, out4[1], out4[2], want=("yhat",))
     assert np.array_equal(only["yhat"], got["yhat"]) and only["s"] is None
+
+
+@pytest.mark.parametrize("n,k,special", [(300, 5, False), (300, 5, True), (520, 10, False), (130, 1, False)])
+def test_predict_split_pipeline_general_k(handle, n, k, special):
+    """Split pipeline for k outside the compile-time cases, with exponents that are exactly 1 / 2 (exact d, d*d as
+    np.power) and outside the table-driven range, against the oracle; ragged m, yhat-only and s-only requests."""
+    X = onp.rlh(n, k, 21)
+    y = onp.f_squared(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    rng = np.random.default_rng(22)
+    theta = 10.0 ** rng.uniform(-1.5, 0.5, k)
+    p = rng.uniform(1.2, 1.95, k)
+    if special:
+        p[0], p[1], p[2] = 2.0, 1.0, 0.2  # 0.2: outside the table-driven range [0.25, 3]
+    out4, info = handle.fit(theta, p)
+    assert info == 0
+    m = 4097
+    Xq = rng.uniform(0, 1, (m, k))
+    Xq[:50] = Xn[:50]
+    y_min = float(np.min(yn))
+    ref = onp.predict_batch_fast(Xn, yn, theta, p, onp.EPS_DIAG, Xq, y_min=y_min)
+    cond = np.linalg.cond(onp.psi_fast(Xn, theta, p))
+    handle.set_predict_variant(3)
+    try:
+        got = handle.predict_batch(Xq, theta, p, out4[1], out4[2], y_min=y_min)
+        only_y = handle.predict_batch(Xq, theta, p, out4[1], out4[2], want=("yhat",))
+        only_s = handle.predict_batch(Xq, theta, p, out4[1], out4[2], want=("s",))
+    finally:
+        handle.set_predict_variant(0)
+    ytol = max(1e-9, 50.0 * cond * 2.2e-16)
+    vtol = out4[2] * max(1e-12, 100.0 * cond * 2.2e-16)
+    assert np.max(np.abs(got["yhat"] - ref["yhat"])) < ytol, cond
+    assert np.max(np.abs(got["s"] ** 2 - ref["s"] ** 2)) < vtol, cond
+    ds = np.abs(got["s"] - ref["s"])
+    sig = np.sqrt(out4[2])
+    assert np.all(np.abs(got["ei"] - ref["ei"]) <= 1e-9 * sig + 0.5 * ds + 1e-9 * np.abs(ref["ei"]))
+    assert np.array_equal(only_y["yhat"], got["yhat"]) and only_y["s"] is None
+    assert np.array_equal(only_s["s"], got["s"])
 
 
 def test_device_pow_and_exp_accuracy(handle):
@@ -358,9 +399,19 @@ def test_regression_fit_predict_large_n_matches_oracle(handle, n, k):
     assert np.all(np.abs(got["ei"] - ref["ei"]) <= 1e-9 * sig + 0.5 * ds + 1e-9 * np.abs(ref["ei"]))
     # more tiles than CTAs of the persistent grid: every tile must come out the same as in the small call
     big = np.tile(Xq, (40, 1))
-    got2 = handle.predict_batch(big, theta, p, out4[1], out4[2], y_min=y_min)
+    handle.set_predict_variant(1)
+    try:
+        got2 = handle.predict_batch(big, theta, p, out4[1], out4[2], y_min=y_min)
+    finally:
+        handle.set_predict_variant(0)
     assert np.array_equal(got2["s"].reshape(40, m), np.tile(got["s"], (40, 1)))
     assert np.array_equal(got2["yhat"].reshape(40, m), np.tile(got["yhat"], (40, 1)))
+    # the same 13320 queries through the split pipeline (default for m >= 4096): its own summation order
+    got3 = handle.predict_batch(big, theta, p, out4[1], out4[2], y_min=y_min)
+    assert np.max(np.abs(got3["yhat"][:m] - ref["yhat"])) < ytol
+    assert np.max(np.abs(got3["s"][:m] ** 2 - ref["s"] ** 2)) < vtol
+    assert np.array_equal(got3["s"].reshape(40, m), np.tile(got3["s"][:m], (40, 1)))
+    assert np.array_equal(got3["yhat"].reshape(40, m), np.tile(got3["yhat"][:m], (40, 1)))
 
 
 def test_predict_device_and_host_paths_agree(handle):
