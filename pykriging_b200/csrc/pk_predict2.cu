@@ -34,28 +34,60 @@ __device__ __forceinline__ double expected_improvement2(double yhat, double S, d
 }
 
 // ---- kernel A: psi rows + yhat -----------------------------------------------------------------------
+// ISSUE bound like psi_pop_kernel (an FP64 instruction holds a scheduler's dispatch port for two cycles, anything
+// else for one: profiles/ncu_psi_rows_r01_a.txt, 2 x 79 + 132 = 290 cycles per warp and psi value at k = 2), so
+// what counts is the instruction count:
+//   * log2_split_rows: no int -> double conversions (the exponent and the interval centre are assembled from
+//     bit patterns), no float round trip of the low part, no special case for d = 0 (E = -1023 falls out of the
+//     bit fields and the clamp at -340 does the rest);
+//   * MEMOISED DIMENSIONS: a warp owns a contiguous run of query points and keeps theta_d |X_rd - xq_d|^p_d of the
+//     leading dimensions of its previous query in shared memory.  When the next query has the same leading
+//     coordinates -- every row-major grid (plot / snapshot / the 4096 x 4096 EI grid of config C5:
+//     krige.py:531-537, 699-708) -- those terms are read back instead of recomputed: bit-identical by
+//     construction, and one pow per (query, sample) instead of k.
 constexpr int PA_THREADS = 768;
 constexpr int PA_WARPS = PA_THREADS / 32;
-constexpr int PA_XT_MAX = 12288;  // staged (transposed) sample coordinates: k * np doubles <= 96 KB
+constexpr int PA_XT_MAX = 12288;   // staged (transposed) sample coordinates: k * np doubles <= 96 KB
+constexpr int PA_SMALL_MAX = 6 * 0x8000 - 0x400;  // bytes in front of the 2^x table that still leave room for it
 
-// bytes in front of the 32 KB-aligned 2^x table: log2 tables + hyper-parameters + per-dimension mode + X^T
-__host__ __device__ inline unsigned pa_small_bytes(int xt_doubles) {
-    return (unsigned)(sizeof(double) * (3 * 64 * 16 + 2 * PK_MAX_K + xt_doubles) + sizeof(int) * PK_MAX_K);
+// bytes in front of the 32 KB-aligned 2^x table: log2 tables + hyper-parameters + per-dimension mode + X^T + memo
+__host__ __device__ inline unsigned pa_small_bytes(int xt_doubles, int memo_doubles) {
+    return (unsigned)(sizeof(double) * (3 * 64 * 16 + 2 * PK_MAX_K + xt_doubles + memo_doubles) + sizeof(int) * PK_MAX_K);
+}
+
+// log2 d = lh + ll (unevaluated sum, same tables and series as log2_split), lh clamped to [-340, 340]
+__device__ __forceinline__ void log2_split_rows(double d, const double* __restrict__ ltab, int bank, double& lh_out,
+                                                double& ll_out) {
+    const int hi = __double2hiint(d);
+    const int j = (hi >> 14) & 63;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(d));
+    const double c = __hiloint2double(0x3ff00000 | ((2 * j + 1) << 13), 0);  // 1 + (2j+1)/128
+    const double* e = ltab + j * 16 + bank;
+    const double z = (m - c) * e[0];
+    double q = c_log2p1[8];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) q = fma(q, z, c_log2p1[i]);
+    const double t = fma(q, z, e[2 * 1024]);
+    // biased exponent as a double: 2^52 + b has b in its low word
+    const double Ed = __hiloint2double(0x43300000, (hi >> 20) & 0x7ff) - 4503599627371519.0;  // - (2^52 + 1023)
+    const double lh = Ed + e[1024];              // exact
+    const double Ls = lh + t;
+    const double bb = Ls - lh;                   // TwoSum: (lh + t) = Ls + r exactly
+    ll_out = (lh - (Ls - bb)) + (t - bb);
+    lh_out = fmin(fmax(Ls, -L2_CLAMP), L2_CLAMP);
 }
 
 // theta_d |d|^p_d for one dimension.  mode: 0 = table-driven 2^(p log2 d) (p in [0.25, 3], not 1 or 2),
 // 1 = p == 1 (exact d), 2 = p == 2 (exact d*d, as np.power), 3 = any other exponent (range-checked path)
+__device__ __forceinline__ double pa_term_lean(double dd, double th, double p, const double* ltab, int bank,
+                                               unsigned tab_saddr) {
+    double lh, ll;
+    log2_split_rows(dd, ltab, bank, lh, ll);
+    return th * exp2_lean4k(p, lh, ll, tab_saddr);
+}
 __device__ __forceinline__ double pa_term(double dd, double th, double p, int mode, const double* ltab, int bank,
                                           unsigned tab_saddr) {
-    if (mode == 0) {
-        double lh;
-        float lf;
-        log2_split_smem(dd, ltab, bank, lh, lf);
-        double ll = (double)lf;
-        if (!(lh > -L2_CLAMP)) { lh = -L2_CLAMP; ll = 0.0; }
-        if (lh > L2_CLAMP) { lh = L2_CLAMP; ll = 0.0; }
-        return th * exp2_lean4k(p, lh, ll, tab_saddr);
-    }
+    if (mode == 0) return pa_term_lean(dd, th, p, ltab, bank, tab_saddr);
     if (mode == 2) return th * (dd * dd);
     if (mode == 1) return th * dd;
     double l0;
@@ -69,7 +101,7 @@ __device__ __forceinline__ double pa_term(double dd, double th, double p, int mo
 template <int KK>
 __global__ void __launch_bounds__(PA_THREADS, 1)
 psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, const double* __restrict__ Xq,
-                const double* __restrict__ hp, const double* __restrict__ w, double mu, int xt_staged,
+                const double* __restrict__ hp, const double* __restrict__ w, double mu, int xt_staged, int memo_dims,
                 double* __restrict__ psi_out, double* __restrict__ yhat_out) {
     extern __shared__ __align__(16) double pa_smem[];
     double* ltab = pa_smem;                                   // 3 x 64 x 16
@@ -77,9 +109,11 @@ psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, 
     double* p_s = th_s + PK_MAX_K;                            // PK_MAX_K
     int* mode_s = reinterpret_cast<int*>(p_s + PK_MAX_K);     // PK_MAX_K
     double* Xt = reinterpret_cast<double*>(mode_s + PK_MAX_K);  // k x np (transposed: conflict-free per-lane reads)
+    double* memo = Xt + (xt_staged ? k * np : 0);             // PA_WARPS x memo_dims x np
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(pa_smem);
-    const unsigned tab_saddr = (smem_base + pa_small_bytes(xt_staged ? k * np : 0) + 0x7fffu) & ~0x7fffu;
+    const unsigned tab_saddr =
+        (smem_base + pa_small_bytes(xt_staged ? k * np : 0, PA_WARPS * memo_dims * np) + 0x7fffu) & ~0x7fffu;
     double* tab4k = pa_smem + (tab_saddr - smem_base) / sizeof(double);
     fill_exp2_4096(tab4k, tid, PA_THREADS);
     fill_log2_tables(ltab, tid, PA_THREADS);
@@ -108,34 +142,31 @@ psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, 
     bool lean = true;  // every exponent takes the table-driven path: straight-line code, two chains interleaved
     for (int d = 0; d < k; ++d) lean &= (mode_s[d] == 0);
     const int nit = np / 32;  // even: np is a multiple of 64
-    for (int64_t q = (int64_t)blockIdx.x * PA_WARPS + warp; q < mc; q += (int64_t)gridDim.x * PA_WARPS) {
+    // this warp's contiguous run of queries
+    const int64_t nwarps = (int64_t)gridDim.x * PA_WARPS;
+    const int64_t per = (mc + nwarps - 1) / nwarps;
+    const int64_t qa = ((int64_t)blockIdx.x * PA_WARPS + warp) * per;
+    const int64_t qb = (qa + per < mc) ? qa + per : mc;
+    double* mw = memo + (size_t)warp * memo_dims * np;
+    double mx[KK > 0 ? KK : 1];  // leading coordinates the memo was built for
+#pragma unroll
+    for (int d = 0; d < (KK > 0 ? KK : 1); ++d) mx[d] = CUDART_NAN;
+    for (int64_t q = qa; q < qb; ++q) {
         double xq_r[KK > 0 ? KK : 1];
+        bool hit = (KK > 0) && lean && memo_dims > 0;
         if constexpr (KK > 0) {
 #pragma unroll
-            for (int d = 0; d < KK; ++d) xq_r[d] = __ldg(Xq + q * KK + d);
-        }
-        const double* xqg = Xq + q * k;
-        // S(r) = sum_d theta_d |X_rd - xq_d|^p_d in NumPy's summation order; r < n (clamped by the caller)
-        auto S_lean = [&](int r) {
-            if constexpr (KK > 0) {
-                double term[KK > 0 ? KK : 1];
-#pragma unroll
-                for (int d = 0; d < KK; ++d) {
-                    const double xr = xt_staged ? Xt[d * np + r] : __ldg(X + (size_t)r * KK + d);
-                    term[d] = pa_term(fabs(xr - xq_r[d]), th_r[d], p_r[d], 0, ltab, bank, tab_saddr);
-                }
-                return sum_numpy_order(KK, [&](int d) { return term[d]; });
-            } else {
-                return sum_numpy_order(k, [&](int d) {
-                    const double xr = xt_staged ? Xt[d * np + r] : __ldg(X + (size_t)r * k + d);
-                    return pa_term(fabs(xr - __ldg(xqg + d)), th_s[d], p_s[d], 0, ltab, bank, tab_saddr);
-                });
+            for (int d = 0; d < KK; ++d) {
+                xq_r[d] = __ldg(Xq + q * KK + d);
+                if (d < memo_dims) hit &= (xq_r[d] == mx[d]);
             }
-        };
+        }
+        const bool use_memo = (KK > 0) && lean && memo_dims > 0;
+        const double* xqg = Xq + q * k;
         auto S_any = [&](int r) {
             return sum_numpy_order(k, [&](int d) {
                 const double xr = xt_staged ? Xt[d * np + r] : __ldg(X + (size_t)r * k + d);
-                return pa_term(fabs(xr - __ldg(xqg + d)), th_s[d], p_s[d], mode_s[d], ltab, bank, tab_saddr);
+                return pa_term(fabs(xr - __ldg(xqg + d)), th_s[d], p_s[d], lean ? 0 : mode_s[d], ltab, bank, tab_saddr);
             });
         };
         double ys0 = 0.0, ys1 = 0.0;
@@ -144,9 +175,42 @@ psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, 
             const int r0 = it * 32 + lane, r1 = r0 + 32;
             const int c0 = min(r0, n - 1), c1 = min(r1, n - 1);  // padding rows: computed on a valid sample, then zeroed
             double S0, S1;
-            if (lean) {
-                S0 = S_lean(c0);
-                S1 = S_lean(c1);
+            if constexpr (KK > 0) {
+                if (lean) {
+                    // S(r) = sum_d theta_d |X_rd - xq_d|^p_d in NumPy's summation order (plain left to right, KK < 8)
+                    double t0[KK], t1[KK];
+                    auto term = [&](int d, int r) {
+                        const double xr = xt_staged ? Xt[d * np + r] : __ldg(X + (size_t)r * KK + d);
+                        return pa_term_lean(fabs(xr - xq_r[d]), th_r[d], p_r[d], ltab, bank, tab_saddr);
+                    };
+                    if (hit) {
+#pragma unroll
+                        for (int d = 0; d < KK; ++d) {
+                            if (d < memo_dims) {
+                                t0[d] = mw[d * np + r0];
+                                t1[d] = mw[d * np + r1];
+                            } else {
+                                t0[d] = term(d, c0);
+                                t1[d] = term(d, c1);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < KK; ++d) {
+                            t0[d] = term(d, c0);
+                            t1[d] = term(d, c1);
+                            if (use_memo && d < memo_dims) {
+                                mw[d * np + r0] = t0[d];
+                                mw[d * np + r1] = t1[d];
+                            }
+                        }
+                    }
+                    S0 = sum_numpy_order(KK, [&](int d) { return t0[d]; });
+                    S1 = sum_numpy_order(KK, [&](int d) { return t1[d]; });
+                } else {
+                    S0 = S_any(c0);
+                    S1 = S_any(c1);
+                }
             } else {
                 S0 = S_any(c0);
                 S1 = S_any(c1);
@@ -159,6 +223,13 @@ psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, 
             if (prow) {
                 prow[r0] = v0;
                 prow[r1] = v1;
+            }
+        }
+        if constexpr (KK > 0) {
+            if (use_memo && !hit) {
+#pragma unroll
+                for (int d = 0; d < KK; ++d) mx[d] = xq_r[d];
+                __syncwarp();
             }
         }
         const double ys = warp_sum(ys0 + ys1);
@@ -386,9 +457,18 @@ static cudaError_t launch_psi_rows(pk_handle* h, int64_t mc, const double* Xq, c
                                    double* psi_out, double* yhat_out) {
     const int k = h->k, np = h->fit_np;
     const int xt = (k * np <= PA_XT_MAX) ? 1 : 0;
+    // memoised leading dimensions (compile-time k only): as many of the first k - 1 as fit beside the tables
+    int memo_dims = 0;
+    if (KK > 1) {
+        const int room = PA_SMALL_MAX - (int)pa_small_bytes(xt ? k * np : 0, 0);
+        const int per_dim = PA_WARPS * np * (int)sizeof(double);
+        memo_dims = (room > 0) ? room / per_dim : 0;
+        if (memo_dims > KK - 1) memo_dims = KK - 1;
+    }
     // the dynamic window starts 1 KB into the CTA's shared memory: leave room for the 32 KB-aligned table wherever
     // the base lies (same sizing rule as psi_pop_kernel)
-    const size_t smem = ((pa_small_bytes(xt ? k * np : 0) + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000;
+    const size_t smem =
+        ((pa_small_bytes(xt ? k * np : 0, PA_WARPS * memo_dims * np) + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(psi_rows_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -397,8 +477,8 @@ static cudaError_t launch_psi_rows(pk_handle* h, int64_t mc, const double* Xq, c
     }
     const int64_t want = (mc + PA_WARPS - 1) / PA_WARPS;
     const int grid = (int)((want < (int64_t)h->sm_count) ? want : (int64_t)h->sm_count);
-    psi_rows_kernel<KK><<<grid, PA_THREADS, smem, h->stream>>>(h->n, np, k, mc, h->dX, Xq, hp, h->d_w, mu, xt, psi_out,
-                                                               yhat_out);
+    psi_rows_kernel<KK><<<grid, PA_THREADS, smem, h->stream>>>(h->n, np, k, mc, h->dX, Xq, hp, h->d_w, mu, xt, memo_dims,
+                                                               psi_out, yhat_out);
     h->launches++;
     return cudaGetLastError();
 }

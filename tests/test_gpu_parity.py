@@ -315,6 +315,35 @@ def test_predict_split_pipeline_general_k(handle, n, k, special):
     assert np.array_equal(only_s["s"], got["s"])
 
 
+@pytest.mark.parametrize("k,side", [(2, 70), (3, 17)])
+def test_predict_grid_memoisation_is_exact(handle, k, side):
+    """Row-major grids (plot / snapshot / the EI grid of config C5) reuse the leading-dimension terms of the previous
+    query point in the psi rows kernel.  The same points in shuffled order (no reuse) must give bit-identical
+    results, and both must match the oracle."""
+    n = 200
+    X = onp.rlh(n, k, 31)
+    y = onp.f_squared(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    theta = np.full(k, 3.0)
+    p = np.full(k, 1.7)
+    out4, info = handle.fit(theta, p)
+    assert info == 0
+    axes = [np.linspace(0, 1, side)] * k
+    grid = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, k)
+    assert len(grid) >= 4096
+    perm = np.random.default_rng(1).permutation(len(grid))
+    y_min = float(np.min(yn))
+    a = handle.predict_batch(grid, theta, p, out4[1], out4[2], y_min=y_min)
+    b = handle.predict_batch(np.ascontiguousarray(grid[perm]), theta, p, out4[1], out4[2], y_min=y_min)
+    for name in ("yhat", "s", "ei"):
+        assert np.array_equal(a[name][perm], b[name]), name
+    ref = onp.predict_batch_fast(Xn, yn, theta, p, onp.EPS_DIAG, grid, y_min=y_min)
+    cond = np.linalg.cond(onp.psi_fast(Xn, theta, p))
+    assert np.max(np.abs(a["yhat"] - ref["yhat"])) < max(1e-9, 50.0 * cond * 2.2e-16)
+    assert np.max(np.abs(a["s"] ** 2 - ref["s"] ** 2)) < out4[2] * max(1e-12, 100.0 * cond * 2.2e-16)
+
+
 def test_device_pow_and_exp_accuracy(handle):
     """The Psi kernel replaces np.power / np.exp (glibc, < 1 ulp) with a log2-split + table-driven 2^x and
     a table-driven e^-S.  Bound their error in ulps against an 80-bit long-double reference."""
