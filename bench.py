@@ -340,6 +340,10 @@ def run_ours(args, rank, world, local_rank):
         pred = run_predictions(torch, dev, local_rank, rank, world, dist)
     traffic = load_traffic()
     if rank == 0:
+        if pred is not None:
+            pred["kernels"] = ("psi_rows_kernel<2> (psi rows + yhat, FP64 ALU, HBM scratch) + tn::trinorm_kernel "
+                               "(|L^-1 psi|^2 on the DMMA pipe, TMA-fed, + s + EI)")
+            pred["frac_of_dmma_peak"] = pred["tflops_algorithmic"] / (peak["dmma_tflops"] * world)  # whole-job TFLOP/s over N GPUs
         n = N_SAMPLES
         flops_chol = (n ** 3) / 3.0 * C * args.steps
         chol_tf = flops_chol / (phases["cholesky"] * 1e-3) * 1e-12 if phases["cholesky"] > 0 else None

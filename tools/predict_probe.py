@@ -35,7 +35,7 @@ if os.environ.get("PK_PROBE_TIME"):
     h.synchronize()
     import time
     best = 1e9
-    for _ in range(3):
+    for _ in range(int(os.environ.get("PK_PROBE_REPS", "3"))):
         t0 = time.perf_counter()
         h.predict_batch_raw(*args)
         h.synchronize()
