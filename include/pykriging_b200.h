@@ -144,6 +144,13 @@ int pk_set_cholesky_variant(pk_handle *h, int variant);
  *     TMA-fed DMMA kernel (any n; what 0 selects for 4096 query points or more). */
 int pk_set_predict_variant(pk_handle *h, int variant);
 
+/* Multi-GPU sharding (the reference has one Python loop over the whole population,
+ * krige.py:436-451, and one over the query points, krige.py:243-257): tells the handle that its next
+ * pk_nll_batch / pk_predict_batch calls evaluate a SLICE of a population of `population` candidates / of a query
+ * set of `query_points` points.  Automatic kernel selection then uses these sizes instead of the slice's, so every
+ * shard computes bit for bit what the unsharded call computes.  0 = no hint. */
+int pk_set_shard_hint(pk_handle *h, int64_t population, int64_t query_points);
+
 /* pk_nll_batch pipelining experiment (the candidate loop of krige.py:429-452 has no such notion: it is
  * strictly sequential).  0 (default): Psi -> Cholesky -> epilogue per resident chunk on one stream.
  * 1: a population larger than the number of resident Cholesky CTAs is split in two parts and the Psi

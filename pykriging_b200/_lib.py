@@ -21,6 +21,7 @@ EXPORTS = [
     "pk_predict_batch", "pk_append_point", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
     "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
     "pk_fp64_peak", "pk_debug_math", "pk_set_cholesky_variant", "pk_set_predict_variant", "pk_set_overlap",
+    "pk_set_shard_hint",
 ]
 
 _lib = None
@@ -77,6 +78,8 @@ def load():
     lib.pk_set_cholesky_variant.restype = ctypes.c_int
     lib.pk_set_predict_variant.argtypes = [hp, ctypes.c_int]
     lib.pk_set_predict_variant.restype = ctypes.c_int
+    lib.pk_set_shard_hint.argtypes = [hp, ctypes.c_int64, ctypes.c_int64]
+    lib.pk_set_shard_hint.restype = ctypes.c_int
     lib.pk_set_overlap.argtypes = [hp, ctypes.c_int]
     lib.pk_set_overlap.restype = ctypes.c_int
     for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
@@ -265,8 +268,13 @@ class Handle(object):
         self._check(self.lib.pk_set_overlap(self._h, int(bool(enabled))), "pk_set_overlap")
 
     def set_predict_variant(self, variant):
-        """0 auto, 1 shared-memory psi tile kernel, 2 register-resident kernel (n <= 512)."""
+        """0 auto, 1 shared-memory psi tile kernel, 2 register-resident kernel (n <= 512), 3 split pipeline."""
         self._check(self.lib.pk_set_predict_variant(self._h, int(variant)), "pk_set_predict_variant")
+
+    def set_shard_hint(self, population=0, query_points=0):
+        """The next calls evaluate a slice of a population / query set of these sizes (0 = no hint): kernel
+        selection follows the whole, so a shard reproduces the unsharded result bit for bit."""
+        self._check(self.lib.pk_set_shard_hint(self._h, int(population), int(query_points)), "pk_set_shard_hint")
 
     def set_workspace_limit(self, nbytes):
         self._check(self.lib.pk_set_workspace_limit(self._h, int(nbytes)), "pk_set_workspace_limit")

@@ -194,6 +194,13 @@ int pk_set_cholesky_variant(pk_handle* h, int variant) {
     return 0;
 }
 
+int pk_set_shard_hint(pk_handle* h, int64_t population, int64_t query_points) {
+    if (!h || population < 0 || query_points < 0) return 1;
+    h->hint_C = population;
+    h->hint_m = query_points;
+    return 0;
+}
+
 int pk_set_overlap(pk_handle* h, int enabled) {
     if (!h) return 1;
     h->overlap = enabled ? 1 : 0;

@@ -24,6 +24,9 @@ struct pk_handle {
     double pivot_tol = 2.0 * PK_EPS_DIAG;  // relative pivot threshold, 2 ulps (see pk_set_pivot_tolerance)
     int chol_variant = 0;                  // 0 auto, 1 one launch per block column, 2 persistent CTA per candidate
     int predict_variant = 0;               // 0 auto, 1 shared-memory psi tile kernel, 2 register-resident (n <= 512), 3 split (psi rows kernel + TMA-fed DMMA kernel)
+    // this handle's calls are slices of a population / query set of these sizes (pk_set_shard_hint; 0 = no hint):
+    // automatic kernel selection uses them, so a shard computes bit for bit what the unsharded call would
+    int64_t hint_C = 0, hint_m = 0;
     unsigned int* d_queue = nullptr;       // candidate queues of the persistent Cholesky kernel (PK_QUEUE_SLOTS counters)
     int queue_slot = 0;                    // counter the next launch_cholesky_cta uses
     // Psi construction of the NEXT part of a population overlaps the Cholesky of the current one: the Psi

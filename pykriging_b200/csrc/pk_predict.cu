@@ -875,7 +875,8 @@ cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const doub
                            double* ei) {
     const int np = h->fit_np;
     // large query sets: psi rows + yhat in one kernel, the triangular DMMA contraction + s + EI in a second one
-    if (h->predict_variant == 3 || (h->predict_variant == 0 && m >= 4096))
+    const int64_t meff = (h->hint_m > m) ? h->hint_m : m;  // the query set this call is a slice of
+    if (h->predict_variant == 3 || (h->predict_variant == 0 && meff >= 4096))
         return launch_predict_split(h, m, Xq, hp, mu, sigma2, y_min, ei_weight, var_extra, yhat, sout, ei);
     if (np <= 512 && h->predict_variant != 1) {
         switch ((np / PK_TILE + 1) / 2) {  // 8-column blocks per warp: np/8 blocks over 16 warps

@@ -581,7 +581,8 @@ cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, doub
 // handful of candidates) the per-block-column launches expose the parallelism inside a matrix.
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     int v = h->chol_variant;
-    if (v == 0) v = (C >= (2 * h->sm_count) / 3) ? 2 : 1;
+    const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;  // the population this call is a slice of
+    if (v == 0) v = (Ceff >= (2 * h->sm_count) / 3) ? 2 : 1;
     if (s.with_inverse) v = 1;  // pk_fit (one matrix + L^-1 rows): the per-block-column kernels
     return (v == 2) ? launch_cholesky_cta(h, s, C, ws, info) : launch_cholesky_steps(h, s, C, ws, info);
 }

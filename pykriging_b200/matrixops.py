@@ -71,7 +71,11 @@ class matrixops(object):
             o = h.nll_batch(theta[lo:hi], p[lo:hi], None if lam is None else lam[lo:hi], mode)
             return np.stack([o["nll"], o["mu"], o["sigma2"], o["lndet"], o["info"].astype(np.float64)], axis=1)
 
-        rows = sharding.sharded_rows(theta.shape[0], eval_slice, shard[0])
+        h.set_shard_hint(population=theta.shape[0])
+        try:
+            rows = sharding.sharded_rows(theta.shape[0], eval_slice, shard[0])
+        finally:
+            h.set_shard_hint()
         return {"nll": rows[:, 0].copy(), "mu": rows[:, 1].copy(), "sigma2": rows[:, 2].copy(),
                 "lndet": rows[:, 3].copy(), "info": rows[:, 4].astype(np.int32)}
 
@@ -230,7 +234,11 @@ class matrixops(object):
                                 var_extra=var_extra, want=want)
             return np.stack([o[nm] for nm in names], axis=1)
 
-        rows = sharding.sharded_rows(Xq.shape[0], eval_slice, shard[0])
+        h.set_shard_hint(query_points=Xq.shape[0])
+        try:
+            rows = sharding.sharded_rows(Xq.shape[0], eval_slice, shard[0])
+        finally:
+            h.set_shard_hint()
         out = {"yhat": None, "s": None, "ei": None}
         for c, nm in enumerate(names):
             out[nm] = rows[:, c].copy()

@@ -344,6 +344,42 @@ def test_predict_grid_memoisation_is_exact(handle, k, side):
     assert np.max(np.abs(a["s"] ** 2 - ref["s"] ** 2)) < out4[2] * max(1e-12, 100.0 * cond * 2.2e-16)
 
 
+def test_shard_hint_makes_slices_bit_identical(handle):
+    """Multi-GPU sharding evaluates slices of a population / query set on different GPUs.  With
+    pk_set_shard_hint the automatic kernel choice follows the WHOLE, so the slices reproduce the unsharded
+    call bit for bit -- 257 candidates select the persistent-CTA Cholesky, a bare slice of 33 would not;
+    5000 query points select the split predictor, a bare slice of 625 would not."""
+    rng = np.random.default_rng(3)
+    n, k = 300, 4
+    X = rng.uniform(0, 1, (n, k))
+    y = np.sum((X - 0.4) ** 2, axis=1)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    C = 257
+    theta = rng.uniform(1e-5, 100, (C, k))
+    p = rng.uniform(1, 2, (C, k))
+    full = handle.nll_batch(theta, p)
+    handle.set_shard_hint(population=C)
+    try:
+        parts = [handle.nll_batch(theta[lo:lo + 33], p[lo:lo + 33]) for lo in range(0, C, 33)]
+    finally:
+        handle.set_shard_hint()
+    for name in ("nll", "mu", "sigma2", "lndet"):
+        assert np.array_equal(np.concatenate([q[name] for q in parts]), full[name], equal_nan=True), name
+    out4, info = handle.fit(theta[0], p[0])
+    assert info == 0
+    Xq = rng.uniform(0, 1, (5000, k))
+    whole = handle.predict_batch(Xq, theta[0], p[0], out4[1], out4[2], y_min=0.0)
+    handle.set_shard_hint(query_points=len(Xq))
+    try:
+        parts = [handle.predict_batch(Xq[lo:lo + 625], theta[0], p[0], out4[1], out4[2], y_min=0.0)
+                 for lo in range(0, len(Xq), 625)]
+    finally:
+        handle.set_shard_hint()
+    for name in ("yhat", "s", "ei"):
+        assert np.array_equal(np.concatenate([q[name] for q in parts]), whole[name]), name
+
+
 def test_device_pow_and_exp_accuracy(handle):
     """The Psi kernel replaces np.power / np.exp (glibc, < 1 ulp) with a log2-split + table-driven 2^x and
     a table-driven e^-S.  Bound their error in ulps against an 80-bit long-double reference."""
