@@ -265,8 +265,8 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
 // stage.  Stage rows are 128 bytes with the 32-byte atoms XOR-swizzled by the row (SWIZZLE_128B_ATOM_32B):
 // lane (fr, fc) reads column 4i + fc of a row congruent to fr mod 8 at soff[i] = ((i ^ (fr & 3)) << 2) + fc.
 template <int LO, int HI>
-__device__ __forceinline__ void consume(double (&acc)[4][4][2], const double* a_s, const double* b_s,
-                                        const int (&soff)[4]) {
+__device__ __forceinline__ void consume(double (&acc)[4][4][2], const double* a_s, const double* b_even,
+                                        const double* b_odd, const int (&soff)[4]) {
     // (skipping the k-steps of the first live block that lie right of the diagonal as well -- a warp-uniform branch
     // per k-step, 3 % fewer DMMAs -- measured 3.5 % SLOWER: the branch splits the DMMA stream of a k-step)
 #pragma unroll
@@ -275,7 +275,7 @@ __device__ __forceinline__ void consume(double (&acc)[4][4][2], const double* a_
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[mi * 8 * KC + soff[i]];
 #pragma unroll
-        for (int ni = LO; ni < HI; ++ni) b[ni] = b_s[ni * 64 * KC + soff[i]];
+        for (int ni = LO; ni < HI; ++ni) b[ni] = ((ni & 1) ? b_odd : b_even)[ni * 64 * KC + soff[i]];
 #pragma unroll
         for (int ni = LO; ni < HI; ++ni)
 #pragma unroll
@@ -365,23 +365,31 @@ trinorm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         mbar_wait(bars + ps, (g / STAGES) & 1u);
         const double* st = pipe + ps * STAGE_DOUBLES;
         const double* a_s = st + (wq * 32 + fr) * KC;
-        const double* b_s = st + A_STAGE + (cg * 8 + fr) * KC;
+        // this warp's 8-column blocks of the pass: columns c0 + 64 ni + 8 cg for even ni, c0 + 64 ni + 8 (7 - cg) for
+        // odd ni -- the triangle gives a block at column c about c / 16 live chunks, and mirroring every other block
+        // hands all warps the same number of DMMAs per pass (with cg everywhere, warp 7 did 20 % more than warp 0 and
+        // the others spun on the next stage's mbarrier: 11 % of the stall samples)
+        const double* b_even = st + A_STAGE + (cg * 8 + fr) * KC;
+        const double* b_odd = st + A_STAGE + ((7 - cg) * 8 + fr) * KC;
         const int c0 = cons.cb * CB;
-        // live column blocks of this warp: ni with c0 + 64 ni + 8 cg + 7 >= 16 kc (lower triangle) and < np
-        const int num = KC * cons.kc - c0 - 8 * cg - 7;
-        const int lo = (num <= 0) ? 0 : ((num + 63) >> 6);
+        // live column blocks: ni with (first column of the block) + 7 >= 16 kc (lower triangle) and < np; the block
+        // columns grow with ni, so the live ones are ni = lo .. hi - 1
+        const int edge = KC * cons.kc - c0 - 7;  // a block starting at relative column >= edge is live
+        int lo = 0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) lo += (64 * ni + 8 * ((ni & 1) ? 7 - cg : cg) < edge) ? 1 : 0;
         const int hi = min(4, (np - c0) >> 6);
         switch (lo * 4 + hi - 1) {
-            case 0: consume<0, 1>(acc, a_s, b_s, soff); break;
-            case 1: consume<0, 2>(acc, a_s, b_s, soff); break;
-            case 2: consume<0, 3>(acc, a_s, b_s, soff); break;
-            case 3: consume<0, 4>(acc, a_s, b_s, soff); break;
-            case 5: consume<1, 2>(acc, a_s, b_s, soff); break;
-            case 6: consume<1, 3>(acc, a_s, b_s, soff); break;
-            case 7: consume<1, 4>(acc, a_s, b_s, soff); break;
-            case 10: consume<2, 3>(acc, a_s, b_s, soff); break;
-            case 11: consume<2, 4>(acc, a_s, b_s, soff); break;
-            case 15: consume<3, 4>(acc, a_s, b_s, soff); break;
+            case 0: consume<0, 1>(acc, a_s, b_even, b_odd, soff); break;
+            case 1: consume<0, 2>(acc, a_s, b_even, b_odd, soff); break;
+            case 2: consume<0, 3>(acc, a_s, b_even, b_odd, soff); break;
+            case 3: consume<0, 4>(acc, a_s, b_even, b_odd, soff); break;
+            case 5: consume<1, 2>(acc, a_s, b_even, b_odd, soff); break;
+            case 6: consume<1, 3>(acc, a_s, b_even, b_odd, soff); break;
+            case 7: consume<1, 4>(acc, a_s, b_even, b_odd, soff); break;
+            case 10: consume<2, 3>(acc, a_s, b_even, b_odd, soff); break;
+            case 11: consume<2, 4>(acc, a_s, b_even, b_odd, soff); break;
+            case 15: consume<3, 4>(acc, a_s, b_even, b_odd, soff); break;
             default: break;
         }
         __syncwarp();
