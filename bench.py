@@ -190,6 +190,9 @@ class ClockSampler(threading.Thread):
 
 
 # ---- reference arm / CPU baseline (the only place bench.py touches oracle/) -------------------------------
+CPU_BASELINE_SAMPLE = 48  # candidates timed for cpu_baseline: ~10 s at ~4 evals/s on the box's 16 host cores
+
+
 def cpu_reference_evals(n_cands, seeds):
     """Times the reference's CPU algorithm (NumPy restatement in reference order: np.power over the
     (n,n,k) distance tensor, dpotrf, six dgesv solves -- matrixops.py:24-56) on `n_cands` candidates of
@@ -392,12 +395,12 @@ def run_ours(args, rank, world, local_rank):
             "fp64_peak": peak, "failed_factorisations_last_step": fails,
         }
         if world == 1 and not args.no_cpu_baseline:
-            res = cpu_reference_evals(6, [0])
+            res = cpu_reference_evals(CPU_BASELINE_SAMPLE, [0])
             secs, ev = res[0]
             line["cpu_baseline"] = {"value": ev / secs, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "6 candidates of step 0 (evenly spaced over both families) through "
+                                    "sample": "%d candidates of step 0 (evenly spaced over both families) through "
                                               "the NumPy/OpenBLAS oracle port of matrixops.py:24-56, all host "
-                                              "threads"}
+                                              "threads (about 10 s of CPU work)" % CPU_BASELINE_SAMPLE}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -35,7 +35,7 @@ __device__ __forceinline__ double expected_improvement2(double yhat, double S, d
 
 // ---- kernel A: psi rows + yhat -----------------------------------------------------------------------
 // ISSUE bound like psi_pop_kernel (an FP64 instruction holds a scheduler's dispatch port for two cycles, anything
-// else for one: profiles/ncu_psi_rows_r01_a.txt, 2 x 79 + 132 = 290 cycles per warp and psi value at k = 2), so
+// else for one: profiles/ncu_psi_rows_r01_s4.txt, 2 x 79 + 132 = 290 cycles per warp and psi value at k = 2), so
 // what counts is the instruction count:
 //   * log2_split_rows: no int -> double conversions (the exponent and the interval centre are assembled from
 //     bit patterns), no float round trip of the low part, no special case for d = 0 (E = -1023 falls out of the
