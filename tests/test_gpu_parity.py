@@ -380,6 +380,93 @@ def test_shard_hint_makes_slices_bit_identical(handle):
         assert np.array_equal(np.concatenate([q[name] for q in parts]), whole[name]), name
 
 
+def test_full_size_c3_population_properties(handle):
+    """BASELINE config C3 at full size (n = 1024, k = 10, population 1024 = 8.3 GiB of Psi matrices): the oracle
+    checks a sample of the candidates; the size-independent properties cover all of them -- a candidate's result
+    does not depend on its position in the population or on its neighbours (permutation: bit-identical), duplicates
+    give identical results, and the 4 scalars are consistent: NegLnLike == n/2 ln(SigmaSqr) + LnDetPsi/2
+    (matrixops.py:56)."""
+    n, k, C = 1024, 10, 1024
+    X = onp.rlh(n, k, 1234)
+    y = onp.f_stybtang_norm(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    cands = np.concatenate([onp.candidates_uniform(C // 2, k, 1), onp.candidates_loguniform(C // 2, k, 2)])
+    cands[7] = cands[900]  # duplicates, far apart
+    th, p = np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:])
+    out = handle.nll_batch(th, p)
+    ok = out["info"] == 0
+    assert ok.sum() > C // 2
+    assert np.all(np.isnan(out["nll"][~ok]))
+    for name in ("nll", "mu", "sigma2", "lndet"):
+        assert out[name][7] == out[name][900] or (np.isnan(out[name][7]) and np.isnan(out[name][900]))
+    ident = 0.5 * n * np.log(out["sigma2"][ok]) + 0.5 * out["lndet"][ok]
+    assert np.max(np.abs(ident - out["nll"][ok]) / np.maximum(1.0, np.abs(ident))) < 1e-13
+    perm = np.random.default_rng(5).permutation(C)
+    out2 = handle.nll_batch(np.ascontiguousarray(th[perm]), np.ascontiguousarray(p[perm]))
+    for name in ("nll", "mu", "sigma2", "lndet"):
+        assert np.array_equal(out2[name], out[name][perm], equal_nan=True), name
+    assert np.array_equal(out2["info"], out["info"][perm])
+    checked = 0
+    for i in (0, 255, 511, 512, 700, 1023):
+        Psi = onp.psi_fast(Xn, th[i], p[i])
+        nll, mu, s2, lndet, info = onp.neglikelihood_fast(Psi, yn)
+        if info != 0:
+            assert out["info"][i] > 0
+            continue
+        cond = np.linalg.cond(Psi)
+        if cond > 1e12:
+            continue
+        assert out["info"][i] == 0
+        tol = tol_for_cond(cond)
+        assert rel_err(out["nll"][i], nll) < tol, (i, cond)
+        assert rel_err(out["mu"][i], mu) < tol, (i, cond)
+        assert rel_err(out["sigma2"][i], s2) < tol, (i, cond)
+        checked += 1
+    assert checked >= 3
+
+
+def test_full_size_c5_grid_properties(handle):
+    """BASELINE config C5 at full size: yhat, s and EI over the 4096 x 4096 grid on a fitted n = 512 model (device
+    buffers, 16 777 216 points).  A random sample of 3000 grid points is checked against the oracle; every point is
+    covered by size-independent properties: s >= 0, EI >= -1e-12 (krige.py:212-217), the points that coincide with
+    nothing still interpolate inside the data range, and the same sample evaluated on its own (scattered points, no
+    memoised dimensions, other tiles) reproduces the grid's values bit for bit."""
+    torch = pytest.importorskip("torch")
+    X = onp.rlh(512, 2, 5)
+    y = onp.f_branin(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    theta, p = np.array([5.0, 5.0]), np.array([1.8, 1.8])
+    out4, info = handle.fit(theta, p)
+    assert info == 0
+    G = 4096
+    ax = torch.linspace(0.0, 1.0, G, dtype=torch.float64, device="cuda")
+    idx = torch.arange(G * G, device="cuda", dtype=torch.int64)
+    Xq = torch.stack([ax[idx // G], ax[idx % G]], dim=1).contiguous()
+    del idx
+    m = G * G
+    dout = torch.empty(3, m, dtype=torch.float64, device="cuda")
+    y_min = float(np.min(yn))
+    handle.predict_batch_raw(m, Xq, theta, p, out4[1], out4[2], y_min, -1.0, 0.0, dout[0], dout[1], dout[2])
+    handle.synchronize()
+    assert bool(torch.isfinite(dout).all())
+    assert float(dout[1].min()) >= 0.0 and float(dout[2].min()) >= -1e-12
+    sel = torch.from_numpy(np.sort(np.random.default_rng(9).choice(m, 6000, replace=False))).cuda()
+    pts = Xq[sel].contiguous()
+    sub = torch.empty(3, len(sel), dtype=torch.float64, device="cuda")
+    handle.predict_batch_raw(len(sel), pts, theta, p, out4[1], out4[2], y_min, -1.0, 0.0, sub[0], sub[1], sub[2])
+    handle.synchronize()
+    assert torch.equal(sub, dout[:, sel])
+    g = dout[:, sel[:3000]].cpu().numpy()
+    ref = onp.predict_batch_fast(Xn, yn, theta, p, onp.EPS_DIAG, pts[:3000].cpu().numpy(), y_min=y_min)
+    cond = np.linalg.cond(onp.psi_fast(Xn, theta, p))
+    assert np.max(np.abs(g[0] - ref["yhat"])) < max(1e-9, 50.0 * cond * 2.2e-16)
+    assert np.max(np.abs(g[1] ** 2 - ref["s"] ** 2)) < out4[2] * max(1e-12, 100.0 * cond * 2.2e-16)
+    ds = np.abs(g[1] - ref["s"])
+    assert np.all(np.abs(g[2] - ref["ei"]) <= 1e-9 * np.sqrt(out4[2]) + 0.5 * ds + 1e-9 * np.abs(ref["ei"]))
+
+
 def test_device_pow_and_exp_accuracy(handle):
     """The Psi kernel replaces np.power / np.exp (glibc, < 1 ulp) with a log2-split + table-driven 2^x and
     a table-driven e^-S.  Bound their error in ulps against an 80-bit long-double reference."""
