@@ -131,8 +131,9 @@ int pk_set_pivot_tolerance(pk_handle *h, double tol);
 
 /* Tuning / test knob for the blocked Cholesky behind pk_nll_batch and pk_fit (np.linalg.cholesky,
  * matrixops.py:31,41): 0 = automatic (default), 1 = one launch per 64-wide block column with the row
- * blocks of every candidate spread over the grid (few candidates, large n), 2 = one persistent CTA
- * per candidate (populations with at least as many candidates as SMs). */
+ * blocks of every candidate spread over the grid, 2 = one persistent CTA per candidate (populations), 3 = the
+ * persistent kernel with a gang of CTAs per candidate (few candidates: SLSQP stencils, a handful of n = 4096
+ * matrices).  Automatic: gangs for up to a third of the CTA slots, otherwise a cost model fitted on B200 picks 1 or 2. */
 int pk_set_cholesky_variant(pk_handle *h, int variant);
 
 /* Tuning / test knob for the fused predictor behind pk_predict_batch (predict_normalized /

@@ -260,7 +260,7 @@ class Handle(object):
         self._check(self.lib.pk_set_pivot_tolerance(self._h, float(tol)), "pk_set_pivot_tolerance")
 
     def set_cholesky_variant(self, variant):
-        """0 auto, 1 per-block-column launches, 2 persistent CTA per candidate."""
+        """0 auto, 1 per-block-column launches, 2 persistent CTA per candidate, 3 the same with gangs of CTAs per candidate."""
         self._check(self.lib.pk_set_cholesky_variant(self._h, int(variant)), "pk_set_cholesky_variant")
 
     def set_overlap(self, enabled):

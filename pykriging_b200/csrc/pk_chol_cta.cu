@@ -55,6 +55,53 @@ __device__ __forceinline__ double negd(double x) {
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));  // sign flip on the ALU pipe
 }
 
+// ---- gangs: several CTAs share ONE candidate (few candidates, large n) ---------------------------------------
+// With fewer candidates than SMs one CTA per candidate leaves most of the GPU idle (n = 1024, 21 candidates of an
+// SLSQP stencil: 2.2 ms whatever the count).  A gang of G CTAs (consecutive block indices, all resident: the grid
+// never exceeds 2 CTAs per SM) then works on the same matrix: the K range of the diagonal-tile product is split in
+// segments of one block column, dealt round-robin over the ranks; the 72 x 64 partial sums are exchanged through a
+// global scratch and every rank adds them in SEGMENT order, so all ranks hold bit-identical tiles -- whatever G is --
+// and factorise them redundantly (no broadcast of L_jj or of the inverted diagonal blocks is needed); the panel's
+// 64-row passes are dealt round-robin as well.  Two gang barriers per block column (a monotone counter in global
+// memory: release fence + atomic add, acquire spin).  A candidate's result is therefore the same in a gang of any
+// size: SLSQP's single-candidate evaluations and its stencil populations agree bit for bit.
+struct Gang {
+    int G, rank;
+    unsigned* ctr;       // this gang's barrier counter (zeroed by the launcher)
+    double* part;        // this gang's partial-sum scratch: (nt - 1) slots of GANG_PART doubles (one per K segment)
+    unsigned epoch;      // arrivals expected at the next barrier
+};
+constexpr int GANG_PART = (PK_TILE + PK_AUG_ROWS) * PK_TILE;  // 72 x 64
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// returns false if the other ranks did not arrive within ~4e9 cycles (never on a healthy launch; keeps a broken
+// one from hanging the GPU)
+__device__ __forceinline__ bool gang_barrier(Gang& g, int* ctl) {
+    g.epoch += (unsigned)g.G;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(g.ctr, 1u);
+        const long long t0 = clock64();
+        int ok = 1;
+        while (ld_acquire_gpu(g.ctr) < g.epoch) {
+            if (clock64() - t0 > (1LL << 32)) {
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence();
+        ctl[2] = ok;
+    }
+    __syncthreads();
+    fence_proxy_async();  // the other ranks' stores are read through TMA from here on
+    return ctl[2] != 0;
+}
+
 // acc(8*MI x 64 per warp) += A(8*MI x 16) * B(64 x 16)^T for one stage (the products are accumulated with a
 // PLUS sign and subtracted from the original tile in one go when it arrives with the solve chunks: no sign
 // flips in the hot loop -- every non-DMMA instruction costs the scheduler's dispatch port a cycle the tensor
@@ -200,7 +247,8 @@ __device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const doubl
 // sections {barrier wait, early produce, first half, late produce, second half, store} into tl[0..5] / tl[8..13].
 __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
                                              int rows, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
-                                             int* rel, unsigned& seq, const Frag& fg, long long* tl = nullptr) {
+                                             int* rel, unsigned& seq, const Frag& fg, int G, int rank,
+                                             long long* tl = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     double* As = pipe;
@@ -209,7 +257,12 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     const int first = (j + 1) * PK_TILE;
     const int nk_gemm = j * (PK_TILE / KC);
     const int nkt = nk_gemm + PK_TILE / KC;
-    const int nblk = (rows - first + BM - 1) / BM;
+    // passes: 128 rows each for a CTA on its own; in a gang 64-row passes dealt round-robin over the ranks
+    const int prow = (G > 1) ? PK_TILE : BM;
+    const int npass = (rows - first + prow - 1) / prow;
+    const int nblk = (rank < npass) ? (npass - rank + G - 1) / G : 0;
+    const int pstride = G * prow;
+    const int first_mine = first + rank * prow;
     const int total = nblk * nkt;
     // Producer: ONE thread per chunk.  A chunk is three TMA tile copies (two 64-row boxes of A, one of B, 16
     // columns each) described by a 3-D tensor map over (column, row, candidate); completion is counted in bytes on
@@ -219,7 +272,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     auto issue = [&](int c, int k_idx, int r0) {
         const int ps = (int)((seq + (unsigned)c) % STAGES);
         unsigned long long* bar = bars + ps;
-        const int nbox = (rows - r0 > BOX_ROWS) ? 2 : 1;
+        const int nbox = (G == 1 && rows - r0 > BOX_ROWS) ? 2 : 1;
         mbar_arrive_expect_tx(bar, (unsigned)((nbox + 1) * BOX_DOUBLES * sizeof(double)));
         double* as = As + ps * A_STAGE;
         tma_load_3d(as, tmap, k_idx * KC, r0, cidx, bar);
@@ -227,10 +280,10 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         tma_load_3d(Bs + ps * B_STAGE, tmap, k_idx * KC, brow0, cidx, bar);
     };
     if (tid == 0) {
-        for (int c = 0; c < STAGES && c < total; ++c) issue(c, c % nkt, first + (c / nkt) * BM);
+        for (int c = 0; c < STAGES && c < total; ++c) issue(c, c % nkt, first_mine + (c / nkt) * pstride);
     }
     // position of the chunk STAGES ahead of the one being consumed (tracked by every warp: any of them may issue it)
-    int pk = STAGES % nkt, p_row0 = first + (STAGES / nkt) * BM;
+    int pk = STAGES % nkt, p_row0 = first_mine + (STAGES / nkt) * pstride;
     double acc[2][8][2];
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
@@ -239,13 +292,13 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     // A 128-row pass gives every warp 16 rows (two DMMA row tiles); a 64-row pass (odd number of tiles left)
     // gives every warp 8 rows, so all four schedulers keep two warps either way.
     auto pass_shape = [&](int r0, int& wrow, int& mic) {
-        const bool full = (rows - r0) >= BM;
+        const bool full = (G == 1) && (rows - r0) >= BM;
         wrow = warp * (full ? 16 : 8);
         mic = full ? 2 : 1;
     };
     int cb = 0, ck = 0, cs = (int)(seq % STAGES);
     unsigned cpar = (seq / STAGES) & 1u;
-    int row0 = first, wrow, mi_count;
+    int row0 = first_mine, wrow, mi_count;
     pass_shape(row0, wrow, mi_count);
     long long tprev = 0, tacc[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool tlw = tl != nullptr && lane == 0 && (warp & 3) == 0;
@@ -281,7 +334,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         }
         if (++pk == nkt) {
             pk = 0;
-            p_row0 += BM;
+            p_row0 += pstride;
         }
         PK_TL(4)
         if (tlw) tacc[6] += 1;
@@ -300,7 +353,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
             }
             ck = 0;
             ++cb;
-            row0 = first + cb * BM;
+            row0 = first_mine + cb * pstride;
             pass_shape(row0, wrow, mi_count);
             PK_TL(5)
         }
@@ -445,23 +498,33 @@ __device__ __forceinline__ void diag_consume(double (&acc)[8][2], double (&accA)
     }
 }
 
-__device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j,
+__device__ __forceinline__ bool diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j,
                                           int np, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
-                                          int* rel, unsigned& seq, const Frag& fg) {
+                                          int* rel, unsigned& seq, const Frag& fg, Gang* gang, int* ctl) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     const int br = (warp < 4) ? warp : 11 - warp;
     double* Bs = pipe + STAGES * A_STAGE;
     const int row0 = j * PK_TILE;
-    const int nk = j * (PK_TILE / KC);
+    const int nk_all = j * (PK_TILE / KC);
+    // A gang splits the K range in SEGMENTS of one block column (4 chunks): segment c < j belongs to rank c % G, its
+    // partial sum goes to slot c of the gang's scratch, and every rank adds the slots in segment order -- so the tile
+    // (and with it every bit of the factor) does not depend on the gang size.
+    constexpr int SEG = PK_TILE / KC;
+    const int G = gang ? gang->G : 1, rank = gang ? gang->rank : 0;
+    const int nseg = (G > 1) ? ((rank < j) ? (j - rank + G - 1) / G : 0) : 0;  // segments of this rank
+    const int nk = (G > 1) ? nseg * SEG : nk_all;
+    // chunk i of this rank -> K chunk index
+    auto kchunk = [&](int i) { return (G > 1) ? (rank + (i / SEG) * G) * SEG + (i % SEG) : i; };
     // two TMA boxes per chunk (L[j, :] and the box that starts at the 8 augmented rows; its 56 rows beyond the
     // matrix are zero-filled by the TMA unit); issued like the panel's chunks (see panel_column)
     auto issue = [&](int c) {
         const int ps = (int)((seq + (unsigned)c) % STAGES);
         unsigned long long* bar = bars + ps;
         mbar_arrive_expect_tx(bar, (unsigned)(2 * BOX_DOUBLES * sizeof(double)));
-        tma_load_3d(Bs + ps * B_STAGE, tmap, c * KC, row0, cidx, bar);
-        tma_load_3d(pipe + ps * A_STAGE, tmap, c * KC, np, cidx, bar);
+        const int kc = kchunk(c);
+        tma_load_3d(Bs + ps * B_STAGE, tmap, kc * KC, row0, cidx, bar);
+        tma_load_3d(pipe + ps * A_STAGE, tmap, kc * KC, np, cidx, bar);
     };
     if (tid == 0) {
         for (int c = 0; c < STAGES && c < nk; ++c) issue(c);
@@ -472,6 +535,37 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
 #pragma unroll
     for (int ni = 0; ni < 8; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
     double accA[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    // slot of the gang's scratch <- this thread's accumulators (minus the ORIGINAL tile for slot 0), accumulators
+    // back to zero.  Nobody reads the original after the barrier: a faster rank may already be overwriting it with L_jj.
+    auto flush_slot = [&](int slot) {
+        double* dst = gang->part + (size_t)slot * GANG_PART;
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+            if (ni <= br) {
+                double2 v = make_double2(acc[ni][0], acc[ni][1]);
+                if (slot == 0) {
+                    const double2 o = *reinterpret_cast<const double2*>(M + (size_t)(row0 + br * 8 + fr) * ld + row0 + ni * 8 + 2 * q);
+                    v.x -= o.x;
+                    v.y -= o.y;
+                }
+                *reinterpret_cast<double2*>(dst + (br * 8 + fr) * PK_TILE + ni * 8 + 2 * q) = v;
+            }
+            acc[ni][0] = acc[ni][1] = 0.0;
+        }
+        if (warp < 4) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                double2 v = make_double2(accA[i][0], accA[i][1]);
+                if (slot == 0) {
+                    const double2 o = *reinterpret_cast<const double2*>(M + (size_t)(np + fr) * ld + row0 + (2 * warp + i) * 8 + 2 * q);
+                    v.x -= o.x;
+                    v.y -= o.y;
+                }
+                *reinterpret_cast<double2*>(dst + (PK_TILE + fr) * PK_TILE + (2 * warp + i) * 8 + 2 * q) = v;
+                accA[i][0] = accA[i][1] = 0.0;
+            }
+        }
+    };
     for (int it = 0; it < nk; ++it) {
         mbar_wait(bars + cs, cpar);
         const double* bs = Bs + cs * B_STAGE;
@@ -499,9 +593,46 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
             *rcnt = 0;
             if (it + STAGES < nk) issue(it + STAGES);
         }
+        if (G > 1 && (it % SEG) == SEG - 1) flush_slot(rank + (it / SEG) * G);  // segment complete
     }
 #undef PK_DIAG_HALF
     seq += (unsigned)nk;
+    if (G > 1) {
+        if (j == 0 && rank == 0) flush_slot(0);  // no products yet: slot 0 = -original
+        if (!gang_barrier(*gang, ctl)) return false;
+        const int nslot = (j > 0) ? j : 1;
+        for (int r = 0; r < nslot; ++r) {
+            const double* pr = gang->part + (size_t)r * GANG_PART;
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                if (ni <= br) {
+                    const double2 v = __ldcg(reinterpret_cast<const double2*>(pr + (br * 8 + fr) * PK_TILE + ni * 8 + 2 * q));
+                    acc[ni][0] += v.x;
+                    acc[ni][1] += v.y;
+                }
+            }
+            if (warp < 4) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double2 v = __ldcg(reinterpret_cast<const double2*>(pr + (PK_TILE + fr) * PK_TILE + (2 * warp + i) * 8 + 2 * q));
+                    accA[i][0] += v.x;
+                    accA[i][1] += v.y;
+                }
+            }
+        }
+        // T = -(sum of the slots) = original - products
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+            if (ni <= br)
+                *reinterpret_cast<double2*>(T + (br * 8 + fr) * TS + ni * 8 + 2 * q) = make_double2(-acc[ni][0], -acc[ni][1]);
+        if (warp < 4) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                *reinterpret_cast<double2*>(T + (PK_TILE + fr) * TS + (2 * warp + i) * 8 + 2 * q) =
+                    make_double2(-accA[i][0], -accA[i][1]);
+        }
+        return true;
+    }
     __syncthreads();  // the stages are drained: T (aliasing the A stages) may be written
     // T = original tile - accumulated products
 #pragma unroll
@@ -522,20 +653,21 @@ __device__ __forceinline__ void diag_gemm(double* T, double* pipe, const double*
                 make_double2(v.x - accA[i][0], v.y - accA[i][1]);
         }
     }
+    return true;
 }
 
 // Diagonal tile of block column j.  Returns 0 or the tile-local failing column (CTA uniform).
 __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag0, int* ctl, double* __restrict__ M,
                                          int ld, int j, int np, double piv_tol, const CUtensorMap* tmap, int cidx,
                                          unsigned long long* bars, int* rel, unsigned& seq, const Frag& fg,
-                                         long long* tm) {
+                                         long long* tm, Gang* gang) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = j * PK_TILE;
     if (tid < PK_TILE) diag0[tid] = M[(size_t)(row0 + tid) * ld + row0 + tid];
     double* T = pipe;
     long long t0 = 0;
     if (tm) t0 = clock64();
-    diag_gemm(T, pipe, M, ld, j, np, tmap, cidx, bars, rel, seq, fg);
+    if (!diag_gemm(T, pipe, M, ld, j, np, tmap, cidx, bars, rel, seq, fg, gang, ctl)) return -1;  // gang barrier timed out
     if (tid == 0) ctl[1] = 0;
     __syncthreads();
     if (tm) {
@@ -606,7 +738,8 @@ template <bool TIMING>
 __global__ void __launch_bounds__(THREADS, 2)
 chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int rows, int ld, size_t elems, double piv_tol,
                 double* __restrict__ ws, int32_t* __restrict__ info, unsigned int* __restrict__ queue,
-                long long* __restrict__ dbg, int alias) {
+                long long* __restrict__ dbg, int alias, int G, unsigned* __restrict__ gang_ctr,
+                double* __restrict__ gang_part) {
     long long tmv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long* tm = TIMING ? tmv : nullptr;
     extern __shared__ __align__(16) double smem_raw[];
@@ -629,6 +762,33 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
     }
     const Frag fg = make_frag(tid & 31);
     unsigned seq = 0;  // pipeline chunks issued == consumed so far (stage = seq % STAGES, parity = seq / STAGES & 1)
+    if (G > 1) {
+        // ---- gang mode: G consecutive CTAs factorise candidate blockIdx.x / G together (see struct Gang) ----
+        const int cand = blockIdx.x / G;
+        if (cand >= C) return;
+        Gang gang{G, (int)(blockIdx.x % G), gang_ctr + cand, gang_part + (size_t)cand * (nt - 1) * GANG_PART, 0u};
+        fence_proxy_async();
+        __syncthreads();
+        if (info[cand] != 0) return;  // uniform over the gang
+        double* M = ws + (size_t)cand * elems;
+        for (int j = 0; j < nt; ++j) {
+            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cand, bars, rel, seq, fg,
+                                      nullptr, &gang);
+            if (bad) {  // every rank holds the same tile and sees the same failure (or the same timed-out barrier)
+                if (tid == 0) info[cand] = (bad > 0) ? j * PK_TILE + bad : -1;
+                break;
+            }
+            if (j + 1 < nt) {
+                panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cand, bars, rel, seq, fg, G, gang.rank);
+                // rows of block column j written by the other ranks are read from the next column on
+                if (!gang_barrier(gang, ctl)) {
+                    if (tid == 0) info[cand] = -1;
+                    break;
+                }
+            }
+        }
+        return;
+    }
     for (;;) {
         fence_proxy_async();  // a failed factorisation leaves generic-proxy writes in the stage buffers
         __syncthreads();
@@ -640,14 +800,15 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
         const int cidx = alias ? (cand & 7) : cand;  // alias: timing experiment only (results are garbage)
         double* M = ws + (size_t)cidx * elems;
         for (int j = 0; j < nt; ++j) {
-            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cidx, bars, rel, seq, fg, tm);
+            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cidx, bars, rel, seq, fg, tm,
+                                      nullptr);
             if (bad && !alias) {
                 if (tid == 0) info[cand] = j * PK_TILE + bad;  // dpotrf convention: order of the failing minor
                 break;
             }
             long long t0 = 0;
             if (TIMING) t0 = clock64();
-            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, rel, seq, fg, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
+            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, rel, seq, fg, 1, 0, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
             if (TIMING) tmv[3] += clock64() - t0;
         }
         if (TIMING) tmv[4] += 1;
@@ -685,6 +846,18 @@ static cudaError_t make_ws_tensor_map(CUtensorMap* tmap, double* ws, const Tiled
     return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// Gang size for a population of Ceff candidates (the whole population when this call is a shard): as many CTAs per
+// candidate as 2 per SM allow, at most one per 64-row pass of the first panel.  Automatic mode wants at least 3
+// ranks: with 2 the exchange and the barriers cost more than the second CTA brings (profiles/variant_sweep_small_r01.jsonl:
+// n = 1024, 128 candidates: 2.30 ms in pairs, 2.20 ms alone; 96 candidates in gangs of 3: 1.76 against 2.19).
+int cholesky_gang_size(const pk_handle* h, const TiledShape& s, int64_t Ceff, bool forced) {
+    if (Ceff > h->sm_count) return 1;
+    const int nt = s.np / PK_TILE;
+    int64_t G = (2 * (int64_t)h->sm_count) / (Ceff > 0 ? Ceff : 1);
+    if (G > nt - 1) G = nt - 1;
+    return (G < (forced ? 2 : 3)) ? 1 : (int)G;
+}
+
 cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     if (s.with_inverse || s.rows != s.np + PK_AUG_ROWS) return cudaErrorInvalidValue;  // population shape only
     const int nt = s.np / PK_TILE;
@@ -706,6 +879,42 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
     unsigned int* queue = h->d_queue + h->queue_slot;
     cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(unsigned int), h->stream);
     if (e != cudaSuccess) return e;
+    // few candidates: gangs of G CTAs per candidate (chol_variant 3 forces gangs, 2 forbids them)
+    int G = 1;
+    {
+        const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;
+        if (h->chol_variant != 2) G = cholesky_gang_size(h, s, Ceff, h->chol_variant == 3);
+        if (const char* ev = getenv("PK_CHOL_GANG")) {  // experiment knob
+            G = atoi(ev);
+            if (G < 1) G = 1;
+            if (G > nt - 1) G = (nt - 1 > 0) ? nt - 1 : 1;
+        }
+        if ((int64_t)C * G > 2 * (int64_t)h->sm_count) G = 1;  // all CTAs of a gang must be resident
+    }
+    if (G > 1) {
+        const size_t ctr_bytes = (sizeof(unsigned) * (size_t)h->sm_count + 255) & ~(size_t)255;
+        // one slot per K segment and candidate; sized for the largest population that still runs in gangs, so that a
+        // varying candidate count (GA generation, then SLSQP stencils, then single evaluations) never reallocates
+        const size_t part_bytes = sizeof(double) * (size_t)h->sm_count * (nt - 1) * cta::GANG_PART;
+        if (ctr_bytes + part_bytes > h->gang_bytes) {
+            e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) return e;
+            if (h->d_gang) cudaFree(h->d_gang);
+            h->d_gang = nullptr;
+            h->gang_bytes = 0;
+            e = cudaMalloc((void**)&h->d_gang, ctr_bytes + part_bytes);
+            if (e != cudaSuccess) return e;
+            h->gang_bytes = ctr_bytes + part_bytes;
+        }
+        e = cudaMemsetAsync(h->d_gang, 0, ctr_bytes, h->stream);
+        if (e != cudaSuccess) return e;
+        unsigned* ctr = reinterpret_cast<unsigned*>(h->d_gang);
+        double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(h->d_gang) + ctr_bytes);
+        cta::chol_cta_kernel<false><<<C * G, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
+                                                                              ws, info, queue, nullptr, 0, G, ctr, part);
+        h->launches++;
+        return cudaGetLastError();
+    }
     int per_sm = 2;
     if (const char* e = getenv("PK_CHOL_CTAS_PER_SM")) per_sm = (atoi(e) == 1) ? 1 : 2;  // experiment knob
     const int grid = (C < per_sm * h->sm_count) ? C : per_sm * h->sm_count;
@@ -714,7 +923,8 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         cudaMalloc((void**)&dbg, sizeof(long long) * (8 * grid + 16));
         cudaMemset(dbg, 0, sizeof(long long) * (8 * grid + 16));
         cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
-                                                                            ws, info, queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0);
+                                                                            ws, info, queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0,
+                                                                            1, nullptr, nullptr);
         cudaStreamSynchronize(h->stream);
         std::vector<long long> host(8 * (size_t)grid + 16);
         cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
@@ -737,7 +947,8 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
                 sum[6] / sum[4], sum[7] / sum[4]);
     } else {
         cta::chol_cta_kernel<false><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(),
-                                                                             h->pivot_tol, ws, info, queue, nullptr, 0);
+                                                                             h->pivot_tol, ws, info, queue, nullptr, 0, 1,
+                                                                             nullptr, nullptr);
     }
     h->launches++;
     return cudaGetLastError();

@@ -27,6 +27,8 @@ struct pk_handle {
     // this handle's calls are slices of a population / query set of these sizes (pk_set_shard_hint; 0 = no hint):
     // automatic kernel selection uses them, so a shard computes bit for bit what the unsharded call would
     int64_t hint_C = 0, hint_m = 0;
+    size_t gang_bytes = 0;
+    void* d_gang = nullptr;                // gang barrier counters + partial-sum scratch of the persistent Cholesky (gang mode)
     unsigned int* d_queue = nullptr;       // candidate queues of the persistent Cholesky kernel (PK_QUEUE_SLOTS counters)
     int queue_slot = 0;                    // counter the next launch_cholesky_cta uses
     // Psi construction of the NEXT part of a population overlaps the Cholesky of the current one: the Psi
@@ -115,6 +117,7 @@ cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const dou
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
+int cholesky_gang_size(const pk_handle* h, const TiledShape& s, int64_t Ceff, bool forced);
 cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,
                                 int out_stride, int32_t* info);
 cudaError_t launch_extract_psi(pk_handle* h, const TiledShape& s, const double* M, double* out, int C);

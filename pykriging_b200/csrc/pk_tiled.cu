@@ -579,6 +579,8 @@ cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, doub
 // Variant choice: the persistent kernel keeps one CTA per candidate busy for the whole factorisation,
 // so it wants at least ~2/3 of the SMs' worth of candidates; below that (pk_fit, n = 4096 with a
 // handful of candidates) the per-block-column launches expose the parallelism inside a matrix.
+// Few candidates (at most a third of the CTA slots): the persistent kernel with a GANG of CTAs per candidate wins
+// everywhere (pk_chol_cta.cu, cholesky_gang_size).  Otherwise:
 // Automatic choice between the two Cholesky variants from a cost model fitted to tools/variant_sweep.py on B200
 // (profiles/variant_sweep_r01.jsonl): the persistent kernel runs candidates in waves of 2 CTAs per SM -- a full
 // wave of 2 x SMs candidates takes T2(n), a partial wave with at most one CTA per SM T1(n) ~ 0.5-0.7 T2(n), anything
@@ -611,9 +613,9 @@ static int choose_cholesky_variant(int np, int64_t C, int sm_count) {
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     int v = h->chol_variant;
     const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;  // the population this call is a slice of
-    if (v == 0) v = choose_cholesky_variant(s.np, Ceff, h->sm_count);
+    if (v == 0) v = (cholesky_gang_size(h, s, Ceff, false) > 1) ? 2 : choose_cholesky_variant(s.np, Ceff, h->sm_count);
     if (s.with_inverse) v = 1;  // pk_fit (one matrix + L^-1 rows): the per-block-column kernels
-    return (v == 2) ? launch_cholesky_cta(h, s, C, ws, info) : launch_cholesky_steps(h, s, C, ws, info);
+    return (v >= 2) ? launch_cholesky_cta(h, s, C, ws, info) : launch_cholesky_steps(h, s, C, ws, info);
 }
 
 cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,

@@ -154,11 +154,12 @@ def test_tiled_path_matches_oracle_on_seeded_inputs(handle, n, k, seed):
         assert rel_err(out["sigma2"][i], s2) < tol, (i, cond)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("n,k,seed", [(130, 4, 3), (333, 7, 5), (640, 10, 6), (1024, 10, 7)])
 def test_cholesky_variants_match_oracle(handle, variant, n, k, seed):
-    """Both blocked-Cholesky variants (per-block-column launches / persistent CTA per candidate) against
-    the oracle, including candidates whose Psi is not positive definite and the info convention."""
+    """The blocked-Cholesky variants (1 per-block-column launches / 2 persistent CTA per candidate / 3 the same
+    kernel with a gang of CTAs per candidate) against the oracle, including candidates whose Psi is not positive
+    definite and the info convention."""
     X = onp.rlh(n, k, seed)
     y = onp.f_stybtang_norm(X)
     Xn, yn, _, _ = onp.normalize_data(X, y)
@@ -465,6 +466,38 @@ def test_full_size_c5_grid_properties(handle):
     assert np.max(np.abs(g[1] ** 2 - ref["s"] ** 2)) < out4[2] * max(1e-12, 100.0 * cond * 2.2e-16)
     ds = np.abs(g[1] - ref["s"])
     assert np.all(np.abs(g[2] - ref["ei"]) <= 1e-9 * np.sqrt(out4[2]) + 0.5 * ds + 1e-9 * np.abs(ref["ei"]))
+
+
+def test_gang_size_does_not_change_results(handle):
+    """Few candidates are factorised by a GANG of CTAs each (the fewer candidates, the larger the gang).  A
+    candidate's result must not depend on the gang size -- SLSQP's single-candidate evaluations
+    (fittingObjective_local, krige.py:454-472) and its finite-difference stencil populations have to agree bit for
+    bit -- and must match the oracle; a candidate that fails to factorise fails alone."""
+    n, k = 1024, 6
+    X = onp.rlh(n, k, 41)
+    y = onp.f_squared(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    cands = onp.candidates_loguniform(40, k, 42, lo=-2.0, hi=1.0)
+    cands[2, :k] = 1e-5  # numerically singular with p = 2: dpotrf fails, and so must the gang
+    cands[2, k:] = 2.0
+    th, p = np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:])
+    big = handle.nll_batch(th, p)                 # 40 candidates: gangs of 7
+    assert big["info"][2] > 0 and np.isnan(big["nll"][2])
+    for lo, hi in ((3, 4), (0, 5), (7, 28)):      # 1 candidate: gang of 15; 5: 15; 21: 14
+        part = handle.nll_batch(th[lo:hi], p[lo:hi])
+        for name in ("nll", "mu", "sigma2", "lndet"):
+            assert np.array_equal(part[name], big[name][lo:hi], equal_nan=True), (name, lo, hi)
+        assert np.array_equal(part["info"], big["info"][lo:hi])
+    for i in (0, 3, 17, 39):
+        Psi = onp.psi_fast(Xn, th[i], p[i])
+        nll, mu, s2, lndet, info = onp.neglikelihood_fast(Psi, yn)
+        cond = np.linalg.cond(Psi)
+        if info != 0 or cond > 1e12:
+            continue
+        tol = tol_for_cond(cond)
+        assert big["info"][i] == 0
+        assert rel_err(big["nll"][i], nll) < tol and rel_err(big["mu"][i], mu) < tol and rel_err(big["sigma2"][i], s2) < tol
 
 
 def test_device_pow_and_exp_accuracy(handle):
