@@ -247,7 +247,7 @@ __device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const doubl
 // sections {barrier wait, early produce, first half, late produce, second half, store} into tl[0..5] / tl[8..13].
 __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
                                              int rows, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
-                                             int* rel, unsigned& seq, const Frag& fg, int G, int rank,
+                                             int* rel, unsigned& seq, const Frag& fg, int G, int rank, int inv_base,
                                              long long* tl = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
@@ -259,10 +259,16 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     const int nkt = nk_gemm + PK_TILE / KC;
     // passes: 128 rows each for a CTA on its own; in a gang 64-row passes dealt round-robin over the ranks
     const int prow = (G > 1) ? PK_TILE : BM;
-    const int npass = (rows - first + prow - 1) / prow;
+    // pk_fit (gang mode only): the identity block that becomes L^-T starts at row inv_base = np + 8; its tiles 0 .. j
+    // are further passes of block column j (tiles beyond j are still zero in every column <= j)
+    const int nbelow = (rows - first + prow - 1) / prow;
+    const int npass = nbelow + ((inv_base > 0) ? j + 1 : 0);
     const int nblk = (rank < npass) ? (npass - rank + G - 1) / G : 0;
-    const int pstride = G * prow;
-    const int first_mine = first + rank * prow;
+    // first row of this rank's i-th pass
+    auto pass_row = [&](int i) {
+        const int P = rank + i * G;
+        return (P < nbelow) ? first + P * prow : inv_base + (P - nbelow) * PK_TILE;
+    };
     const int total = nblk * nkt;
     // Producer: ONE thread per chunk.  A chunk is three TMA tile copies (two 64-row boxes of A, one of B, 16
     // columns each) described by a 3-D tensor map over (column, row, candidate); completion is counted in bytes on
@@ -280,10 +286,10 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         tma_load_3d(Bs + ps * B_STAGE, tmap, k_idx * KC, brow0, cidx, bar);
     };
     if (tid == 0) {
-        for (int c = 0; c < STAGES && c < total; ++c) issue(c, c % nkt, first_mine + (c / nkt) * pstride);
+        for (int c = 0; c < STAGES && c < total; ++c) issue(c, c % nkt, pass_row(c / nkt));
     }
     // position of the chunk STAGES ahead of the one being consumed (tracked by every warp: any of them may issue it)
-    int pk = STAGES % nkt, p_row0 = first_mine + (STAGES / nkt) * pstride;
+    int pk = STAGES % nkt, p_pass = STAGES / nkt, p_row0 = pass_row(STAGES / nkt);
     double acc[2][8][2];
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
@@ -298,7 +304,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     };
     int cb = 0, ck = 0, cs = (int)(seq % STAGES);
     unsigned cpar = (seq / STAGES) & 1u;
-    int row0 = first_mine, wrow, mi_count;
+    int row0 = pass_row(0), wrow, mi_count;
     pass_shape(row0, wrow, mi_count);
     long long tprev = 0, tacc[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool tlw = tl != nullptr && lane == 0 && (warp & 3) == 0;
@@ -334,7 +340,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
         }
         if (++pk == nkt) {
             pk = 0;
-            p_row0 += pstride;
+            p_row0 = pass_row(++p_pass);
         }
         PK_TL(4)
         if (tlw) tacc[6] += 1;
@@ -353,7 +359,7 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
             }
             ck = 0;
             ++cb;
-            row0 = first_mine + cb * pstride;
+            row0 = pass_row(cb);
             pass_shape(row0, wrow, mi_count);
             PK_TL(5)
         }
@@ -739,7 +745,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int rows, int ld, size_t elems, double piv_tol,
                 double* __restrict__ ws, int32_t* __restrict__ info, unsigned int* __restrict__ queue,
                 long long* __restrict__ dbg, int alias, int G, unsigned* __restrict__ gang_ctr,
-                double* __restrict__ gang_part) {
+                double* __restrict__ gang_part, int inv_base) {
     long long tmv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long* tm = TIMING ? tmv : nullptr;
     extern __shared__ __align__(16) double smem_raw[];
@@ -778,8 +784,8 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
                 if (tid == 0) info[cand] = (bad > 0) ? j * PK_TILE + bad : -1;
                 break;
             }
-            if (j + 1 < nt) {
-                panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cand, bars, rel, seq, fg, G, gang.rank);
+            if (j + 1 < nt || inv_base > 0) {
+                panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cand, bars, rel, seq, fg, G, gang.rank, inv_base);
                 // rows of block column j written by the other ranks are read from the next column on
                 if (!gang_barrier(gang, ctl)) {
                     if (tid == 0) info[cand] = -1;
@@ -808,7 +814,7 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
             }
             long long t0 = 0;
             if (TIMING) t0 = clock64();
-            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, rel, seq, fg, 1, 0, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
+            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, rel, seq, fg, 1, 0, 0, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
             if (TIMING) tmv[3] += clock64() - t0;
         }
         if (TIMING) tmv[4] += 1;
@@ -859,7 +865,6 @@ int cholesky_gang_size(const pk_handle* h, const TiledShape& s, int64_t Ceff, bo
 }
 
 cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
-    if (s.with_inverse || s.rows != s.np + PK_AUG_ROWS) return cudaErrorInvalidValue;  // population shape only
     const int nt = s.np / PK_TILE;
     const size_t smem = sizeof(double) * (size_t)cta::SMEM_DOUBLES + cta::SMEM_ALIGN;
     CUtensorMap tmap;
@@ -883,7 +888,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
     int G = 1;
     {
         const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;
-        if (h->chol_variant != 2) G = cholesky_gang_size(h, s, Ceff, h->chol_variant == 3);
+        if (h->chol_variant != 2 || s.with_inverse) G = cholesky_gang_size(h, s, Ceff, h->chol_variant == 3 || s.with_inverse);
         if (const char* ev = getenv("PK_CHOL_GANG")) {  // experiment knob
             G = atoi(ev);
             if (G < 1) G = 1;
@@ -891,6 +896,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         }
         if ((int64_t)C * G > 2 * (int64_t)h->sm_count) G = 1;  // all CTAs of a gang must be resident
     }
+    if (s.with_inverse && G == 1) return cudaErrorInvalidValue;  // the L^-T rows are passes of the gang kernel only
     if (G > 1) {
         const size_t ctr_bytes = (sizeof(unsigned) * (size_t)h->sm_count + 255) & ~(size_t)255;
         // one slot per K segment and candidate; sized for the largest population that still runs in gangs, so that a
@@ -911,7 +917,8 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         unsigned* ctr = reinterpret_cast<unsigned*>(h->d_gang);
         double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(h->d_gang) + ctr_bytes);
         cta::chol_cta_kernel<false><<<C * G, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
-                                                                              ws, info, queue, nullptr, 0, G, ctr, part);
+                                                                              ws, info, queue, nullptr, 0, G, ctr, part,
+                                                                              s.with_inverse ? s.np + PK_AUG_ROWS : 0);
         h->launches++;
         return cudaGetLastError();
     }
@@ -924,7 +931,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         cudaMemset(dbg, 0, sizeof(long long) * (8 * grid + 16));
         cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
                                                                             ws, info, queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0,
-                                                                            1, nullptr, nullptr);
+                                                                            1, nullptr, nullptr, 0);
         cudaStreamSynchronize(h->stream);
         std::vector<long long> host(8 * (size_t)grid + 16);
         cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
@@ -948,7 +955,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
     } else {
         cta::chol_cta_kernel<false><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(),
                                                                              h->pivot_tol, ws, info, queue, nullptr, 0, 1,
-                                                                             nullptr, nullptr);
+                                                                             nullptr, nullptr, 0);
     }
     h->launches++;
     return cudaGetLastError();

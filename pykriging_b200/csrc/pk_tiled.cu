@@ -614,7 +614,9 @@ cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws
     int v = h->chol_variant;
     const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;  // the population this call is a slice of
     if (v == 0) v = (cholesky_gang_size(h, s, Ceff, false) > 1) ? 2 : choose_cholesky_variant(s.np, Ceff, h->sm_count);
-    if (s.with_inverse) v = 1;  // pk_fit (one matrix + L^-1 rows): the per-block-column kernels
+    // pk_fit (one matrix + L^-T rows): the gang kernel, the inverse rows being further panel passes (per-block-column
+    // kernels when pinned to variant 1 or when the matrix has fewer than three block columns)
+    if (s.with_inverse) v = (h->chol_variant != 1 && cholesky_gang_size(h, s, Ceff, true) > 1) ? 3 : 1;
     return (v >= 2) ? launch_cholesky_cta(h, s, C, ws, info) : launch_cholesky_steps(h, s, C, ws, info);
 }
 
