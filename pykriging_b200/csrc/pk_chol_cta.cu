@@ -245,10 +245,13 @@ __device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const doubl
 // ------------------------------------------------------------------------------------------------
 // tl != nullptr (diagnostic build only): lanes 0 of warps 0 and 4 accumulate clock64() deltas of the loop's
 // sections {barrier wait, early produce, first half, late produce, second half, store} into tl[0..5] / tl[8..13].
+template <bool GANG>
 __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
                                              int rows, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
-                                             int* rel, unsigned& seq, const Frag& fg, int G, int rank, int inv_base,
+                                             int* rel, unsigned& seq, const Frag& fg, int G_, int rank_, int inv_base_,
                                              long long* tl = nullptr) {
+    // GANG == false: one CTA per candidate -- the gang arithmetic below folds away at compile time
+    const int G = GANG ? G_ : 1, rank = GANG ? rank_ : 0, inv_base = GANG ? inv_base_ : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     double* As = pipe;
@@ -504,6 +507,7 @@ __device__ __forceinline__ void diag_consume(double (&acc)[8][2], double (&accA)
     }
 }
 
+template <bool GANG>
 __device__ __forceinline__ bool diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j,
                                           int np, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
                                           int* rel, unsigned& seq, const Frag& fg, Gang* gang, int* ctl) {
@@ -517,7 +521,7 @@ __device__ __forceinline__ bool diag_gemm(double* T, double* pipe, const double*
     // partial sum goes to slot c of the gang's scratch, and every rank adds the slots in segment order -- so the tile
     // (and with it every bit of the factor) does not depend on the gang size.
     constexpr int SEG = PK_TILE / KC;
-    const int G = gang ? gang->G : 1, rank = gang ? gang->rank : 0;
+    const int G = GANG ? gang->G : 1, rank = GANG ? gang->rank : 0;
     const int nseg = (G > 1) ? ((rank < j) ? (j - rank + G - 1) / G : 0) : 0;  // segments of this rank
     const int nk = (G > 1) ? nseg * SEG : nk_all;
     // chunk i of this rank -> K chunk index
@@ -663,6 +667,7 @@ __device__ __forceinline__ bool diag_gemm(double* T, double* pipe, const double*
 }
 
 // Diagonal tile of block column j.  Returns 0 or the tile-local failing column (CTA uniform).
+template <bool GANG>
 __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag0, int* ctl, double* __restrict__ M,
                                          int ld, int j, int np, double piv_tol, const CUtensorMap* tmap, int cidx,
                                          unsigned long long* bars, int* rel, unsigned& seq, const Frag& fg,
@@ -673,7 +678,7 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
     double* T = pipe;
     long long t0 = 0;
     if (tm) t0 = clock64();
-    if (!diag_gemm(T, pipe, M, ld, j, np, tmap, cidx, bars, rel, seq, fg, gang, ctl)) return -1;  // gang barrier timed out
+    if (!diag_gemm<GANG>(T, pipe, M, ld, j, np, tmap, cidx, bars, rel, seq, fg, gang, ctl)) return -1;  // gang barrier timed out
     if (tid == 0) ctl[1] = 0;
     __syncthreads();
     if (tm) {
@@ -740,7 +745,7 @@ __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag
 
 // TIMING: thread 0 accumulates clock64() per phase {diag product, 64x64 factorisation, inverse + copy-out,
 // panel column, candidates} into dbg[8 * blockIdx.x ..] (diagnostic build of the same kernel).
-template <bool TIMING>
+template <bool TIMING, bool GANG>
 __global__ void __launch_bounds__(THREADS, 2)
 chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int rows, int ld, size_t elems, double piv_tol,
                 double* __restrict__ ws, int32_t* __restrict__ info, unsigned int* __restrict__ queue,
@@ -768,7 +773,7 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
     }
     const Frag fg = make_frag(tid & 31);
     unsigned seq = 0;  // pipeline chunks issued == consumed so far (stage = seq % STAGES, parity = seq / STAGES & 1)
-    if (G > 1) {
+    if constexpr (GANG) {
         // ---- gang mode: G consecutive CTAs factorise candidate blockIdx.x / G together (see struct Gang) ----
         const int cand = blockIdx.x / G;
         if (cand >= C) return;
@@ -778,14 +783,14 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
         if (info[cand] != 0) return;  // uniform over the gang
         double* M = ws + (size_t)cand * elems;
         for (int j = 0; j < nt; ++j) {
-            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cand, bars, rel, seq, fg,
-                                      nullptr, &gang);
+            const int bad = diag_tile<true>(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cand, bars, rel, seq, fg,
+                                            nullptr, &gang);
             if (bad) {  // every rank holds the same tile and sees the same failure (or the same timed-out barrier)
                 if (tid == 0) info[cand] = (bad > 0) ? j * PK_TILE + bad : -1;
                 break;
             }
             if (j + 1 < nt || inv_base > 0) {
-                panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cand, bars, rel, seq, fg, G, gang.rank, inv_base);
+                panel_column<true>(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cand, bars, rel, seq, fg, G, gang.rank, inv_base);
                 // rows of block column j written by the other ranks are read from the next column on
                 if (!gang_barrier(gang, ctl)) {
                     if (tid == 0) info[cand] = -1;
@@ -806,15 +811,15 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
         const int cidx = alias ? (cand & 7) : cand;  // alias: timing experiment only (results are garbage)
         double* M = ws + (size_t)cidx * elems;
         for (int j = 0; j < nt; ++j) {
-            const int bad = diag_tile(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cidx, bars, rel, seq, fg, tm,
-                                      nullptr);
+            const int bad = diag_tile<false>(pipe, Dsm, diag0, ctl, M, ld, j, nt * PK_TILE, piv_tol, &tmap, cidx, bars, rel, seq, fg, tm,
+                                             nullptr);
             if (bad && !alias) {
                 if (tid == 0) info[cand] = j * PK_TILE + bad;  // dpotrf convention: order of the failing minor
                 break;
             }
             long long t0 = 0;
             if (TIMING) t0 = clock64();
-            if (j + 1 < nt) panel_column(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, rel, seq, fg, 1, 0, 0, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
+            if (j + 1 < nt) panel_column<false>(pipe, Dsm, M, ld, j, nt * PK_TILE, &tmap, cidx, bars, rel, seq, fg, 1, 0, 0, (TIMING && blockIdx.x == 0) ? dbg + 8 * gridDim.x : nullptr);
             if (TIMING) tmv[3] += clock64() - t0;
         }
         if (TIMING) tmv[4] += 1;
@@ -875,9 +880,11 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e =
-            cudaFuncSetAttribute(cta::chol_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(cta::chol_cta_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(cta::chol_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(cta::chol_cta_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(cta::chol_cta_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -916,7 +923,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         if (e != cudaSuccess) return e;
         unsigned* ctr = reinterpret_cast<unsigned*>(h->d_gang);
         double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(h->d_gang) + ctr_bytes);
-        cta::chol_cta_kernel<false><<<C * G, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
+        cta::chol_cta_kernel<false, true><<<C * G, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
                                                                               ws, info, queue, nullptr, 0, G, ctr, part,
                                                                               s.with_inverse ? s.np + PK_AUG_ROWS : 0);
         h->launches++;
@@ -929,7 +936,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         long long* dbg = nullptr;
         cudaMalloc((void**)&dbg, sizeof(long long) * (8 * grid + 16));
         cudaMemset(dbg, 0, sizeof(long long) * (8 * grid + 16));
-        cta::chol_cta_kernel<true><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
+        cta::chol_cta_kernel<true, false><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
                                                                             ws, info, queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0,
                                                                             1, nullptr, nullptr, 0);
         cudaStreamSynchronize(h->stream);
@@ -953,7 +960,7 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
                 grid, sum[4], sum[0] / sum[4], sum[1] / sum[4], sum[2] / sum[4], sum[3] / sum[4], sum[5] / sum[4],
                 sum[6] / sum[4], sum[7] / sum[4]);
     } else {
-        cta::chol_cta_kernel<false><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(),
+        cta::chol_cta_kernel<false, false><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(),
                                                                              h->pivot_tol, ws, info, queue, nullptr, 0, 1,
                                                                              nullptr, nullptr, 0);
     }
