@@ -426,6 +426,12 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
         host_out |= !is_device_ptr(info);
     }
     if (host_out) PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (info && !is_device_ptr(info)) {
+        // info < 0 is not a numerical outcome: a gang barrier of the persistent Cholesky timed out (its CTAs were not
+        // all resident -- another kernel holding the SMs for seconds).  Fail loudly instead of handing back a penalty.
+        for (int i = 0; i < C; ++i)
+            if (info[i] < 0) PK_FAIL(h, "pk_nll_batch: gang barrier timed out for candidate %d (GPU shared with a long-running kernel?)", i);
+    }
     return 0;
 }
 
@@ -474,6 +480,7 @@ int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, in
                                    h->stream));
     PK_CUDA(h, cudaMemcpyAsync(&host_info, h->d_info, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (host_info < 0) PK_FAIL(h, "pk_fit: gang barrier timed out (GPU shared with a long-running kernel?)");
     if (host_info == 0) {
         double* t = h->d_fit;
         h->d_fit = h->d_try;
