@@ -110,6 +110,7 @@ __device__ __forceinline__ void log2_split(double d, double& L, float& res) {
 static __device__ const double g_exp2_4096[4096] = {PK_EXP2_4096_LIST};
 constexpr double MAGIC32K = 6755399441055744.0 / 32768.0;  // 1.5 * 2^37: ulp 2^-15
 constexpr double HALF_STEP_4096 = 1.0 / 8192.0;
+constexpr double MAGIC4K = 6755399441055744.0 / 4096.0;    // 1.5 * 2^40: ulp 2^-12
 constexpr double L2_CLAMP = 340.0;
 static __constant__ double c_e2q[3] = {0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58fp-3, 0x1.c6b08d704a0c0p-5};
 
@@ -123,6 +124,8 @@ __device__ __forceinline__ void fill_exp2_4096(double* tab, int tid, int nthread
 // the address by the same LOP3 that masks them -- bits 15.. are the binary exponent, and kd with the low
 // three bits cleared is x rounded to the nearest 1/4096: kf.
 __device__ __forceinline__ double exp2_lean4k(double pd, double lh, double ll, unsigned tab_saddr) {
+#ifdef PK_EXP2_4K_MASKED
+    // first version: x rounded to 2^-15, low three bits masked off (one LOP3 + one register move more per call)
     const double kd = fma(pd, lh, MAGIC32K + HALF_STEP_4096);
     const int kl = __double2loint(kd);
     const double kf = __longlong_as_double(__double_as_longlong(kd) & ~0x7LL) - MAGIC32K;
@@ -136,6 +139,24 @@ __device__ __forceinline__ double exp2_lean4k(double pd, double lh, double ll, u
     int hi;
     asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(hi) : "r"(kl >> 15), "r"(__double2hiint(v)));
     return __hiloint2double(hi, __double2loint(v));
+#else
+    // x = pd * lh rounded to the nearest multiple of 2^-12 by the magic add: the low word of kd is 4096 x in two's
+    // complement -- bits 0..11 the table index, bits 12.. the binary exponent -- and kd - MAGIC4K is the rounded x
+    // itself.  8 FP64 + 4 integer instructions + 1 shared load.
+    const double kd = fma(pd, lh, MAGIC4K);
+    const int k8 = __double2loint(kd) << 3;      // index as a byte offset in bits 3..14, exponent in bits 15..
+    const double kf = kd - MAGIC4K;
+    double r = fma(pd, lh, -kf);
+    r = fma(pd, ll, r);                          // |r| <= 2^-13
+    double q = fma(r, c_e2q[2], c_e2q[1]);
+    q = fma(r, q, c_e2q[0]);
+    double T;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_saddr | (unsigned)(k8 & 0x7ff8)));
+    const double v = fma(T * r, q, T);
+    int hi;
+    asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(hi) : "r"(k8 >> 15), "r"(__double2hiint(v)));
+    return __hiloint2double(hi, __double2loint(v));
+#endif
 }
 
 // e^(-S), S >= 0: Cody-Waite with ln2/4096 = hi (20 bits: k * hi is exact for |k| < 2^33) + lo, quadratic.

@@ -50,7 +50,8 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
     // 2^(j/4096) (32 KB) at the first 32 KB-aligned shared address behind the arrays above (the launcher sizes the
     // dynamic allocation for it): exp2_lean4k ORs the entry's byte offset into the address
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(psi_smem);
-    const unsigned tab_saddr = (smem_base + psi_small_bytes<K, PPT>() + 0x7fffu) & ~0x7fffu;
+    unsigned tab_saddr = (smem_base + psi_small_bytes<K, PPT>() + 0x7fffu) & ~0x7fffu;
+    asm volatile("" : "+r"(tab_saddr));  // opaque: keeps the address in a register instead of re-deriving it (5 instructions) per candidate
     double* tab4k = psi_smem + (tab_saddr - smem_base) / sizeof(double);
     // block -> (lower tile, row block)
     const int t = blockIdx.x / SPT, sb = blockIdx.x % SPT;
