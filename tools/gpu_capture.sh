@@ -1,3 +1,4 @@
+# Bench + launch list + ncu --set full captures of the four hot kernels (run under gpurun; summaries -> profiles/ with tools/summarize_ncu.py)
 mkdir -p gpurun_out
 T=s4
 timeout 900 python bench.py > gpurun_out/bench_r01_$T.json 2> gpurun_out/bench_err.log; echo "bench rc=$?"; tail -3 gpurun_out/bench_err.log

@@ -1,3 +1,4 @@
+# 8-GPU bench + sharding check (gpurun --gpus 8)
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/bench_r01_s4_8gpu.json 2> gpurun_out/bench8_err.log; echo "bench8 rc=$?"; tail -c 400 gpurun_out/bench8_err.log

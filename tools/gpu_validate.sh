@@ -1,3 +1,4 @@
+# Full GPU validation: pytest -m gpu, smoke(), default bench, shape sweep (run under gpurun)
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_r01_s4.log
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
