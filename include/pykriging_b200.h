@@ -142,7 +142,10 @@ int pk_set_cholesky_variant(pk_handle *h, int variant);
  *     lives in a per-CTA slab of a global scratch),
  * 2 = v = L^-1 psi held in registers, psi chunks generated on the fly (n <= 512; falls back otherwise),
  * 3 = split pipeline: psi rows + yhat in one FP64-ALU kernel (through an HBM scratch), |L^-1 psi|^2, s and EI in a
- *     TMA-fed DMMA kernel (any n; what 0 selects for 4096 query points or more). */
+ *     TMA-fed DMMA kernel (any n; what 0 selects for 4096 query points or more).  Row-major tensor grids (plot,
+ *     snapshot: krige.py:531-537, 699-708) are detected on the device and take a psi kernel that evaluates the
+ *     separated exponent from per-row / per-column tables (bit-identical results),
+ * 4 = 3 with that detection switched off. */
 int pk_set_predict_variant(pk_handle *h, int variant);
 
 /* Multi-GPU sharding (the reference has one Python loop over the whole population,

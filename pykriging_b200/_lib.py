@@ -268,7 +268,8 @@ class Handle(object):
         self._check(self.lib.pk_set_overlap(self._h, int(bool(enabled))), "pk_set_overlap")
 
     def set_predict_variant(self, variant):
-        """0 auto, 1 shared-memory psi tile kernel, 2 register-resident kernel (n <= 512), 3 split pipeline."""
+        """0 auto, 1 shared-memory psi tile kernel, 2 register-resident kernel (n <= 512), 3 split pipeline, 4 split
+        pipeline without the device-side grid detection."""
         self._check(self.lib.pk_set_predict_variant(self._h, int(variant)), "pk_set_predict_variant")
 
     def set_shard_hint(self, population=0, query_points=0):

@@ -157,7 +157,7 @@ int pk_destroy(pk_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
-                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch, h->d_gang};
+                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch, h->d_gang, h->d_gridinfo};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -208,8 +208,9 @@ int pk_set_overlap(pk_handle* h, int enabled) {
 }
 
 int pk_set_predict_variant(pk_handle* h, int variant) {
-    if (!h || variant < 0 || variant > 3) return 1;
-    h->predict_variant = variant;
+    if (!h || variant < 0 || variant > 4) return 1;
+    h->predict_grid_mode = (variant == 4) ? 0 : 1;  // 4 = split pipeline with the grid detection switched off
+    h->predict_variant = (variant == 4) ? 3 : variant;
     return 0;
 }
 

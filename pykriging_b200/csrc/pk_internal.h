@@ -82,6 +82,8 @@ struct pk_handle {
     int64_t cap_q = 0;      // doubles in d_q
     int64_t cap_qout = 0;   // query points d_qout has room for (3 outputs each)
     double* d_hp = nullptr;   // 2 x PK_MAX_K (theta | p) for predict
+    int* d_gridinfo = nullptr;     // {period P, ok}: verdict of the device-side grid detection (pk_predict2.cu)
+    int predict_grid_mode = 1;     // 0: never use the grid-mode psi kernel (tests compare the two)
     double* d_pscratch = nullptr;  // psi slabs of predict_big_kernel (np > 2944): grid x 32 x (np + 4)
     size_t cap_pscratch = 0;
 };

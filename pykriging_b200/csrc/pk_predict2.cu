@@ -77,32 +77,35 @@ __device__ __forceinline__ void log2_split_rows(double d, const double* __restri
     lh_out = fmin(fmax(Ls, -L2_CLAMP), L2_CLAMP);
 }
 
+// The product is rounded on its own (__dmul_rn, as NumPy's theta * np.power(...) is) and never contracted into the
+// sum over dimensions: the generic and the grid-mode kernel add the same rounded terms in the same order.
 // theta_d |d|^p_d for one dimension.  mode: 0 = table-driven 2^(p log2 d) (p in [0.25, 3], not 1 or 2),
 // 1 = p == 1 (exact d), 2 = p == 2 (exact d*d, as np.power), 3 = any other exponent (range-checked path)
 __device__ __forceinline__ double pa_term_lean(double dd, double th, double p, const double* ltab, int bank,
                                                unsigned tab_saddr) {
     double lh, ll;
     log2_split_rows(dd, ltab, bank, lh, ll);
-    return th * exp2_lean4k(p, lh, ll, tab_saddr);
+    return __dmul_rn(th, exp2_lean4k(p, lh, ll, tab_saddr));
 }
 __device__ __forceinline__ double pa_term(double dd, double th, double p, int mode, const double* ltab, int bank,
                                           unsigned tab_saddr) {
     if (mode == 0) return pa_term_lean(dd, th, p, ltab, bank, tab_saddr);
-    if (mode == 2) return th * (dd * dd);
-    if (mode == 1) return th * dd;
+    if (mode == 2) return __dmul_rn(th, dd * dd);
+    if (mode == 1) return __dmul_rn(th, dd);
     double l0;
     float l1;
     log2_split(dd, l0, l1);
     const double s = p * l0;
     const double e = fma(p, (double)l1, fma(p, l0, -s));
-    return th * exp2_const(s, e);
+    return __dmul_rn(th, exp2_const(s, e));
 }
 
 template <int KK>
 __global__ void __launch_bounds__(PA_THREADS, 1)
 psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, const double* __restrict__ Xq,
                 const double* __restrict__ hp, const double* __restrict__ w, double mu, int xt_staged, int memo_dims,
-                double* __restrict__ psi_out, double* __restrict__ yhat_out) {
+                double* __restrict__ psi_out, double* __restrict__ yhat_out, const int* __restrict__ gridinfo) {
+    if (gridinfo && gridinfo[1]) return;  // the query set is a row-major grid: psi_rows_grid_kernel does this block
     extern __shared__ __align__(16) double pa_smem[];
     double* ltab = pa_smem;                                   // 3 x 64 x 16
     double* th_s = ltab + 3 * 64 * 16;                        // PK_MAX_K
@@ -234,6 +237,134 @@ psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, 
         }
         const double ys = warp_sum(ys0 + ys1);
         if (lane == 0 && yhat_out) yhat_out[q] = mu + ys;
+    }
+}
+
+// ---- kernel A, grid mode: the query set is a row-major tensor grid -----------------------------------------
+// plot / snapshot / the 4096 x 4096 EI grid of config C5 (krige.py:531-537, 699-708) evaluate a meshgrid: query
+// g = row * P + col has the leading coordinates of its row and the last coordinate of its column.  The exponent
+// then separates, S(g, r) = lead[row][r] + last[col][r] with lead = sum of the first k - 1 terms (left to right,
+// NumPy's order for k < 8) and last = theta |X_r - x|^p of the fast axis, and a CTA that owns an R x R patch of the
+// grid computes 2 R tables of np entries once and is left with ONE e^-S per (query, sample): (2 R np) pow instead of
+// (R^2 np k).  Same functions on the same inputs in the same order: bit-identical to psi_rows_kernel
+// (test_predict_grid_memoisation_is_exact).  The structure is DETECTED on the device (grid_period_kernel: P = length
+// of the first run of equal leading coordinates; grid_verify_kernel: every query equals its row's lead and its
+// column's last coordinate, exactly); the verdict stays in device memory -- both psi kernels are launched and the
+// one that does not apply returns at once, so the call stays asynchronous.
+__global__ void grid_init_kernel(int* info) {
+    info[0] = 0x7fffffff;  // P
+    info[1] = 1;           // ok
+}
+__global__ void grid_period_kernel(int k, int64_t m, const double* __restrict__ Xq, int* __restrict__ info) {
+    const int64_t lim = (m < ((int64_t)1 << 22)) ? m : ((int64_t)1 << 22);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < lim; i += (int64_t)gridDim.x * blockDim.x) {
+        bool differs = false;
+        for (int d = 0; d < k - 1; ++d) differs |= (Xq[i * k + d] != Xq[d]);
+        if (differs) {
+            atomicMin(info, (int)i);
+            return;  // later indices of this thread are larger
+        }
+    }
+}
+__global__ void grid_verify_kernel(int k, int64_t m, const double* __restrict__ Xq, int* __restrict__ info, int min_period) {
+    const int P = info[0];
+    if (P == 0x7fffffff || P < min_period) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) info[1] = 0;
+        return;
+    }
+    bool bad = false;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < m; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = g / P, col = g - row * P;
+        for (int d = 0; d < k - 1; ++d) bad |= (Xq[g * k + d] != Xq[row * P * k + d]);
+        bad |= (Xq[g * k + k - 1] != Xq[col * k + k - 1]);
+    }
+    if (bad) info[1] = 0;
+}
+
+constexpr int PG_RMAX = 16;
+__global__ void __launch_bounds__(PA_THREADS, 1)
+psi_rows_grid_kernel(int n, int np, int k, int64_t m, int64_t q0, int64_t mc, int R, const double* __restrict__ X,
+                     const double* __restrict__ Xq, const double* __restrict__ hp, const double* __restrict__ w, double mu,
+                     const int* __restrict__ gridinfo, double* __restrict__ psi_out, double* __restrict__ yhat_out) {
+    if (!gridinfo[1]) return;
+    const int P = gridinfo[0];
+    extern __shared__ __align__(16) double pa_smem[];
+    double* ltab = pa_smem;                                   // 3 x 64 x 16
+    double* th_s = ltab + 3 * 64 * 16;                        // PK_MAX_K
+    double* p_s = th_s + PK_MAX_K;                            // PK_MAX_K
+    int* mode_s = reinterpret_cast<int*>(p_s + PK_MAX_K);     // PK_MAX_K
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(pa_smem);
+    unsigned tab_saddr = (smem_base + pa_small_bytes(0, 0) + 0x7fffu) & ~0x7fffu;
+    double* tab4k = pa_smem + (tab_saddr - smem_base) / sizeof(double);
+    double* lead_t = tab4k + 4096;                            // R x np
+    double* last_t = lead_t + (size_t)R * np;                 // R x np
+    fill_exp2_4096(tab4k, tid, PA_THREADS);
+    fill_log2_tables(ltab, tid, PA_THREADS);
+    if (tid < k) {
+        const double pd = hp[PK_MAX_K + tid];
+        th_s[tid] = hp[tid];
+        p_s[tid] = pd;
+        mode_s[tid] = (pd == 1.0) ? 1 : (pd == 2.0) ? 2 : (pd >= 0.25 && pd <= 3.0) ? 0 : 3;
+    }
+    const int bank = tid & 15;
+    const int64_t row_lo = q0 / P, row_hi = (q0 + mc - 1) / P;
+    const int nrp = (int)((row_hi - row_lo + R) / R), ncp = (P + R - 1) / R;
+    const int nit = np / 32;
+    for (int patch = blockIdx.x; patch < nrp * ncp; patch += gridDim.x) {
+        const int64_t row0 = row_lo + (int64_t)(patch / ncp) * R;
+        const int col0 = (patch % ncp) * R;
+        __syncthreads();  // tables of the previous patch are no longer read (first pass: th / p / mode are in place)
+        for (int e = tid; e < 2 * R * np; e += PA_THREADS) {
+            const int which = e / (R * np), rem = e - which * R * np;
+            const int idx = rem / np, r = rem - idx * np;
+            double v = 0.0;
+            if (r < n) {
+                if (which == 0) {
+                    const int64_t g = (row0 + idx) * P;  // first query of the row
+                    if (g < m) {
+                        const double* xq = Xq + g * k;
+                        for (int d = 0; d < k - 1; ++d)
+                            v += pa_term(fabs(__ldg(X + (size_t)r * k + d) - __ldg(xq + d)), th_s[d], p_s[d], mode_s[d], ltab, bank,
+                                         tab_saddr);
+                    }
+                } else {
+                    const int col = col0 + idx;
+                    if (col < P && col < m) {
+                        const int d = k - 1;
+                        v = pa_term(fabs(__ldg(X + (size_t)r * k + d) - __ldg(Xq + (size_t)col * k + d)), th_s[d], p_s[d], mode_s[d], ltab,
+                                    bank, tab_saddr);
+                    }
+                }
+            }
+            (which == 0 ? lead_t : last_t)[idx * np + r] = v;
+        }
+        __syncthreads();
+        for (int qi = warp; qi < R * R; qi += PA_WARPS) {
+            const int ri = qi / R, ci = qi - ri * R;
+            const int col = col0 + ci;
+            const int64_t g = (row0 + ri) * P + col;
+            if (col >= P || g < q0 || g >= q0 + mc) continue;  // warp uniform
+            const double* lt = lead_t + ri * np;
+            const double* ct = last_t + ci * np;
+            double ys0 = 0.0, ys1 = 0.0;
+            double* prow = psi_out ? psi_out + (size_t)(g - q0) * np : nullptr;
+            for (int it = 0; it < nit; it += 2) {
+                const int r0 = it * 32 + lane, r1 = r0 + 32;
+                const int c0 = min(r0, n - 1), c1 = min(r1, n - 1);
+                double v0 = expneg_4k(lt[c0] + ct[c0], tab_saddr), v1 = expneg_4k(lt[c1] + ct[c1], tab_saddr);
+                v0 = (r0 < n) ? v0 : 0.0;
+                v1 = (r1 < n) ? v1 : 0.0;
+                ys0 = fma(v0, __ldg(w + c0), ys0);
+                ys1 = fma(v1, __ldg(w + c1), ys1);
+                if (prow) {
+                    prow[r0] = v0;
+                    prow[r1] = v1;
+                }
+            }
+            const double ys = warp_sum(ys0 + ys1);
+            if (lane == 0 && yhat_out) yhat_out[g - q0] = mu + ys;
+        }
     }
 }
 
@@ -476,7 +607,7 @@ static cudaError_t encode_2d(CUtensorMap* tmap, const double* base, uint64_t col
 
 template <int KK>
 static cudaError_t launch_psi_rows(pk_handle* h, int64_t mc, const double* Xq, const double* hp, double mu,
-                                   double* psi_out, double* yhat_out) {
+                                   double* psi_out, double* yhat_out, const int* gridinfo) {
     const int k = h->k, np = h->fit_np;
     const int xt = (k * np <= PA_XT_MAX) ? 1 : 0;
     // memoised leading dimensions (compile-time k only): as many of the first k - 1 as fit beside the tables
@@ -500,7 +631,7 @@ static cudaError_t launch_psi_rows(pk_handle* h, int64_t mc, const double* Xq, c
     const int64_t want = (mc + PA_WARPS - 1) / PA_WARPS;
     const int grid = (int)((want < (int64_t)h->sm_count) ? want : (int64_t)h->sm_count);
     psi_rows_kernel<KK><<<grid, PA_THREADS, smem, h->stream>>>(h->n, np, k, mc, h->dX, Xq, hp, h->d_w, mu, xt, memo_dims,
-                                                               psi_out, yhat_out);
+                                                               psi_out, yhat_out, gridinfo);
     h->launches++;
     return cudaGetLastError();
 }
@@ -541,15 +672,49 @@ cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, cons
             attr_done = true;
         }
     }
+    // row-major tensor grid?  (2 <= k < 8: the separated exponent needs NumPy's left-to-right summation)
+    int* gridinfo = nullptr;
+    int R = 0;
+    if (k >= 2 && k < 8 && h->predict_grid_mode) {
+        R = (int)(((size_t)128 * 1024) / ((size_t)2 * np * sizeof(double)));
+        if (R > PG_RMAX) R = PG_RMAX;
+        if (R >= 2) {
+            if (!h->d_gridinfo) {
+                cudaError_t e = cudaMalloc((void**)&h->d_gridinfo, 2 * sizeof(int));
+                if (e != cudaSuccess) return e;
+            }
+            gridinfo = h->d_gridinfo;
+            grid_init_kernel<<<1, 1, 0, h->stream>>>(gridinfo);
+            grid_period_kernel<<<2 * h->sm_count, 256, 0, h->stream>>>(k, m, Xq, gridinfo);
+            grid_verify_kernel<<<4 * h->sm_count, 256, 0, h->stream>>>(k, m, Xq, gridinfo, 2 * R);
+            h->launches += 3;
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaError_t e = cudaFuncSetAttribute(psi_rows_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                if (e != cudaSuccess) return e;
+                attr_done = true;
+            }
+        }
+    }
     for (int64_t q0 = 0; q0 < m; q0 += mcap) {
         const int64_t mc = (m - q0 < mcap) ? (m - q0) : mcap;
         double* yh = yhat ? yhat + q0 : ytmp;
         cudaError_t e;
+        if (gridinfo) {
+            // table + small arrays as in psi_rows_kernel (64 KB with the alignment slack) + the 2 R patch tables
+            const size_t smem = ((pa_small_bytes(0, 0) + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000 +
+                                (size_t)2 * R * np * sizeof(double);
+            psi_rows_grid_kernel<<<h->sm_count, PA_THREADS, smem, h->stream>>>(h->n, np, k, m, q0, mc, R, h->dX, Xq, hp, h->d_w, mu,
+                                                                              gridinfo, need_s ? psi : nullptr, yh);
+            h->launches++;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
         switch (k) {
-#define PK_PA(KK_) case KK_: e = launch_psi_rows<KK_>(h, mc, Xq + q0 * k, hp, mu, need_s ? psi : nullptr, yh); break;
+#define PK_PA(KK_) case KK_: e = launch_psi_rows<KK_>(h, mc, Xq + q0 * k, hp, mu, need_s ? psi : nullptr, yh, gridinfo); break;
             PK_PA(1) PK_PA(2) PK_PA(3)
 #undef PK_PA
-            default: e = launch_psi_rows<0>(h, mc, Xq + q0 * k, hp, mu, need_s ? psi : nullptr, yh); break;
+            default: e = launch_psi_rows<0>(h, mc, Xq + q0 * k, hp, mu, need_s ? psi : nullptr, yh, gridinfo); break;
         }
         if (e != cudaSuccess) return e;
         if (!need_s) continue;

@@ -316,7 +316,7 @@ def test_predict_split_pipeline_general_k(handle, n, k, special):
     assert np.array_equal(only_s["s"], got["s"])
 
 
-@pytest.mark.parametrize("k,side", [(2, 70), (3, 17)])
+@pytest.mark.parametrize("k,side", [(2, 70), (3, 17), (3, 40)])
 def test_predict_grid_memoisation_is_exact(handle, k, side):
     """Row-major grids (plot / snapshot / the EI grid of config C5) reuse the leading-dimension terms of the previous
     query point in the psi rows kernel.  The same points in shuffled order (no reuse) must give bit-identical
@@ -339,6 +339,24 @@ def test_predict_grid_memoisation_is_exact(handle, k, side):
     b = handle.predict_batch(np.ascontiguousarray(grid[perm]), theta, p, out4[1], out4[2], y_min=y_min)
     for name in ("yhat", "s", "ei"):
         assert np.array_equal(a[name][perm], b[name]), name
+    # the same grid with the device-side grid detection switched off (memoised leading dimensions only), and a grid
+    # whose last row is incomplete / a grid with one perturbed point (detection must reject it, results unchanged)
+    handle.set_predict_variant(4)
+    try:
+        c = handle.predict_batch(grid, theta, p, out4[1], out4[2], y_min=y_min)
+    finally:
+        handle.set_predict_variant(0)
+    for name in ("yhat", "s", "ei"):
+        assert np.array_equal(a[name], c[name]), name
+    cut = len(grid) - side // 2
+    d = handle.predict_batch(np.ascontiguousarray(grid[:cut]), theta, p, out4[1], out4[2], y_min=y_min)
+    broken = grid.copy()
+    broken[len(grid) // 2, k - 1] += 1e-3
+    e = handle.predict_batch(broken, theta, p, out4[1], out4[2], y_min=y_min)
+    keep = np.arange(len(grid)) != len(grid) // 2
+    for name in ("yhat", "s", "ei"):
+        assert np.array_equal(d[name], a[name][:cut]), name
+        assert np.array_equal(e[name][keep], a[name][keep]), name
     ref = onp.predict_batch_fast(Xn, yn, theta, p, onp.EPS_DIAG, grid, y_min=y_min)
     cond = np.linalg.cond(onp.psi_fast(Xn, theta, p))
     assert np.max(np.abs(a["yhat"] - ref["yhat"])) < max(1e-9, 50.0 * cond * 2.2e-16)
