@@ -12,4 +12,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:chol_cta -c 1 -o gpurun_out/prof_chol_cta_r01_$T -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-predictions > gpurun_out/ncu_${T}1.log 2>&1; tail -1 gpurun_out/ncu_${T}1.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:psi_pop -c 1 -o gpurun_out/prof_psi_pop_r01_$T -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-predictions > gpurun_out/ncu_${T}2.log 2>&1; tail -1 gpurun_out/ncu_${T}2.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:trinorm -c 1 -s 2 -o gpurun_out/prof_trinorm_r01_$T -f python tools/predict_probe.py > gpurun_out/ncu_${T}3.log 2>&1; tail -1 gpurun_out/ncu_${T}3.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:psi_rows -c 1 -s 2 -o gpurun_out/prof_psi_rows_r01_$T -f python tools/predict_probe.py > gpurun_out/ncu_${T}4.log 2>&1; tail -1 gpurun_out/ncu_${T}4.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:psi_rows_grid -c 1 -s 20 -o gpurun_out/prof_psi_rows_grid_r01_$T -f env PK_PROBE_TIME=1 PK_PROBE_REPS=1 python tools/predict_probe.py > gpurun_out/ncu_${T}4.log 2>&1; tail -1 gpurun_out/ncu_${T}4.log
