@@ -877,7 +877,8 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         cudaError_t e = make_ws_tensor_map(&tmap, ws, s, C);
         if (e != cudaSuccess) return e;
     }
-    static bool attr_done = false;
+    static bool attr_done_dev[PK_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     if (!attr_done) {
         cudaError_t e =
             cudaFuncSetAttribute(cta::chol_cta_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -10,6 +10,7 @@
 #include "pk_common.cuh"
 
 constexpr int PK_QUEUE_SLOTS = 64;
+constexpr int PK_MAX_DEVICES = 64;  // per-device "function attributes set" flags (cudaFuncSetAttribute is per device)
 
 struct pk_handle {
     int device = 0;

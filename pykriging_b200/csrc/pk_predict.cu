@@ -843,7 +843,8 @@ static cudaError_t launch_predict_reg_k(pk_handle* h, int64_t m, const double* X
     const size_t smem = sizeof(double) * (64 * 16 + 3 * 64 * 16 + 2 * PR_QT * PR_ALD + 2 * PR_QT * ((k + 1) & ~1) +
                                           2 * PK_MAX_K + 2 * PR_WARPS * PR_QT + 2 * PR_WARPS * (PR_QT + 1) + 16 +
                                           2 * PR_WARPS * NTW * 128 + xs);
-    static bool attr_done = false;
+    static bool attr_done_dev[PK_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(predict_reg_kernel<NTW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024);

@@ -622,7 +622,8 @@ static cudaError_t launch_psi_rows(pk_handle* h, int64_t mc, const double* Xq, c
     // the base lies (same sizing rule as psi_pop_kernel)
     const size_t smem =
         ((pa_small_bytes(xt ? k * np : 0, PA_WARPS * memo_dims * np) + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000;
-    static bool attr_done = false;
+    static bool attr_done_dev[PK_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(psi_rows_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
@@ -665,7 +666,8 @@ cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, cons
     if (need_s) {
         cudaError_t e = tn::encode_2d(&tmapB, h->d_linv, (uint64_t)np, (uint64_t)np);
         if (e != cudaSuccess) return e;
-        static bool attr_done = false;
+        static bool attr_done_dev[PK_MAX_DEVICES] = {};
+        bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
         if (!attr_done) {
             e = cudaFuncSetAttribute(tn::trinorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
             if (e != cudaSuccess) return e;
@@ -688,7 +690,8 @@ cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, cons
             grid_period_kernel<<<2 * h->sm_count, 256, 0, h->stream>>>(k, m, Xq, gridinfo);
             grid_verify_kernel<<<4 * h->sm_count, 256, 0, h->stream>>>(k, m, Xq, gridinfo, 2 * R);
             h->launches += 3;
-            static bool attr_done = false;
+            static bool attr_done_dev[PK_MAX_DEVICES] = {};
+            bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
             if (!attr_done) {
                 cudaError_t e = cudaFuncSetAttribute(psi_rows_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
                 if (e != cudaSuccess) return e;

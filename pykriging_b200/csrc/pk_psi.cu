@@ -247,7 +247,8 @@ __global__ void debug_math_kernel(int64_t m, const double* __restrict__ d, const
 
 cudaError_t launch_debug_math(pk_handle* h, int64_t m, const double* d, const double* p, double* out_pow,
                               double* out_expneg) {
-    static bool attr_done = false;
+    static bool attr_done_dev[PK_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(debug_math_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 0x10000);
         if (e != cudaSuccess) return e;
@@ -273,7 +274,8 @@ static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, cons
     // dynamic shared memory starts 1 KB into the CTA's window (the first KB is reserved by the system): room for
     // the table at the next 32 KB boundary wherever the base actually lies
     constexpr size_t smem = ((psi_small_bytes<K, PPT>() + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000;
-    static bool attr_done = false;
+    static bool attr_done_dev[PK_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(psi_pop_kernel<K, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

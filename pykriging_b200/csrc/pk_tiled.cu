@@ -554,7 +554,8 @@ cudaError_t launch_aug_init(pk_handle* h, const TiledShape& s, int C, double* ws
 cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     const int nt = s.np / PK_TILE;
     const size_t smem = sizeof(double) * (size_t)SMEM_DOUBLES;
-    static bool attr_done = false;
+    static bool attr_done_dev[PK_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(chol_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -640,3 +640,39 @@ def test_predict_device_and_host_paths_agree(handle):
     # EI is a difference of two tiny terms far from the optimum: rounding can leave it a hair below zero,
     # exactly as the reference formula does (krige.py:212-217)
     assert np.all(host["s"] >= 0) and np.all(host["ei"] >= -1e-12)
+
+
+def test_two_devices_in_one_process():
+    """One handle per GPU in the SAME process (function attributes such as the opt-in shared-memory size are per
+    device): both devices must run every large-shared-memory kernel and agree bit for bit."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from pykriging_b200._lib import Handle
+
+    X = onp.rlh(400, 3, 51)
+    y = onp.f_squared(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    cands = onp.candidates_loguniform(200, 3, 52, lo=-2.0, hi=1.0)
+    th, p = np.ascontiguousarray(cands[:, :3]), np.ascontiguousarray(cands[:, 3:])
+    Xq = np.random.default_rng(53).uniform(0, 1, (5000, 3))
+    res = []
+    for dev in (1, 0):  # device 1 first: nothing may rely on device 0 having been set up
+        h = Handle(dev)
+        try:
+            h.set_data(Xn, yn)
+            pop = h.nll_batch(th, p)            # persistent Cholesky
+            few = h.nll_batch(th[:5], p[:5])    # gang mode
+            out4, info = h.fit(th[0], p[0])
+            assert info == 0
+            pred = h.predict_batch(Xq, th[0], p[0], out4[1], out4[2], y_min=0.0)     # split pipeline
+            small = h.predict_batch(Xq[:100], th[0], p[0], out4[1], out4[2], y_min=0.0)  # fused kernel
+            res.append((pop, few, out4, pred, small))
+        finally:
+            h.close()
+    a, b = res
+    for name in ("nll", "mu", "sigma2", "lndet"):
+        assert np.array_equal(a[0][name], b[0][name], equal_nan=True) and np.array_equal(a[1][name], b[1][name], equal_nan=True)
+    assert np.array_equal(a[2], b[2])
+    for name in ("yhat", "s", "ei"):
+        assert np.array_equal(a[3][name], b[3][name]) and np.array_equal(a[4][name], b[4][name])
