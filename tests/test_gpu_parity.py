@@ -642,6 +642,77 @@ def test_predict_device_and_host_paths_agree(handle):
     assert np.all(host["s"] >= 0) and np.all(host["ei"] >= -1e-12)
 
 
+def test_edge_cases_empty_tiny_wide_duplicate_nan(handle):
+    """Edges of the domain: an empty population / query set, n = 2 and n = 3 samples, k = 24 design variables (beyond the
+    compile-time Psi kernels) in the fused and in the tiled path, duplicated sample points and a NaN
+    hyper-parameter."""
+    rng = np.random.default_rng(61)
+    # empty inputs
+    X = onp.rlh(50, 2, 61)
+    Xn, yn, _, _ = onp.normalize_data(X, onp.f_branin(X))
+    handle.set_data(Xn, yn)
+    out = handle.nll_batch(np.zeros((0, 2)), np.zeros((0, 2)))
+    assert out["nll"].shape == (0,) and out["info"].shape == (0,)
+    out4, info = handle.fit(np.array([1.0, 1.0]), np.array([1.5, 1.5]))
+    assert info == 0
+    pr = handle.predict_batch(np.zeros((0, 2)), np.array([1.0, 1.0]), np.array([1.5, 1.5]), out4[1], out4[2])
+    assert pr["yhat"].shape == (0,)
+    # tiny models
+    for n in (2, 3):
+        Xs, ys = Xn[:n], (yn[:n] - yn[:n].min()) / (yn[:n].max() - yn[:n].min())
+        handle.set_data(Xs, ys)
+        c = onp.candidates_uniform(4, 2, 62)
+        got = handle.nll_batch(c[:, :2], c[:, 2:])
+        for i in range(4):
+            nll, mu, s2, lndet, inf = onp.neglikelihood_fast(onp.psi_fast(Xs, c[i, :2], c[i, 2:]), ys)
+            assert inf == 0 and got["info"][i] == 0
+            # sigma2 <= 0 by round-off gives NaN / -inf in the reference too (matrixops.py:56)
+            if np.isfinite(nll):
+                assert rel_err(got["nll"][i], nll) < 1e-9 and rel_err(got["mu"][i], mu) < 1e-9
+    # k = 24: fused small-n kernel (n = 100) and tiled path (n = 200)
+    for n in (100, 200):
+        k = 24
+        Xw = onp.rlh(n, k, 63)
+        yw = onp.f_squared(Xw)
+        Xwn, ywn, _, _ = onp.normalize_data(Xw, yw)
+        handle.set_data(Xwn, ywn)
+        c = onp.candidates_loguniform(6, k, 64, lo=-2.0, hi=0.0)
+        got = handle.nll_batch(c[:, :k], c[:, k:])
+        for i in range(6):
+            Psi = onp.psi_fast(Xwn, c[i, :k], c[i, k:])
+            nll, mu, s2, lndet, inf = onp.neglikelihood_fast(Psi, ywn)
+            assert inf == 0 and got["info"][i] == 0
+            tol = tol_for_cond(np.linalg.cond(Psi))
+            assert rel_err(got["nll"][i], nll) < tol and rel_err(got["mu"][i], mu) < tol and rel_err(got["sigma2"][i], s2) < tol
+        out4, info = handle.fit(c[0, :k], c[0, k:])
+        assert info == 0
+        Xq = rng.uniform(0, 1, (300, k))
+        ref = onp.predict_batch_fast(Xwn, ywn, c[0, :k], c[0, k:], onp.EPS_DIAG, Xq, y_min=0.0)
+        pr = handle.predict_batch(Xq, c[0, :k], c[0, k:], out4[1], out4[2], y_min=0.0)
+        assert np.max(np.abs(pr["yhat"] - ref["yhat"])) < 1e-8
+    # duplicated sample points: Psi is singular up to the eps nugget (cond ~ 1/eps, the knife edge of DESIGN.md's
+    # "failure parity": dpotrf happens to succeed with pivots of a few ulps) -- the candidate must either be
+    # reported as failed or produce finite scalars, never an error status; and a NaN hyper-parameter never yields a
+    # finite likelihood (n = 150: tiled path; n = 60: fused kernel)
+    for n in (60, 150):
+        Xd = onp.rlh(n, 3, 65)
+        Xd[n - 1] = Xd[0]
+        yd = onp.f_squared(Xd)
+        Xdn, ydn, _, _ = onp.normalize_data(Xd, yd)
+        handle.set_data(Xdn, ydn)
+        c = onp.candidates_uniform(3, 3, 66)
+        got = handle.nll_batch(c[:, :3], c[:, 3:])
+        for i in range(3):
+            assert got["info"][i] > 0 or np.isfinite(got["mu"][i])
+        Xok = onp.rlh(n, 3, 67)
+        Xokn, yokn, _, _ = onp.normalize_data(Xok, onp.f_squared(Xok))
+        handle.set_data(Xokn, yokn)
+        c[1, 0] = np.nan
+        got = handle.nll_batch(c[:, :3], c[:, 3:])
+        assert got["info"][0] == 0 and got["info"][2] == 0
+        assert got["info"][1] > 0 or not np.isfinite(got["nll"][1])  # never a finite likelihood
+
+
 def test_two_devices_in_one_process():
     """One handle per GPU in the SAME process (function attributes such as the opt-in shared-memory size are per
     device): both devices must run every large-shared-memory kernel and agree bit for bit."""
