@@ -27,8 +27,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_SAMPLES, K_DIMS, POP = 1024, 10, 1024
-METRIC = "FP64 NegLnLike evals/sec at n=1024,k=10"
+# BASELINE.json's metric, verbatim; `value` is its first half (likelihood evaluations/s), the second half
+# (predictions/s) is reported in the same line under "predictions"
+METRIC = "FP64 NegLnLike evals/sec at n=1024,k=10 and predictions/sec, 1/2/4/8 B200"
 UNIT = "evals/s"
+PSI_FP64_PER_ENTRY = 103  # FP64 instructions of psi_pop_kernel<10,1> per Psi entry (SASS count: 72 DFMA + 15 DMUL + 14 DADD + 2 DSETP)
 
 
 # ---- synthetic workload (no oracle import: this is the measured path's input) ---------------------------
@@ -212,6 +215,30 @@ def cpu_reference_evals(n_cands, seeds):
     return out
 
 
+def cpu_reference_predictions(n_points):
+    """predictions/s of the reference's per-point path (predict + predict_var + expimp per query point: the Python
+    loop over the samples and the dgesv solves of matrixops.py:68-95, krige.py:201-234) on `n_points` points of the
+    C5 grid, n = 512 model, oracle port in reference order."""
+    from oracle import oracle_np as onp
+
+    X, y = make_branin_samples(PRED_N)
+    model = onp.OracleKriging(X, y)
+    model.update([5.0, 5.0, 1.8, 1.8])
+    model.neglikelihood()
+    ax = np.linspace(0.0, 1.0, PRED_GRID)
+    idx = np.linspace(0, PRED_GRID * PRED_GRID - 1, n_points).astype(np.int64)
+    pts = np.stack([ax[idx // PRED_GRID], ax[idx % PRED_GRID]], axis=1)
+    t0 = time.perf_counter()
+    for x in pts:
+        model.predict(x)
+        model.predict_var(x)
+        model.expimp(x)
+    secs = time.perf_counter() - t0
+    return {"value": n_points / secs, "unit": "predictions/s", "points": int(n_points), "n": PRED_N, "k": PRED_K,
+            "outputs": "yhat, s, EI per point",
+            "sample": "%d points of the 4096 x 4096 grid, one at a time as the reference does" % n_points}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -222,6 +249,7 @@ def run_reference(args, rank):
     evals = sum(e for _, e in timed)
     value = evals / secs
     cores = os.cpu_count()
+    pred = cpu_reference_predictions(24)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -231,6 +259,7 @@ def run_reference(args, rank):
                                        "families), NumPy/OpenBLAS oracle port of matrixops.py:24-56 with all host "
                                        "threads" % (sample, POP)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "predictions": pred,
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -381,20 +410,22 @@ def run_ours(args, rank, world, local_rank):
                                    "switched off (pk_set_profiling) so that the duration is the kernel's own"
                                    % args.steps,
                          "phase_ms_per_step": {kk: v / args.steps for kk, v in phases.items()}},
-            "roofline_psi": {"kernel": "psi_pop_kernel<10,2>", "bound": "hbm", "achieved": psi_gbs, "peak": hbm_peak,
+            "roofline_psi": {"kernel": "psi_pop_kernel<10,1>", "bound": "hbm", "achieved": psi_gbs, "peak": hbm_peak,
                              "unit": "GB/s", "frac": (psi_gbs / hbm_peak) if psi_gbs else None,
                              "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)",
                              "algorithmic": "8 B per lower-triangle tile entry written; FP64-ALU bound for general p "
-                                            "(10 table-driven 2^x + 1 e^-S per entry = 106 FP64 instructions, see fp64_pipe_frac); "
+                                            "(10 table-driven 2^x + 1 e^-S per entry = 103 FP64 instructions, see fp64_pipe_frac); "
                                             "issue bound: an FP64 instruction takes two dispatch cycles",
-                             "fp64_instr_per_entry": 10 * 9 + 7 + 9,
-                             "fp64_pipe_frac": ((10 * 9 + 7 + 9) * (n * (n - 1) / 2) * C * args.steps * 2.0 /
+                             "fp64_instr_per_entry": PSI_FP64_PER_ENTRY,
+                             "fp64_pipe_frac": (PSI_FP64_PER_ENTRY * (n * (n - 1) / 2) * C * args.steps * 2.0 /
                                                 (phases["psi"] * 1e-3) * 1e-12 / peak["dfma_tflops"])
                              if phases["psi"] > 0 else None},
             "predictions": pred,
             "fp64_peak": peak, "failed_factorisations_last_step": fails,
         }
         if world == 1 and not args.no_cpu_baseline:
+            if pred is not None:
+                pred["cpu_baseline"] = cpu_reference_predictions(24)
             res = cpu_reference_evals(CPU_BASELINE_SAMPLE, [0])
             secs, ev = res[0]
             line["cpu_baseline"] = {"value": ev / secs, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
