@@ -162,6 +162,7 @@ int pk_destroy(pk_handle* h) {
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_pipe) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_pred) cudaEventDestroy(e);
     if (h->stream2) {
         cudaStreamSynchronize(h->stream2);
         cudaStreamDestroy(h->stream2);
@@ -568,35 +569,66 @@ int pk_predict_batch(pk_handle* h, int64_t m, const double* Xq, const double* th
         pk::phase_end(h);
         return 0;
     }
-    // host path: stream the queries through a device staging buffer in chunks
-    const int64_t chunk = m < ((int64_t)1 << 22) ? m : ((int64_t)1 << 22);
-    if (chunk * k > h->cap_q) {
+    // Host path: the queries stream through device staging buffers in chunks of 1 Mi points, double buffered -- the
+    // upload of chunk c+1 and the download of chunk c-1 (copy stream) run under the kernels of chunk c (main stream).
+    const int64_t chunk = m < ((int64_t)1 << 20) ? m : ((int64_t)1 << 20);
+    const int nbuf = (m > chunk) ? 2 : 1;
+    if (!q_dev && nbuf * chunk * k > h->cap_q) {
         PK_CUDA(h, cudaStreamSynchronize(h->stream));
-        PK_CUDA(h, regrow(&h->d_q, (size_t)chunk * k));
-        h->cap_q = chunk * k;
+        PK_CUDA(h, regrow(&h->d_q, (size_t)nbuf * chunk * k));
+        h->cap_q = nbuf * chunk * k;
     }
-    if (chunk > h->cap_qout) {  // sized on its own: k may have changed since the query buffer last grew
+    if (nbuf * chunk > h->cap_qout) {  // sized on its own: k may have changed since the query buffer last grew
         PK_CUDA(h, cudaStreamSynchronize(h->stream));
-        PK_CUDA(h, regrow(&h->d_qout, (size_t)chunk * 3));
-        h->cap_qout = chunk;
+        PK_CUDA(h, regrow(&h->d_qout, (size_t)nbuf * chunk * 3));
+        h->cap_qout = nbuf * chunk;
     }
-    for (int64_t q0 = 0; q0 < m; q0 += chunk) {
-        const int64_t mc = (m - q0 < chunk) ? (m - q0) : chunk;
-        const double* xq_d = Xq + q0 * k;
+    while (h->ev_pred.size() < 7) {
+        cudaEvent_t ev;
+        PK_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->ev_pred.push_back(ev);
+    }
+    cudaEvent_t* ev_in = h->ev_pred.data();        // [2] chunk uploaded
+    cudaEvent_t* ev_done = h->ev_pred.data() + 2;  // [2] chunk computed
+    cudaEvent_t* ev_free = h->ev_pred.data() + 4;  // [2] chunk downloaded: its output buffer may be overwritten
+    // the copy stream starts behind everything already queued on the main stream (hyper-parameters, w)
+    PK_CUDA(h, cudaEventRecord(h->ev_pred[6], h->stream));
+    PK_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_pred[6], 0));
+    const int64_t nchunks = (m + chunk - 1) / chunk;
+    auto upload = [&](int64_t c) -> cudaError_t {
+        const int b = (int)(c % nbuf);
+        const int64_t q0 = c * chunk, mc = (m - q0 < chunk) ? (m - q0) : chunk;
         if (!q_dev) {
-            PK_CUDA(h, cudaMemcpyAsync(h->d_q, Xq + q0 * k, sizeof(double) * mc * k, cudaMemcpyDefault, h->stream));
-            xq_d = h->d_q;
+            cudaError_t e = cudaMemcpyAsync(h->d_q + (size_t)b * chunk * k, Xq + q0 * k, sizeof(double) * mc * k,
+                                            cudaMemcpyDefault, h->stream2);
+            if (e != cudaSuccess) return e;
         }
-        double* o0 = yhat ? h->d_qout : nullptr;
-        double* o1 = s ? h->d_qout + chunk : nullptr;
-        double* o2 = ei ? h->d_qout + 2 * chunk : nullptr;
+        return cudaEventRecord(ev_in[b], h->stream2);
+    };
+    PK_CUDA(h, upload(0));
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c % nbuf);
+        const int64_t q0 = c * chunk, mc = (m - q0 < chunk) ? (m - q0) : chunk;
+        // next upload first: on the copy stream it sits in front of this chunk's download, which waits for the kernels
+        if (c + 1 < nchunks) PK_CUDA(h, upload(c + 1));
+        const double* xq_d = q_dev ? Xq + q0 * k : h->d_q + (size_t)b * chunk * k;
+        double* ob = h->d_qout + (size_t)b * 3 * chunk;
+        double* o0 = yhat ? ob : nullptr;
+        double* o1 = s ? ob + chunk : nullptr;
+        double* o2 = ei ? ob + 2 * chunk : nullptr;
+        PK_CUDA(h, cudaStreamWaitEvent(h->stream, ev_in[b], 0));
+        if (c >= nbuf) PK_CUDA(h, cudaStreamWaitEvent(h->stream, ev_free[b], 0));
         pk::phase_begin(h, 3);
         PK_CUDA(h, pk::launch_predict(h, mc, xq_d, h->d_hp, mu, sigma2, y_min, ei_weight, var_extra, o0, o1, o2));
         pk::phase_end(h);
-        if (yhat) PK_CUDA(h, cudaMemcpyAsync(yhat + q0, o0, sizeof(double) * mc, cudaMemcpyDefault, h->stream));
-        if (s) PK_CUDA(h, cudaMemcpyAsync(s + q0, o1, sizeof(double) * mc, cudaMemcpyDefault, h->stream));
-        if (ei) PK_CUDA(h, cudaMemcpyAsync(ei + q0, o2, sizeof(double) * mc, cudaMemcpyDefault, h->stream));
+        PK_CUDA(h, cudaEventRecord(ev_done[b], h->stream));
+        PK_CUDA(h, cudaStreamWaitEvent(h->stream2, ev_done[b], 0));
+        if (yhat) PK_CUDA(h, cudaMemcpyAsync(yhat + q0, o0, sizeof(double) * mc, cudaMemcpyDefault, h->stream2));
+        if (s) PK_CUDA(h, cudaMemcpyAsync(s + q0, o1, sizeof(double) * mc, cudaMemcpyDefault, h->stream2));
+        if (ei) PK_CUDA(h, cudaMemcpyAsync(ei + q0, o2, sizeof(double) * mc, cudaMemcpyDefault, h->stream2));
+        PK_CUDA(h, cudaEventRecord(ev_free[b], h->stream2));
     }
+    PK_CUDA(h, cudaStreamSynchronize(h->stream2));
     PK_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

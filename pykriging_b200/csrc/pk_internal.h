@@ -36,6 +36,7 @@ struct pk_handle {
     // kernels are issued on stream2, the factorisations on stream, ordered by events (pk_nll_batch)
     cudaStream_t stream2 = nullptr;
     std::vector<cudaEvent_t> ev_pipe;
+    std::vector<cudaEvent_t> ev_pred;       // upload / compute / download events of the chunked host path of pk_predict_batch
     int overlap = 0;                       // 1: two-part pipeline on two streams (pk_set_overlap; measured slower, off)
 
     // model data (pk_set_data)
