@@ -100,3 +100,45 @@ def test_single_process_passthrough():
     rows = sharding.sharded_rows(5, lambda lo, hi: np.arange(lo, hi, dtype=float)[:, None] * np.ones((1, 3)))
     assert rows.shape == (5, 3) and rows[4, 2] == 4.0
     assert sharding.global_argmax(np.array([1.0, 5.0, 5.0]), 10) == (5.0, 11)
+
+
+def test_sharded_paths_bracket_their_slice_with_the_shard_hint():
+    """The sharded glue of matrixops tells the handle the size of the WHOLE population / query set before it
+    evaluates its slice and clears the hint afterwards (kernel selection then follows the whole: bit-identical
+    shards), also when the evaluation raises.  Fake handle, single process (no process group: one slice)."""
+    from pykriging_b200.matrixops import matrixops
+
+    class FakeHandle(object):
+        def __init__(self):
+            self.log = []
+
+        def set_shard_hint(self, population=0, query_points=0):
+            self.log.append(("hint", int(population), int(query_points)))
+
+        def nll_batch(self, theta, p, lam, mode):
+            self.log.append(("nll", theta.shape[0]))
+            z = np.zeros(theta.shape[0])
+            return {"nll": z, "mu": z, "sigma2": z, "lndet": z, "info": np.zeros(theta.shape[0], dtype=np.int32)}
+
+        def predict_batch(self, Xq, theta, pl, mu, s2, y_min=0.0, ei_weight=-1.0, var_extra=0.0, want=("yhat", "s", "ei")):
+            self.log.append(("predict", Xq.shape[0]))
+            if Xq.shape[0] == 7:
+                raise RuntimeError("boom")
+            return {nm: (np.zeros(Xq.shape[0]) if nm in want else None) for nm in ("yhat", "s", "ei")}
+
+    m = matrixops.__new__(matrixops)
+    fake = FakeHandle()
+    m.__dict__["_pk_handle"] = lambda: fake
+    m.__dict__["_pk_shard"] = (None, 1)
+    m.__dict__.update(_has_U=True, _pending_factor=None, mu=0.5, SigmaSqr=1.0, theta=np.ones(2), pl=np.ones(2) * 2, k=2)
+    out = m._pk_nll_population(np.ones((13, 2)), np.ones((13, 2)), None, 0)
+    assert out["nll"].shape == (13,)
+    assert fake.log == [("hint", 13, 0), ("nll", 13), ("hint", 0, 0)]
+    fake.log.clear()
+    batched = m._pk_predict
+    batched(np.zeros((11, 2)), ("yhat",))
+    assert fake.log == [("hint", 0, 11), ("predict", 11), ("hint", 0, 0)]
+    fake.log.clear()
+    with pytest.raises(RuntimeError):
+        batched(np.zeros((7, 2)), ("yhat",))
+    assert fake.log[0] == ("hint", 0, 7) and fake.log[-1] == ("hint", 0, 0)
