@@ -133,8 +133,23 @@ int pk_set_pivot_tolerance(pk_handle *h, double tol);
  * matrixops.py:31,41): 0 = automatic (default), 1 = one launch per 64-wide block column with the row
  * blocks of every candidate spread over the grid, 2 = one persistent CTA per candidate (populations), 3 = the
  * persistent kernel with a gang of CTAs per candidate (few candidates: SLSQP stencils, a handful of n = 4096
- * matrices).  Automatic: gangs for up to a third of the CTA slots, otherwise a cost model fitted on B200 picks 1 or 2. */
+ * matrices), 4 = TASK mode: the persistent CTAs pull tile tasks (diagonal tile / one 64- or 128-row panel pass of one
+ * candidate) from a ticket counter, dependencies through per-candidate completion counters in global memory -- every
+ * SM stays busy whatever the population size (128 candidates per GPU of a sharded population, the default 300, a
+ * 150-particle swarm at n = 4096) and the results are bit-identical to variant 2.
+ * Automatic: gangs for up to a third of the CTA slots, task mode otherwise. */
 int pk_set_cholesky_variant(pk_handle *h, int variant);
+
+/* Tuning knobs of task mode (variant 4): block columns with at most `single_below` row blocks left are cut into
+ * 64-row passes (default 4; the late columns are a chain of short dependent tasks), `cohort` = number of candidates that
+ * walk the task list together (0 = all candidates of the call).  Neither changes a bit of the result. */
+int pk_set_task_options(pk_handle *h, int single_below, int cohort);
+
+/* Diagnostic (no device needed): the task list of ONE candidate with `nt` block columns as (type, j, row block,
+ * blocks) quadruples -- type 0 = diagonal tile j, 1 = panel pass of block column j over `blocks` row blocks starting
+ * at `row block`.  Returns the number of tasks (writes at most `cap` of them), or -1 if the list is not a valid
+ * dependency order (tests/test_library_cpu.py checks the invariants the device-side waits rely on). */
+int pk_task_schedule(int nt, int single_below, int32_t *out4, int cap);
 
 /* Tuning / test knob for the fused predictor behind pk_predict_batch (predict_normalized /
  * predicterr_normalized / expimp loops, matrixops.py:68-95, krige.py:201-258): 0 = automatic,

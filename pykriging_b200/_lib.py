@@ -21,7 +21,7 @@ EXPORTS = [
     "pk_predict_batch", "pk_append_point", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
     "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
     "pk_fp64_peak", "pk_debug_math", "pk_set_cholesky_variant", "pk_set_predict_variant", "pk_set_overlap",
-    "pk_set_shard_hint",
+    "pk_set_shard_hint", "pk_set_task_options", "pk_task_schedule",
 ]
 
 _lib = None
@@ -82,6 +82,10 @@ def load():
     lib.pk_set_shard_hint.restype = ctypes.c_int
     lib.pk_set_overlap.argtypes = [hp, ctypes.c_int]
     lib.pk_set_overlap.restype = ctypes.c_int
+    lib.pk_set_task_options.argtypes = [hp, ctypes.c_int, ctypes.c_int]
+    lib.pk_set_task_options.restype = ctypes.c_int
+    lib.pk_task_schedule.argtypes = [ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int]
+    lib.pk_task_schedule.restype = ctypes.c_int
     for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
                  "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_set_workspace_limit"):
         getattr(lib, name).restype = ctypes.c_int
@@ -103,6 +107,17 @@ def _f64(a):
     if hasattr(a, "data_ptr"):
         return a
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def task_schedule(nt, single_below=4):
+    """Task list of one candidate in task mode (no device needed): array of (type, j, row block, blocks)."""
+    lib = load()
+    n = lib.pk_task_schedule(int(nt), int(single_below), None, 0)
+    if n < 0:
+        raise PkError("pk_task_schedule: invalid schedule for nt=%d" % nt)
+    out = np.zeros((n, 4), dtype=np.int32)
+    lib.pk_task_schedule(int(nt), int(single_below), _addr(out), n)
+    return out
 
 
 class Handle(object):
@@ -260,11 +275,18 @@ class Handle(object):
         self._check(self.lib.pk_set_pivot_tolerance(self._h, float(tol)), "pk_set_pivot_tolerance")
 
     def set_cholesky_variant(self, variant):
-        """0 auto, 1 per-block-column launches, 2 persistent CTA per candidate, 3 the same with gangs of CTAs per candidate."""
+        """0 auto, 1 per-block-column launches, 2 persistent CTA per candidate, 3 the same with gangs of CTAs per candidate,
+        4 task mode (persistent CTAs pulling tile tasks; bit-identical to 2)."""
         self._check(self.lib.pk_set_cholesky_variant(self._h, int(variant)), "pk_set_cholesky_variant")
 
+    def set_task_options(self, single_below=4, cohort=0):
+        """Task-mode knobs (pk_set_task_options): 64-row passes for block columns with at most `single_below` row
+        blocks left; `cohort` candidates walk the task list together (0 = all)."""
+        self._check(self.lib.pk_set_task_options(self._h, int(single_below), int(cohort)), "pk_set_task_options")
+
     def set_overlap(self, enabled):
-        """Psi construction of the second part of a population overlaps the factorisation of the first (default on)."""
+        """Experiment knob, default OFF (measured slower): Psi construction of the second part of a population on a
+        second stream under the factorisation of the first."""
         self._check(self.lib.pk_set_overlap(self._h, int(bool(enabled))), "pk_set_overlap")
 
     def set_predict_variant(self, variant):

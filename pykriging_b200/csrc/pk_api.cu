@@ -100,6 +100,21 @@ static int to_device(pk_handle* h, const double* src, double* stage, size_t coun
     return 0;
 }
 
+// info < 0 is not a numerical outcome: a spin-wait of the persistent Cholesky (gang barrier / task dependency) timed out
+// -- its CTAs were starved by another kernel holding the SMs for seconds.  The likelihood epilogue raises a sticky
+// device flag for such candidates; it is read back wherever the stream has just been synchronised (host outputs,
+// pk_synchronize), so the failure is loud wherever the outputs live.
+static int check_fault(pk_handle* h, const char* where) {
+    int f = 0;
+    PK_CUDA(h, cudaMemcpy(&f, h->d_fault, sizeof(int), cudaMemcpyDeviceToHost));
+    if (f != 0) {
+        PK_CUDA(h, cudaMemset(h->d_fault, 0, sizeof(int)));
+        PK_FAIL(h, "%s: a spin-wait of the persistent Cholesky timed out for at least one candidate (GPU shared with a "
+                   "long-running kernel?); its results are invalid", where);
+    }
+    return 0;
+}
+
 extern "C" {
 
 int pk_version(void) { return PK_VERSION; }
@@ -141,7 +156,14 @@ int pk_create(pk_handle** out, int device) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_fit_hp, sizeof(double) * 2 * PK_MAX_K);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_try_hp, sizeof(double) * 2 * PK_MAX_K);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_queue, sizeof(unsigned int) * PK_QUEUE_SLOTS);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_fault, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->d_fault, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    if (const char* v = getenv("PK_SPLIT")) h->env_split = v;
+    if (const char* v = getenv("PK_CHOL_GANG")) h->env_gang = atoi(v) > 0 ? atoi(v) : 0;
+    if (const char* v = getenv("PK_CHOL_CTAS_PER_SM")) h->env_ctas_per_sm = (atoi(v) == 1) ? 1 : 2;
+    h->env_cta_timing = getenv("PK_CTA_TIMING") != nullptr;
+    h->env_cta_alias = getenv("PK_CTA_ALIAS") != nullptr;
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);
@@ -157,7 +179,7 @@ int pk_destroy(pk_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
-                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch, h->d_gang, h->d_gridinfo};
+                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch, h->d_gang, h->d_gridinfo, h->d_tasks, h->d_taskws, h->d_fault};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -176,7 +198,7 @@ int pk_synchronize(pk_handle* h) {
     if (!h) return 1;
     PK_CUDA(h, cudaSetDevice(h->device));
     PK_CUDA(h, cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_fault(h, "pk_synchronize");
 }
 
 void* pk_stream(pk_handle* h) { return h ? (void*)h->stream : nullptr; }
@@ -190,9 +212,27 @@ int pk_set_pivot_tolerance(pk_handle* h, double tol) {
 }
 
 int pk_set_cholesky_variant(pk_handle* h, int variant) {
-    if (!h || variant < 0 || variant > 3) return 1;
+    if (!h || variant < 0 || variant > 4) return 1;
     h->chol_variant = variant;
     return 0;
+}
+
+int pk_set_task_options(pk_handle* h, int single_below, int cohort) {
+    if (!h || single_below < 0 || cohort < 0) return 1;
+    h->task_single_below = single_below;
+    h->task_cohort = cohort;
+    return 0;
+}
+
+int pk_task_schedule(int nt, int single_below, int32_t* out4, int cap) {
+    if (nt < 1 || single_below < 0) return -1;
+    std::vector<int> flat;
+    if (!pk::task_schedule_flat(nt, single_below, flat)) return -1;
+    const int count = (int)(flat.size() / 4);
+    if (out4)
+        for (int i = 0; i < count && i < cap; ++i)
+            for (int c = 0; c < 4; ++c) out4[4 * i + c] = flat[4 * i + c];
+    return count;
 }
 
 int pk_set_shard_hint(pk_handle* h, int64_t population, int64_t query_points) {
@@ -281,6 +321,8 @@ int pk_set_data(pk_handle* h, int n, int k, const double* X, const double* y) {
     h->k = k;
     h->fit_valid = false;  // a cached factor belongs to the previous data set
     h->w_valid = false;
+    h->psi_n = 0;          // and so does the Psi copy
+    h->psi_matches_fit = false;
     return 0;
 }
 
@@ -301,6 +343,7 @@ static int ensure_workspace(pk_handle* h, size_t per_matrix_bytes, int C, int* c
     size_t chunk = limit / per_matrix_bytes;
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)C) chunk = (size_t)C;
+    if (chunk > 65535) chunk = 65535;  // some launchers put the candidate index on grid.y / grid.z
     const size_t need = chunk * per_matrix_bytes;
     if (need > h->ws_bytes) {
         PK_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -323,9 +366,9 @@ static int ensure_workspace(pk_handle* h, size_t per_matrix_bytes, int C, int* c
 static void plan_parts(pk_handle* h, int cc, std::vector<int>& parts) {
     parts.clear();
     const int slots = 2 * h->sm_count;
-    if (const char* e = getenv("PK_SPLIT")) {  // experiment knob: comma-separated part sizes
+    if (!h->env_split.empty()) {  // experiment knob (PK_SPLIT): comma-separated part sizes
         int left = cc;
-        const char* q = e;
+        const char* q = h->env_split.c_str();
         while (*q && left > 0) {
             int v = atoi(q);
             if (v <= 0) break;
@@ -427,12 +470,9 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
         PK_CUDA(h, cudaMemcpyAsync(info, h->d_info, sizeof(int32_t) * C, cudaMemcpyDefault, h->stream));
         host_out |= !is_device_ptr(info);
     }
-    if (host_out) PK_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (info && !is_device_ptr(info)) {
-        // info < 0 is not a numerical outcome: a gang barrier of the persistent Cholesky timed out (its CTAs were not
-        // all resident -- another kernel holding the SMs for seconds).  Fail loudly instead of handing back a penalty.
-        for (int i = 0; i < C; ++i)
-            if (info[i] < 0) PK_FAIL(h, "pk_nll_batch: gang barrier timed out for candidate %d (GPU shared with a long-running kernel?)", i);
+    if (host_out) {
+        PK_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (check_fault(h, "pk_nll_batch")) return 1;  // device outputs: reported by pk_synchronize
     }
     return 0;
 }
@@ -473,6 +513,8 @@ int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, in
     PK_CUDA(h, cudaMemcpyAsync(h->d_try_hp + PK_MAX_K, d_p, sizeof(double) * k, cudaMemcpyDeviceToDevice, h->stream));
     PK_CUDA(h, pk::launch_psi_build(h, s, 1, d_theta, d_p, h->d_lambda, mode, h->d_try, h->d_info));
     PK_CUDA(h, pk::launch_extract_psi(h, s, h->d_try, h->d_psi, 1));
+    h->psi_n = h->n;
+    h->psi_matches_fit = false;  // until the factorisation below is known to have succeeded
     PK_CUDA(h, pk::launch_cholesky(h, s, 1, h->d_try, h->d_info));
     PK_CUDA(h, pk::launch_nll_epilogue(h, s, 1, h->d_try, h->d_out, h->cap_C, h->d_info));
     double host4[4];
@@ -496,6 +538,7 @@ int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, in
         h->fit_valid = true;
         h->fit_n = h->n;
         h->w_valid = false;
+        h->psi_matches_fit = true;
     }
     if (out4) PK_CUDA(h, cudaMemcpy(out4, host4, sizeof(host4), cudaMemcpyDefault));
     if (info) PK_CUDA(h, cudaMemcpy(info, &host_info, sizeof(int32_t), cudaMemcpyDefault));
@@ -509,6 +552,8 @@ int pk_append_point(pk_handle* h, const double* x_new, double y_new, double* out
     if (h->n == 0) PK_FAIL(h, "pk_append_point: pk_set_data has not been called");
     // in place only with a cached factor of the current data and room inside the padded order
     if (!h->fit_valid || h->fit_n != h->n) return 0;
+    // ... and with the Psi copy of THAT factor (a failed pk_fit since has replaced it: take the rebuild route)
+    if (!h->psi_matches_fit || h->psi_n != h->n) return 0;
     const int n = h->n, k = h->k;
     const pk::TiledShape s = pk::tiled_shape(n, true);
     if (n + 1 > s.np || n + 1 > h->cap_rows || s.np != h->fit_np) return 0;
@@ -531,6 +576,7 @@ int pk_append_point(pk_handle* h, const double* x_new, double y_new, double* out
                                h->stream));
     h->n = n + 1;
     h->fit_n = n + 1;
+    h->psi_n = n + 1;
     h->w_valid = false;
     const pk::TiledShape s1 = pk::tiled_shape(n + 1, true);
     PK_CUDA(h, pk::launch_nll_epilogue(h, s1, 1, h->d_fit, h->d_out, h->cap_C, h->d_info));
@@ -635,7 +681,8 @@ int pk_predict_batch(pk_handle* h, int64_t m, const double* Xq, const double* th
 
 int pk_get_psi(pk_handle* h, double* out) {
     if (!h || !out) return 1;
-    if (!h->d_psi || h->fit_np == 0) PK_FAIL(h, "pk_get_psi: pk_fit has not been called");
+    if (!h->d_psi || h->fit_np == 0 || h->psi_n != h->n)
+        PK_FAIL(h, "pk_get_psi: no Psi for the current data (pk_fit has not been called since pk_set_data)");
     PK_CUDA(h, cudaSetDevice(h->device));
     PK_CUDA(h, cudaMemcpyAsync(out, h->d_psi, sizeof(double) * h->n * h->n, cudaMemcpyDefault, h->stream));
     PK_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -23,6 +23,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "pk_internal.h"
 
@@ -249,7 +250,7 @@ template <bool GANG>
 __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
                                              int rows, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
                                              int* rel, unsigned& seq, const Frag& fg, int G_, int rank_, int inv_base_,
-                                             long long* tl = nullptr) {
+                                             long long* tl = nullptr, int first_ = -1) {
     // GANG == false: one CTA per candidate -- the gang arithmetic below folds away at compile time
     const int G = GANG ? G_ : 1, rank = GANG ? rank_ : 0, inv_base = GANG ? inv_base_ : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -257,7 +258,9 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     double* As = pipe;
     double* Bs = pipe + STAGES * A_STAGE;
     const int brow0 = j * PK_TILE;
-    const int first = (j + 1) * PK_TILE;
+    // first row of the panel: everything below the diagonal tile, or (task mode) the first row of ONE pass whose
+    // last row is rows - 1
+    const int first = (first_ >= 0) ? first_ : (j + 1) * PK_TILE;
     const int nk_gemm = j * (PK_TILE / KC);
     const int nkt = nk_gemm + PK_TILE / KC;
     // passes: 128 rows each for a CTA on its own; in a gang 64-row passes dealt round-robin over the ranks
@@ -829,6 +832,157 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TASK mode: the factorisation of every candidate as a stream of tile tasks.
+//
+// One CTA per candidate leaves SMs idle whenever the population is not a multiple of the resident CTA slots
+// (128 candidates per GPU when a population of 1024 is sharded over 8 GPUs: 128 of 296 slots; the reference's
+// default population of 300; the 150-particle regression swarm at n = 4096) and ties a candidate's latency to ONE
+// CTA.  Here the persistent CTAs pull TASKS from a global ticket counter instead:
+//     D(j)        diagonal tile of block column j: product, 64 x 64 factorisation, the 8 augmented rows
+//     P(j, r, b)  one panel pass of block column j: the b (1 or 2) 64-row blocks starting at row block r
+// Ticket t belongs to candidate (t % S) of its cohort and to entry t / S of the per-shape task list built by the
+// launcher (task_schedule below): every task depends only on tasks of the SAME candidate that come EARLIER in the
+// list, so a ticket's dependencies have always been claimed by a running CTA (or are done) and waiting for them can
+// never deadlock, resident or not.  Completion is published per candidate in global memory -- ddone = number of
+// finished diagonal tiles, rdone[rb] = number of finished block columns of row block rb (release store after a
+// device-scope fence; the waiter acquires, then orders its TMA reads with fence.proxy.async).  The inverted 8 x 8
+// diagonal blocks a panel pass needs travel through a global scratch (4 KB per diagonal tile).
+// Every tile is produced by exactly the arithmetic of the one-CTA-per-candidate kernel above (same K order, same
+// accumulators), so the results are bit-identical to it for any population size, cohort size or pass partition.
+// ------------------------------------------------------------------------------------------------
+struct Task {
+    int type, j, rb, nb;  // type 0 = D(j), 1 = P(j, rb, nb)
+};
+constexpr int DINV_DOUBLES = 8 * 8 * 8;  // the eight inverted diagonal blocks of a tile, dense
+
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// warp 0: lane 0 watches ddone >= need_d, lanes 1..nb watch rdone[rb + lane - 1] >= need_r.
+// Returns 1 = ready, 0 = the candidate failed meanwhile (skip), -1 = timed out (never on a healthy launch).
+__device__ __forceinline__ int task_wait(const int* fl, int need_d, int rb, int nb, int need_r, const int32_t* info_c,
+                                         const int* fault, int lane) {
+    const int* addr = (lane == 0) ? fl : fl + 1 + rb + (lane - 1);
+    const int need = (lane == 0) ? need_d : need_r;
+    const bool watch = lane <= nb;
+    const long long t0 = clock64();
+    for (;;) {
+        const int v = watch ? ld_acquire_gpu_s32(addr) : need;
+        if (__all_sync(0xffffffffu, v >= need)) return 1;
+        int bad = 0, dead = 0;
+        if (lane == 0) {
+            bad = ld_acquire_gpu_s32(reinterpret_cast<const int*>(info_c));
+            dead = ld_acquire_gpu_s32(fault);
+        }
+        bad = __shfl_sync(0xffffffffu, bad, 0);
+        dead = __shfl_sync(0xffffffffu, dead, 0);
+        if (bad != 0) return 0;
+        if (dead != 0 || clock64() - t0 > (1LL << 32)) return -1;  // somebody timed out already: the launch is being abandoned
+        __nanosleep(64);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld, size_t elems, double piv_tol,
+                 double* __restrict__ ws, int32_t* __restrict__ info, unsigned int* __restrict__ queue,
+                 const Task* __restrict__ tasks, int ntasks, int S, int* __restrict__ flags, int fstride,
+                 double* __restrict__ dinv, int* __restrict__ fault) {
+    extern __shared__ __align__(16) double smem_raw[];
+    double* smem = smem_raw + ((SMEM_ALIGN - ((unsigned)__cvta_generic_to_shared(smem_raw) & (SMEM_ALIGN - 1))) &
+                               (SMEM_ALIGN - 1)) / sizeof(double);
+    double* pipe = smem;
+    double* Dsm = pipe + PIPE_DOUBLES;
+    double* diag0 = Dsm + D_DOUBLES;
+    int* ctl = reinterpret_cast<int*>(diag0 + PK_TILE);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(diag0 + PK_TILE + 2);
+    int* rel = reinterpret_cast<int*>(bars + STAGES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + s, 1);
+            rel[s] = 0;
+        }
+        mbar_fence_init();
+    }
+    const Frag fg = make_frag(lane);
+    unsigned seq = 0;
+    const int np = nt * PK_TILE;
+    // tickets: cohorts of S consecutive candidates walk the task list together (ticket = cohort base + entry * size
+    // + member), one cohort after the other
+    const long long total = (long long)C * ntasks;
+    for (;;) {
+        fence_proxy_async();  // a failed or skipped task leaves generic-proxy writes in the stage buffers
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned t = atomicAdd(queue, 1u);
+            ctl[0] = (int)t;
+            ctl[3] = ld_acquire_gpu_s32(fault);
+        }
+        __syncthreads();
+        const long long t = (unsigned)ctl[0];
+        if (t >= total || ctl[3] != 0) break;  // fault: a dependency wait timed out somewhere -- abandon the launch (the host fails loudly)
+        const int cohort = (int)(t / ((long long)S * ntasks));
+        const int csize = min(S, C - cohort * S);
+        const int within = (int)(t - (long long)cohort * S * ntasks);
+        const int cand = cohort * S + within % csize;
+        const Task tk = tasks[within / csize];
+        int* fl = flags + (size_t)cand * fstride;
+        if (warp == 0) {
+            int ok;
+            if (tk.type == 0) ok = task_wait(fl, tk.j, tk.j, (tk.j > 0) ? 1 : 0, tk.j, info + cand, fault, lane);
+            else ok = task_wait(fl, tk.j + 1, tk.rb, (tk.j > 0) ? tk.nb : 0, tk.j, info + cand, fault, lane);
+            if (lane == 0) ctl[2] = ok;
+        }
+        __syncthreads();
+        const int ok = ctl[2];
+        if (ok <= 0) {
+            if (ok < 0 && tid == 0) {
+                info[cand] = -1;
+                atomicOr(fault, 1);
+                __threadfence();
+            }
+            continue;
+        }
+        fence_proxy_async();  // the producers' (generic-proxy) stores are read through TMA from here on
+        double* M = ws + (size_t)cand * elems;
+        double* dv = dinv + ((size_t)cand * nt + tk.j) * DINV_DOUBLES;
+        if (tk.type == 0) {
+            const int bad = diag_tile<false>(pipe, Dsm, diag0, ctl, M, ld, tk.j, np, piv_tol, &tmap, cand, bars, rel, seq, fg,
+                                             nullptr, nullptr);
+            if (bad) {
+                if (tid == 0) {
+                    st_release_gpu_s32(reinterpret_cast<int*>(info + cand), tk.j * PK_TILE + bad);  // dpotrf convention
+                    __threadfence();
+                }
+                continue;
+            }
+            for (int i = tid; i < DINV_DOUBLES; i += THREADS) dv[i] = Dsm[(i >> 3) * DLD + (i & 7)];
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                st_release_gpu_s32(fl, tk.j + 1);
+            }
+        } else {
+            for (int i = tid; i < DINV_DOUBLES; i += THREADS) Dsm[(i >> 3) * DLD + (i & 7)] = __ldcg(dv + i);
+            __syncthreads();
+            const int r0 = tk.rb * PK_TILE;
+            panel_column<false>(pipe, Dsm, M, ld, tk.j, r0 + tk.nb * PK_TILE, &tmap, cand, bars, rel, seq, fg, 1, 0, 0, nullptr, r0);
+            if (tid < tk.nb) {
+                __threadfence();
+                st_release_gpu_s32(fl + 1 + tk.rb + tid, tk.j + 1);
+            }
+        }
+    }
+}
+
 }  // namespace cta
 
 // 3-D tensor map over the candidate workspace: (column, row, candidate), boxes of 16 columns x 64 rows,
@@ -897,9 +1051,8 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
     {
         const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;
         if (h->chol_variant != 2 || s.with_inverse) G = cholesky_gang_size(h, s, Ceff, h->chol_variant == 3 || s.with_inverse);
-        if (const char* ev = getenv("PK_CHOL_GANG")) {  // experiment knob
-            G = atoi(ev);
-            if (G < 1) G = 1;
+        if (h->env_gang > 0) {  // experiment knob (PK_CHOL_GANG)
+            G = h->env_gang;
             if (G > nt - 1) G = (nt - 1 > 0) ? nt - 1 : 1;
         }
         if ((int64_t)C * G > 2 * (int64_t)h->sm_count) G = 1;  // all CTAs of a gang must be resident
@@ -931,14 +1084,14 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
         return cudaGetLastError();
     }
     int per_sm = 2;
-    if (const char* e = getenv("PK_CHOL_CTAS_PER_SM")) per_sm = (atoi(e) == 1) ? 1 : 2;  // experiment knob
+    per_sm = h->env_ctas_per_sm;  // experiment knob (PK_CHOL_CTAS_PER_SM)
     const int grid = (C < per_sm * h->sm_count) ? C : per_sm * h->sm_count;
-    if (getenv("PK_CTA_TIMING")) {  // diagnostic: per-phase cycle counts of the persistent kernel, printed to stderr
+    if (h->env_cta_timing) {  // diagnostic: per-phase cycle counts of the persistent kernel, printed to stderr
         long long* dbg = nullptr;
         cudaMalloc((void**)&dbg, sizeof(long long) * (8 * grid + 16));
         cudaMemset(dbg, 0, sizeof(long long) * (8 * grid + 16));
         cta::chol_cta_kernel<true, false><<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.rows, s.ld, s.elems(), h->pivot_tol,
-                                                                            ws, info, queue, dbg, getenv("PK_CTA_ALIAS") ? 1 : 0,
+                                                                            ws, info, queue, dbg, h->env_cta_alias ? 1 : 0,
                                                                             1, nullptr, nullptr, 0);
         cudaStreamSynchronize(h->stream);
         std::vector<long long> host(8 * (size_t)grid + 16);
@@ -965,6 +1118,147 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
                                                                              h->pivot_tol, ws, info, queue, nullptr, 0, 1,
                                                                              nullptr, nullptr, 0);
     }
+    h->launches++;
+    return cudaGetLastError();
+}
+
+
+// Task list of one candidate for nt block columns (see cta::chol_task_kernel).  Panel passes take row blocks in
+// pairs from the top (128 rows: two DMMA row tiles per warp); a column with at most `single_below` row blocks left
+// is cut into single blocks instead -- the late columns are a chain of short dependent tasks and want the
+// parallelism more than the operand reuse.  Order, with look-ahead: D(0), P(0,first), D(1), P(0,rest), P(1,first),
+// D(2), P(1,rest), ... -- the diagonal tile of column j+1 is claimed as soon as the pass that feeds it is.
+void task_schedule(int nt, int single_below, std::vector<cta::Task>& out) {
+    out.clear();
+    auto passes = [&](int j, std::vector<cta::Task>& ps) {
+        ps.clear();
+        const int left = nt - 1 - j;
+        int b = j + 1;
+        while (b < nt) {
+            const int nb = (left <= single_below || b + 1 >= nt) ? 1 : 2;
+            ps.push_back(cta::Task{1, j, b, nb});
+            b += nb;
+        }
+    };
+    std::vector<cta::Task> cur, nxt;
+    out.push_back(cta::Task{0, 0, 0, 0});
+    passes(0, cur);
+    if (!cur.empty()) out.push_back(cur[0]);
+    for (int j = 0; j < nt; ++j) {
+        passes(j, cur);
+        if (j + 1 < nt) out.push_back(cta::Task{0, j + 1, 0, 0});
+        for (size_t i = 1; i < cur.size(); ++i) out.push_back(cur[i]);
+        if (j + 1 < nt) {
+            passes(j + 1, nxt);
+            if (!nxt.empty()) out.push_back(nxt[0]);
+        }
+    }
+}
+
+// true when every task's inputs are produced by tasks earlier in the list (what makes ticket order deadlock free)
+bool task_schedule_valid(int nt, const std::vector<cta::Task>& tl) {
+    std::vector<int> ddone(1, 0), rdone(nt, 0);
+    std::vector<char> seen_d(nt, 0);
+    std::vector<std::vector<char>> seen_p(nt, std::vector<char>(nt, 0));  // [j][rb]
+    for (const cta::Task& t : tl) {
+        if (t.j < 0 || t.j >= nt) return false;
+        if (t.type == 0) {
+            if (ddone[0] != t.j) return false;                  // D tasks in order
+            if (t.j > 0 && rdone[t.j] != t.j) return false;     // row block j complete up to column j - 1
+            ddone[0] = t.j + 1;
+            seen_d[t.j] = 1;
+        } else {
+            if (t.nb < 1 || t.nb > 2 || t.rb <= t.j || t.rb + t.nb > nt) return false;
+            if (ddone[0] < t.j + 1) return false;
+            for (int b = t.rb; b < t.rb + t.nb; ++b) {
+                if (rdone[b] != t.j || seen_p[t.j][b]) return false;
+                rdone[b] = t.j + 1;
+                seen_p[t.j][b] = 1;
+            }
+        }
+    }
+    for (int j = 0; j < nt; ++j) {
+        if (!seen_d[j]) return false;
+        for (int b = j + 1; b < nt; ++b)
+            if (!seen_p[j][b]) return false;
+    }
+    return true;
+}
+
+bool task_schedule_flat(int nt, int single_below, std::vector<int>& out4) {
+    std::vector<cta::Task> tl;
+    task_schedule(nt, single_below, tl);
+    out4.clear();
+    for (const cta::Task& t : tl) {
+        out4.push_back(t.type);
+        out4.push_back(t.j);
+        out4.push_back(t.rb);
+        out4.push_back(t.nb);
+    }
+    return task_schedule_valid(nt, tl);
+}
+
+cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
+    if (s.with_inverse) return cudaErrorInvalidValue;  // pk_fit's L^-T rows are passes of the gang kernel
+    const int nt = s.np / PK_TILE;
+    const size_t smem = sizeof(double) * (size_t)cta::SMEM_DOUBLES + cta::SMEM_ALIGN;
+    CUtensorMap tmap;
+    cudaError_t e = make_ws_tensor_map(&tmap, ws, s, C);
+    if (e != cudaSuccess) return e;
+    static bool attr_done_dev[PK_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
+    if (!attr_done) {
+        e = cudaFuncSetAttribute(cta::chol_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    // per-shape task list, cached on the device
+    if (h->task_nt != nt || h->task_single != h->task_single_below || !h->d_tasks) {
+        std::vector<cta::Task> tl;
+        task_schedule(nt, h->task_single_below, tl);
+        if (!task_schedule_valid(nt, tl)) return cudaErrorInvalidValue;
+        e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return e;
+        if (h->d_tasks) cudaFree(h->d_tasks);
+        h->d_tasks = nullptr;
+        e = cudaMalloc((void**)&h->d_tasks, sizeof(cta::Task) * tl.size());
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpy(h->d_tasks, tl.data(), sizeof(cta::Task) * tl.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+        h->task_nt = nt;
+        h->task_single = h->task_single_below;
+        h->task_count = (int)tl.size();
+    }
+    // completion flags (zeroed per launch) + the inverted diagonal blocks
+    const int fstride = ((nt + 1 + 31) / 32) * 32;
+    const size_t flag_bytes = ((sizeof(int) * (size_t)C * fstride) + 255) & ~(size_t)255;
+    const size_t dinv_bytes = sizeof(double) * (size_t)C * nt * cta::DINV_DOUBLES;
+    if (flag_bytes + dinv_bytes > h->task_bytes) {
+        e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return e;
+        if (h->d_taskws) cudaFree(h->d_taskws);
+        h->d_taskws = nullptr;
+        h->task_bytes = 0;
+        e = cudaMalloc((void**)&h->d_taskws, flag_bytes + dinv_bytes);
+        if (e != cudaSuccess) return e;
+        h->task_bytes = flag_bytes + dinv_bytes;
+    }
+    int* flags = reinterpret_cast<int*>(h->d_taskws);
+    double* dinv = reinterpret_cast<double*>(reinterpret_cast<char*>(h->d_taskws) + flag_bytes);
+    e = cudaMemsetAsync(flags, 0, flag_bytes, h->stream);
+    if (e != cudaSuccess) return e;
+    unsigned int* queue = h->d_queue + h->queue_slot;
+    e = cudaMemsetAsync(queue, 0, sizeof(unsigned int), h->stream);
+    if (e != cudaSuccess) return e;
+    const long long total = (long long)C * h->task_count;
+    if (total >= (1LL << 32)) return cudaErrorInvalidValue;  // 32-bit ticket counter
+    int S = h->task_cohort > 0 ? h->task_cohort : C;
+    if (S > C) S = C;
+    const long long slots = 2LL * h->sm_count;
+    const int grid = (int)(total < slots ? total : slots);
+    cta::chol_task_kernel<<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.ld, s.elems(), h->pivot_tol, ws, info, queue,
+                                                               reinterpret_cast<const cta::Task*>(h->d_tasks), h->task_count, S,
+                                                               flags, fstride, dinv, h->d_fault);
     h->launches++;
     return cudaGetLastError();
 }

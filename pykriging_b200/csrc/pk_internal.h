@@ -32,12 +32,27 @@ struct pk_handle {
     void* d_gang = nullptr;                // gang barrier counters + partial-sum scratch of the persistent Cholesky (gang mode)
     unsigned int* d_queue = nullptr;       // candidate queues of the persistent Cholesky kernel (PK_QUEUE_SLOTS counters)
     int queue_slot = 0;                    // counter the next launch_cholesky_cta uses
+    // task mode of the persistent Cholesky (cta::chol_task_kernel): per-shape task list + per-launch completion flags
+    // and inverted diagonal blocks
+    void* d_tasks = nullptr;
+    int task_nt = 0, task_single = -1, task_count = 0;
+    int task_single_below = 4;             // block columns with at most this many row blocks left use 64-row passes
+    int task_cohort = 0;                   // candidates that walk the task list together (0 = the whole call)
+    void* d_taskws = nullptr;
+    size_t task_bytes = 0;
     // Psi construction of the NEXT part of a population overlaps the Cholesky of the current one: the Psi
     // kernels are issued on stream2, the factorisations on stream, ordered by events (pk_nll_batch)
     cudaStream_t stream2 = nullptr;
     std::vector<cudaEvent_t> ev_pipe;
     std::vector<cudaEvent_t> ev_pred;       // upload / compute / download events of the chunked host path of pk_predict_batch
     int overlap = 0;                       // 1: two-part pipeline on two streams (pk_set_overlap; measured slower, off)
+    // experiment knobs, read from the environment ONCE in pk_create (never on the per-generation path)
+    std::string env_split;                 // PK_SPLIT: comma-separated part sizes of a resident chunk
+    int env_gang = 0;                      // PK_CHOL_GANG: forced gang size (0 = automatic)
+    int env_ctas_per_sm = 2;               // PK_CHOL_CTAS_PER_SM
+    bool env_cta_timing = false;           // PK_CTA_TIMING: per-phase cycle counts of the persistent kernel on stderr
+    bool env_cta_alias = false;            // PK_CTA_ALIAS: timing experiment (results are garbage)
+    int* d_fault = nullptr;                // sticky device flag: some candidate came back with info < 0 (a spin-wait timed out)
 
     // model data (pk_set_data)
     int n = 0, k = 0;
@@ -65,6 +80,8 @@ struct pk_handle {
     double* d_fit = nullptr;  // factorised augmented matrix of the last successful fit
     double* d_try = nullptr;  // scratch for the attempt (swapped in on success)
     double* d_psi = nullptr;  // n x n Psi of the last attempt (row-major, full symmetric)
+    int psi_n = 0;            // order of the matrix in d_psi (0 = none: pk_set_data drops it)
+    bool psi_matches_fit = false;  // d_psi is the Psi of the CACHED factor (false after a failed attempt)
     double* d_linv = nullptr; // fit_np x fit_np row-major L^-1 (lower)
     double* d_ad = nullptr;   // 2 x fit_np : a = L^-1 1, d = L^-1 y
     double* d_w = nullptr;    // fit_np : w = L^-T (d - mu a)
@@ -121,6 +138,9 @@ cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const dou
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
+cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
+// task list of one candidate as (type, j, row block, blocks) quadruples; returns false if it is not a valid order
+bool task_schedule_flat(int nt, int single_below, std::vector<int>& out4);
 int cholesky_gang_size(const pk_handle* h, const TiledShape& s, int64_t Ceff, bool forced);
 cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,
                                 int out_stride, int32_t* info);

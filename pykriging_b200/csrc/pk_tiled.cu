@@ -494,11 +494,12 @@ chol_step_kernel(int j, int nt, int rows, int ld, size_t elems, double piv_tol, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 nll_epilogue_kernel(int n, int np, int ld, size_t elems, const double* __restrict__ ws, double* __restrict__ out4,
-                    int out_stride, const int32_t* __restrict__ info) {
+                    int out_stride, const int32_t* __restrict__ info, int* __restrict__ fault) {
     __shared__ double scratch[32];
     const int cand = blockIdx.x, tid = threadIdx.x;
     if (info[cand] != 0) {
         if (tid < 4) out4[tid * out_stride + cand] = CUDART_NAN;
+        if (tid == 0 && info[cand] < 0) atomicOr(fault, 1);  // not a numerical outcome: a spin-wait timed out (pk_api.cu check_fault)
         return;
     }
     const double* M = ws + (size_t)cand * elems;
@@ -618,12 +619,13 @@ cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws
     // pk_fit (one matrix + L^-T rows): the gang kernel, the inverse rows being further panel passes (per-block-column
     // kernels when pinned to variant 1 or when the matrix has fewer than three block columns)
     if (s.with_inverse) v = (h->chol_variant != 1 && cholesky_gang_size(h, s, Ceff, true) > 1) ? 3 : 1;
+    if (v == 4) return launch_cholesky_task(h, s, C, ws, info);
     return (v >= 2) ? launch_cholesky_cta(h, s, C, ws, info) : launch_cholesky_steps(h, s, C, ws, info);
 }
 
 cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,
                                 int out_stride, int32_t* info) {
-    nll_epilogue_kernel<<<C, 256, 0, h->stream>>>(s.n, s.np, s.ld, s.elems(), ws, out4, out_stride, info);
+    nll_epilogue_kernel<<<C, 256, 0, h->stream>>>(s.n, s.np, s.ld, s.elems(), ws, out4, out_stride, info, h->d_fault);
     h->launches++;
     return cudaGetLastError();
 }

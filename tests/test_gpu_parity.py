@@ -154,11 +154,11 @@ def test_tiled_path_matches_oracle_on_seeded_inputs(handle, n, k, seed):
         assert rel_err(out["sigma2"][i], s2) < tol, (i, cond)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("n,k,seed", [(130, 4, 3), (333, 7, 5), (640, 10, 6), (1024, 10, 7)])
 def test_cholesky_variants_match_oracle(handle, variant, n, k, seed):
     """The blocked-Cholesky variants (1 per-block-column launches / 2 persistent CTA per candidate / 3 the same
-    kernel with a gang of CTAs per candidate) against the oracle, including candidates whose Psi is not positive
+    kernel with a gang of CTAs per candidate / 4 task mode) against the oracle, including candidates whose Psi is not positive
     definite and the info convention."""
     X = onp.rlh(n, k, seed)
     y = onp.f_stybtang_norm(X)
@@ -484,6 +484,47 @@ def test_full_size_c5_grid_properties(handle):
     assert np.max(np.abs(g[1] ** 2 - ref["s"] ** 2)) < out4[2] * max(1e-12, 100.0 * cond * 2.2e-16)
     ds = np.abs(g[1] - ref["s"])
     assert np.all(np.abs(g[2] - ref["ei"]) <= 1e-9 * np.sqrt(out4[2]) + 0.5 * ds + 1e-9 * np.abs(ref["ei"]))
+
+
+@pytest.mark.parametrize("n,k,C", [(200, 3, 37), (640, 5, 150), (1024, 10, 300), (1100, 4, 131)])
+def test_task_mode_is_bit_identical_to_one_cta_per_candidate(handle, n, k, C):
+    """Task mode (variant 4) hands the tiles of every candidate to whichever CTA is free; each tile is still
+    produced by the arithmetic of the one-CTA-per-candidate kernel (variant 2), so the four scalars and info[] must
+    agree BIT FOR BIT -- for every pass partition (single_below), cohort size and slice of the population, with
+    failing candidates in the mix.  This is what lets a population sharded over GPUs (any slice size) reproduce the
+    unsharded fitness vector, and so the same GA/PSO trajectory at any world size."""
+    X = onp.rlh(n, k, 100 + n)
+    y = onp.f_stybtang_norm(X) if k != 3 else onp.f_squared(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    cands = np.concatenate([onp.candidates_uniform(C // 2, k, n + 1), onp.candidates_loguniform(C - C // 2, k, n + 2, lo=-4)])
+    for i in (3, C // 2, C - 1):  # numerically singular: fail at different block columns
+        cands[i, :k] = 1e-5
+        cands[i, k:] = 2.0
+    cands[5, :k] = 3e-4
+    cands[5, k:] = 2.0
+    th, p = np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:])
+    names = ("nll", "mu", "sigma2", "lndet")
+    try:
+        handle.set_cholesky_variant(2)
+        ref = handle.nll_batch(th, p)
+        assert (ref["info"] > 0).sum() >= 3 and (ref["info"] == 0).sum() > C // 2
+        handle.set_cholesky_variant(4)
+        for single_below, cohort in ((4, 0), (0, 0), (100, 0), (4, 16), (2, 7)):
+            handle.set_task_options(single_below, cohort)
+            got = handle.nll_batch(th, p)
+            assert np.array_equal(got["info"], ref["info"]), (single_below, cohort)
+            for nm in names:
+                assert np.array_equal(got[nm], ref[nm], equal_nan=True), (nm, single_below, cohort)
+        handle.set_task_options(4, 0)
+        for lo, hi in ((0, 1), (2, 9), (C // 3, C // 3 + 33), (C - 20, C)):
+            part = handle.nll_batch(th[lo:hi], p[lo:hi])
+            assert np.array_equal(part["info"], ref["info"][lo:hi])
+            for nm in names:
+                assert np.array_equal(part[nm], ref[nm][lo:hi], equal_nan=True), (nm, lo, hi)
+    finally:
+        handle.set_task_options(4, 0)
+        handle.set_cholesky_variant(0)
 
 
 def test_gang_size_does_not_change_results(handle):
