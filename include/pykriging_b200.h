@@ -140,16 +140,19 @@ int pk_set_pivot_tolerance(pk_handle *h, double tol);
  * Automatic: gangs for up to a third of the CTA slots, task mode otherwise. */
 int pk_set_cholesky_variant(pk_handle *h, int variant);
 
-/* Tuning knobs of task mode (variant 4): block columns with at most `single_below` row blocks left are cut into
- * 64-row passes (default 4; the late columns are a chain of short dependent tasks), `cohort` = number of candidates that
- * walk the task list together (0 = all candidates of the call).  Neither changes a bit of the result. */
-int pk_set_task_options(pk_handle *h, int single_below, int cohort);
+/* Tuning knobs of task mode (variant 4); none of them changes a bit of the result.  A panel task takes up to
+ * `blocks_per_task` 64-row blocks of a block column (0 = automatic: 1-2 for few candidates, the whole column for
+ * populations of several waves); block columns with at most `single_below` row blocks left are cut into single blocks
+ * (-1 = automatic); `cohort` = number of candidates that walk the task list together (0 = all candidates of the call);
+ * candidate m of a cohort runs `m % skew` list entries behind the others, so that the CTAs resident at any moment hold
+ * a mix of latency-bound diagonal tiles and DMMA-bound panel tasks (0 = automatic, 1 = none). */
+int pk_set_task_options(pk_handle *h, int single_below, int blocks_per_task, int cohort, int skew);
 
 /* Diagnostic (no device needed): the task list of ONE candidate with `nt` block columns as (type, j, row block,
- * blocks) quadruples -- type 0 = diagonal tile j, 1 = panel pass of block column j over `blocks` row blocks starting
+ * blocks) quadruples -- type 0 = diagonal tile j, 1 = panel task of block column j over `blocks` row blocks starting
  * at `row block`.  Returns the number of tasks (writes at most `cap` of them), or -1 if the list is not a valid
  * dependency order (tests/test_library_cpu.py checks the invariants the device-side waits rely on). */
-int pk_task_schedule(int nt, int single_below, int32_t *out4, int cap);
+int pk_task_schedule(int nt, int single_below, int blocks_per_task, int32_t *out4, int cap);
 
 /* Tuning / test knob for the fused predictor behind pk_predict_batch (predict_normalized /
  * predicterr_normalized / expimp loops, matrixops.py:68-95, krige.py:201-258): 0 = automatic,

@@ -82,9 +82,9 @@ def load():
     lib.pk_set_shard_hint.restype = ctypes.c_int
     lib.pk_set_overlap.argtypes = [hp, ctypes.c_int]
     lib.pk_set_overlap.restype = ctypes.c_int
-    lib.pk_set_task_options.argtypes = [hp, ctypes.c_int, ctypes.c_int]
+    lib.pk_set_task_options.argtypes = [hp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.pk_set_task_options.restype = ctypes.c_int
-    lib.pk_task_schedule.argtypes = [ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int]
+    lib.pk_task_schedule.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int]
     lib.pk_task_schedule.restype = ctypes.c_int
     for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
                  "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_set_workspace_limit"):
@@ -109,14 +109,14 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def task_schedule(nt, single_below=4):
+def task_schedule(nt, single_below=4, blocks_per_task=2):
     """Task list of one candidate in task mode (no device needed): array of (type, j, row block, blocks)."""
     lib = load()
-    n = lib.pk_task_schedule(int(nt), int(single_below), None, 0)
+    n = lib.pk_task_schedule(int(nt), int(single_below), int(blocks_per_task), None, 0)
     if n < 0:
         raise PkError("pk_task_schedule: invalid schedule for nt=%d" % nt)
     out = np.zeros((n, 4), dtype=np.int32)
-    lib.pk_task_schedule(int(nt), int(single_below), _addr(out), n)
+    lib.pk_task_schedule(int(nt), int(single_below), int(blocks_per_task), _addr(out), n)
     return out
 
 
@@ -279,10 +279,12 @@ class Handle(object):
         4 task mode (persistent CTAs pulling tile tasks; bit-identical to 2)."""
         self._check(self.lib.pk_set_cholesky_variant(self._h, int(variant)), "pk_set_cholesky_variant")
 
-    def set_task_options(self, single_below=4, cohort=0):
-        """Task-mode knobs (pk_set_task_options): 64-row passes for block columns with at most `single_below` row
-        blocks left; `cohort` candidates walk the task list together (0 = all)."""
-        self._check(self.lib.pk_set_task_options(self._h, int(single_below), int(cohort)), "pk_set_task_options")
+    def set_task_options(self, single_below=-1, blocks_per_task=0, cohort=0, skew=0):
+        """Task-mode knobs (pk_set_task_options; defaults = automatic): 64-row tasks for block columns with at most
+        `single_below` row blocks left; up to `blocks_per_task` row blocks per panel task; `cohort` candidates walk the
+        task list together (0 = all), member m running m % skew entries behind.  None of them changes a bit of the result."""
+        self._check(self.lib.pk_set_task_options(self._h, int(single_below), int(blocks_per_task), int(cohort), int(skew)),
+                    "pk_set_task_options")
 
     def set_overlap(self, enabled):
         """Experiment knob, default OFF (measured slower): Psi construction of the second part of a population on a

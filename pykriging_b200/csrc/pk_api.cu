@@ -217,17 +217,19 @@ int pk_set_cholesky_variant(pk_handle* h, int variant) {
     return 0;
 }
 
-int pk_set_task_options(pk_handle* h, int single_below, int cohort) {
-    if (!h || single_below < 0 || cohort < 0) return 1;
+int pk_set_task_options(pk_handle* h, int single_below, int blocks_per_task, int cohort, int skew) {
+    if (!h || single_below < -1 || blocks_per_task < 0 || cohort < 0 || skew < 0) return 1;
     h->task_single_below = single_below;
+    h->task_blocks = blocks_per_task;
     h->task_cohort = cohort;
+    h->task_skew = skew;
     return 0;
 }
 
-int pk_task_schedule(int nt, int single_below, int32_t* out4, int cap) {
-    if (nt < 1 || single_below < 0) return -1;
+int pk_task_schedule(int nt, int single_below, int blocks_per_task, int32_t* out4, int cap) {
+    if (nt < 1 || single_below < 0 || blocks_per_task < 1) return -1;
     std::vector<int> flat;
-    if (!pk::task_schedule_flat(nt, single_below, flat)) return -1;
+    if (!pk::task_schedule_flat(nt, single_below, blocks_per_task, flat)) return -1;
     const int count = (int)(flat.size() / 4);
     if (out4)
         for (int i = 0; i < count && i < cap; ++i)

@@ -103,6 +103,47 @@ __device__ __forceinline__ bool gang_barrier(Gang& g, int* ctl) {
     return ctl[2] != 0;
 }
 
+// ---- task mode: dependencies that are only needed LATE in a task ------------------------------------------------
+// A task of cta::chol_task_kernel starts as soon as the inputs of its FIRST pipeline chunks exist and lets the thread
+// that issues the TMA copies wait for the rest: the product chunks of a panel pass only read finished block columns,
+// the pass needs L_jj and the inverted diagonal blocks (diagonal tile j) only for its four solve chunks; a diagonal
+// tile accumulates block columns 0 .. j-2 while the pass that produces column j-1 of its rows is still running.  This
+// takes the DMMA main loops off the critical path D(j) -> P(j, first) -> D(j+1) -> ... of a candidate, which is what
+// bounds the run time when there are fewer candidates than CTA slots.
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+struct LateDep {
+    const int* f0;   // first counter (never null)
+    int need0;
+    const int* f1;   // second counter or null
+    int need1;
+    const int* dead; // candidate's info word: non-zero = the candidate failed, nothing will ever arrive
+    int* fault;      // sticky launch-wide flag: a wait timed out somewhere, the launch is being abandoned
+    int from;        // first K chunk (within the task) that needs the counters
+};
+// Spin (one thread) until the counters have arrived; gives up when the candidate is dead or the launch abandoned --
+// the task then runs on stale data, which nobody will read.  Ends with the proxy fence that orders this thread's TMA
+// copies behind the producers' generic-proxy stores.
+__device__ __forceinline__ void late_wait(const LateDep& d) {
+    const long long t0 = clock64();
+    for (;;) {
+        if (ld_acquire_gpu_s32(d.f0) >= d.need0 && (d.f1 == nullptr || ld_acquire_gpu_s32(d.f1) >= d.need1)) break;
+        if (ld_acquire_gpu_s32(d.dead) != 0 || ld_acquire_gpu_s32(d.fault) != 0) break;
+        if (clock64() - t0 > (1LL << 32)) {
+            atomicOr(d.fault, 1);
+            break;
+        }
+        __nanosleep(32);
+    }
+    fence_proxy_async();
+}
+
 // acc(8*MI x 64 per warp) += A(8*MI x 16) * B(64 x 16)^T for one stage (the products are accumulated with a
 // PLUS sign and subtracted from the original tile in one go when it arrives with the solve chunks: no sign
 // flips in the hot loop -- every non-DMMA instruction costs the scheduler's dispatch port a cycle the tensor
@@ -247,10 +288,12 @@ __device__ __forceinline__ void consume_half(double (&acc)[2][8][2], const doubl
 // tl != nullptr (diagnostic build only): lanes 0 of warps 0 and 4 accumulate clock64() deltas of the loop's
 // sections {barrier wait, early produce, first half, late produce, second half, store} into tl[0..5] / tl[8..13].
 template <bool GANG>
-__device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, double* __restrict__ M, int ld, int j,
+__device__ __forceinline__ void panel_column(double* pipe, double* Dsm_w, double* __restrict__ M, int ld, int j,
                                              int rows, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
                                              int* rel, unsigned& seq, const Frag& fg, int G_, int rank_, int inv_base_,
-                                             long long* tl = nullptr, int first_ = -1) {
+                                             long long* tl = nullptr, int first_ = -1, const LateDep* late = nullptr,
+                                             const double* __restrict__ dinv_g = nullptr) {
+    const double* Dsm = Dsm_w;
     // GANG == false: one CTA per candidate -- the gang arithmetic below folds away at compile time
     const int G = GANG ? G_ : 1, rank = GANG ? rank_ : 0, inv_base = GANG ? inv_base_ : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -281,7 +324,12 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     // the stage's mbarrier.  Chunk c of the column goes to stage (seq + c) % STAGES; the first STAGES chunks are
     // issued here, chunk c + STAGES by whichever warp is the LAST to release chunk c (a counter per stage):
     // nobody ever waits for a stage to become free.
+    bool late_ok = (late == nullptr);
     auto issue = [&](int c, int k_idx, int r0) {
+        if (!late_ok && k_idx >= late->from) {  // task mode: the solve chunks need diagonal tile j
+            late_wait(*late);
+            late_ok = true;
+        }
         const int ps = (int)((seq + (unsigned)c) % STAGES);
         unsigned long long* bar = bars + ps;
         const int nbox = (G == 1 && rows - r0 > BOX_ROWS) ? 2 : 1;
@@ -326,6 +374,12 @@ __device__ __forceinline__ void panel_column(double* pipe, const double* Dsm, do
     // stage refills it.  Warps on different schedulers may be up to STAGES - 1 chunks apart.
     for (int g = 0; g < total; ++g) {
         mbar_wait(bars + cs, cpar);  // chunk g has landed
+        if (dinv_g != nullptr && ck == nk_gemm && cb == 0) {
+            // task mode, first solve chunk of the pass: its copies were issued behind the wait for diagonal tile j, so
+            // the inverted diagonal blocks that tile's task left in the global scratch are complete -- fetch them
+            for (int i = tid; i < 8 * 8 * 8; i += THREADS) Dsm_w[(i >> 3) * DLD + (i & 7)] = __ldcg(dinv_g + i);
+            __syncthreads();
+        }
         PK_TL(0)
         PK_TL(1)
         const double* as = As + cs * A_STAGE;
@@ -513,7 +567,8 @@ __device__ __forceinline__ void diag_consume(double (&acc)[8][2], double (&accA)
 template <bool GANG>
 __device__ __forceinline__ bool diag_gemm(double* T, double* pipe, const double* __restrict__ M, int ld, int j,
                                           int np, const CUtensorMap* tmap, int cidx, unsigned long long* bars,
-                                          int* rel, unsigned& seq, const Frag& fg, Gang* gang, int* ctl) {
+                                          int* rel, unsigned& seq, const Frag& fg, Gang* gang, int* ctl,
+                                          const LateDep* late = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, q = lane & 3;
     const int br = (warp < 4) ? warp : 11 - warp;
@@ -531,7 +586,12 @@ __device__ __forceinline__ bool diag_gemm(double* T, double* pipe, const double*
     auto kchunk = [&](int i) { return (G > 1) ? (rank + (i / SEG) * G) * SEG + (i % SEG) : i; };
     // two TMA boxes per chunk (L[j, :] and the box that starts at the 8 augmented rows; its 56 rows beyond the
     // matrix are zero-filled by the TMA unit); issued like the panel's chunks (see panel_column)
+    bool late_ok = (late == nullptr);
     auto issue = [&](int c) {
+        if (!late_ok && c >= late->from) {  // task mode: the last block column of this row block is still being produced
+            late_wait(*late);
+            late_ok = true;
+        }
         const int ps = (int)((seq + (unsigned)c) % STAGES);
         unsigned long long* bar = bars + ps;
         mbar_arrive_expect_tx(bar, (unsigned)(2 * BOX_DOUBLES * sizeof(double)));
@@ -674,14 +734,14 @@ template <bool GANG>
 __device__ __forceinline__ int diag_tile(double* pipe, double* Dsm, double* diag0, int* ctl, double* __restrict__ M,
                                          int ld, int j, int np, double piv_tol, const CUtensorMap* tmap, int cidx,
                                          unsigned long long* bars, int* rel, unsigned& seq, const Frag& fg,
-                                         long long* tm, Gang* gang) {
+                                         long long* tm, Gang* gang, const LateDep* late = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = j * PK_TILE;
     if (tid < PK_TILE) diag0[tid] = M[(size_t)(row0 + tid) * ld + row0 + tid];
     double* T = pipe;
     long long t0 = 0;
     if (tm) t0 = clock64();
-    if (!diag_gemm<GANG>(T, pipe, M, ld, j, np, tmap, cidx, bars, rel, seq, fg, gang, ctl)) return -1;  // gang barrier timed out
+    if (!diag_gemm<GANG>(T, pipe, M, ld, j, np, tmap, cidx, bars, rel, seq, fg, gang, ctl, late)) return -1;  // gang barrier timed out
     if (tid == 0) ctl[1] = 0;
     __syncthreads();
     if (tm) {
@@ -856,23 +916,16 @@ struct Task {
     int type, j, rb, nb;  // type 0 = D(j), 1 = P(j, rb, nb)
 };
 constexpr int DINV_DOUBLES = 8 * 8 * 8;  // the eight inverted diagonal blocks of a tile, dense
+constexpr int TASK_MAX_BLOCKS = 30;      // row blocks of one panel task (one lane of warp 0 watches each)
 
-__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
 
-// warp 0: lane 0 watches ddone >= need_d, lanes 1..nb watch rdone[rb + lane - 1] >= need_r.
+// warp 0: lane 0 watches *a0 >= need0 (a0 may be null), lanes 1..nb watch arows[lane - 1] >= need_r.
 // Returns 1 = ready, 0 = the candidate failed meanwhile (skip), -1 = timed out (never on a healthy launch).
-__device__ __forceinline__ int task_wait(const int* fl, int need_d, int rb, int nb, int need_r, const int32_t* info_c,
-                                         const int* fault, int lane) {
-    const int* addr = (lane == 0) ? fl : fl + 1 + rb + (lane - 1);
-    const int need = (lane == 0) ? need_d : need_r;
-    const bool watch = lane <= nb;
+__device__ __forceinline__ int task_wait(const int* a0, int need0, const int* arows, int nb, int need_r,
+                                         const int32_t* info_c, const int* fault, int lane) {
+    const int* addr = (lane == 0) ? a0 : arows + (lane - 1);
+    const int need = (lane == 0) ? need0 : need_r;
+    const bool watch = (lane == 0) ? (a0 != nullptr) : (lane <= nb);
     const long long t0 = clock64();
     for (;;) {
         const int v = watch ? ld_acquire_gpu_s32(addr) : need;
@@ -893,7 +946,7 @@ __device__ __forceinline__ int task_wait(const int* fl, int need_d, int rb, int 
 __global__ void __launch_bounds__(THREADS, 2)
 chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld, size_t elems, double piv_tol,
                  double* __restrict__ ws, int32_t* __restrict__ info, unsigned int* __restrict__ queue,
-                 const Task* __restrict__ tasks, int ntasks, int S, int* __restrict__ flags, int fstride,
+                 const Task* __restrict__ tasks, int ntasks, int S, int skew, int* __restrict__ flags, int fstride,
                  double* __restrict__ dinv, int* __restrict__ fault) {
     extern __shared__ __align__(16) double smem_raw[];
     double* smem = smem_raw + ((SMEM_ALIGN - ((unsigned)__cvta_generic_to_shared(smem_raw) & (SMEM_ALIGN - 1))) &
@@ -915,9 +968,13 @@ chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld
     const Frag fg = make_frag(lane);
     unsigned seq = 0;
     const int np = nt * PK_TILE;
-    // tickets: cohorts of S consecutive candidates walk the task list together (ticket = cohort base + entry * size
-    // + member), one cohort after the other
-    const long long total = (long long)C * ntasks;
+    // tickets: cohorts of S consecutive candidates walk the task list together (ticket = cohort base + step * size
+    // + member), one cohort after the other.  Member m is `m % skew` entries BEHIND the step, so that any window of
+    // consecutive tickets -- what the resident CTAs are working on at a given moment -- mixes latency-bound diagonal
+    // tiles with DMMA-bound panel tasks instead of holding one kind (steps before a member's first / after its last
+    // entry are null tickets).  Dependencies still point to earlier tickets: entry i' < i of a member lies in an earlier step.
+    const int nsteps = ntasks + skew - 1;
+    const long long total = (long long)C * nsteps;
     for (;;) {
         fence_proxy_async();  // a failed or skipped task leaves generic-proxy writes in the stage buffers
         __syncthreads();
@@ -929,23 +986,35 @@ chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld
         __syncthreads();
         const long long t = (unsigned)ctl[0];
         if (t >= total || ctl[3] != 0) break;  // fault: a dependency wait timed out somewhere -- abandon the launch (the host fails loudly)
-        const int cohort = (int)(t / ((long long)S * ntasks));
+        const int cohort = (int)(t / ((long long)S * nsteps));
         const int csize = min(S, C - cohort * S);
-        const int within = (int)(t - (long long)cohort * S * ntasks);
-        const int cand = cohort * S + within % csize;
-        const Task tk = tasks[within / csize];
-        int* fl = flags + (size_t)cand * fstride;
+        const int within = (int)(t - (long long)cohort * S * nsteps);
+        const int member = within % csize;
+        const int entry = within / csize - member % skew;
+        if (entry < 0 || entry >= ntasks) continue;  // null ticket
+        const int cand = cohort * S + member;
+        const Task tk = tasks[entry];
+        int* fl = flags + (size_t)cand * fstride;  // [0] = finished diagonal tiles, [1 + rb] = finished block columns of row block rb
+        const int j = tk.j;
+        // what the FIRST chunks of the task read (everything else: LateDep, waited for by the thread that issues the copies)
         if (warp == 0) {
-            int ok;
-            if (tk.type == 0) ok = task_wait(fl, tk.j, tk.j, (tk.j > 0) ? 1 : 0, tk.j, info + cand, fault, lane);
-            else ok = task_wait(fl, tk.j + 1, tk.rb, (tk.j > 0) ? tk.nb : 0, tk.j, info + cand, fault, lane);
+            int ok = 1;
+            if (tk.type == 0) {
+                // block columns 0 .. j-2 of row block j and of the augmented rows
+                if (j >= 2) ok = task_wait(fl, j - 1, fl + 1 + j, 1, j - 1, info + cand, fault, lane);
+            } else {
+                // block columns 0 .. j-1 of the pass's row blocks and of row block j (the B operand)
+                if (j >= 1) ok = task_wait(fl + 1 + j, j, fl + 1 + tk.rb, tk.nb, j, info + cand, fault, lane);
+                // diagonal tile j already there (the usual case in a large population)?  then no late wait at all
+                if (lane == 0) ctl[1] = (ld_acquire_gpu_s32(fl) >= j + 1) ? 1 : 0;
+            }
             if (lane == 0) ctl[2] = ok;
         }
         __syncthreads();
         const int ok = ctl[2];
         if (ok <= 0) {
             if (ok < 0 && tid == 0) {
-                info[cand] = -1;
+                atomicCAS(reinterpret_cast<int*>(info + cand), 0, -1);
                 atomicOr(fault, 1);
                 __threadfence();
             }
@@ -953,13 +1022,15 @@ chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld
         }
         fence_proxy_async();  // the producers' (generic-proxy) stores are read through TMA from here on
         double* M = ws + (size_t)cand * elems;
-        double* dv = dinv + ((size_t)cand * nt + tk.j) * DINV_DOUBLES;
+        double* dv = dinv + ((size_t)cand * nt + j) * DINV_DOUBLES;
         if (tk.type == 0) {
-            const int bad = diag_tile<false>(pipe, Dsm, diag0, ctl, M, ld, tk.j, np, piv_tol, &tmap, cand, bars, rel, seq, fg,
-                                             nullptr, nullptr);
+            // the last block column (K chunks 4(j-1) ..) waits for the pass that produces it and for diagonal tile j-1
+            const LateDep late{fl, j, fl + 1 + j, j, reinterpret_cast<const int*>(info + cand), fault, 4 * (j - 1)};
+            const int bad = diag_tile<false>(pipe, Dsm, diag0, ctl, M, ld, j, np, piv_tol, &tmap, cand, bars, rel, seq, fg,
+                                             nullptr, nullptr, (j >= 1) ? &late : nullptr);
             if (bad) {
                 if (tid == 0) {
-                    st_release_gpu_s32(reinterpret_cast<int*>(info + cand), tk.j * PK_TILE + bad);  // dpotrf convention
+                    atomicCAS(reinterpret_cast<int*>(info + cand), 0, j * PK_TILE + bad);  // dpotrf convention; the first failure stays
                     __threadfence();
                 }
                 continue;
@@ -968,16 +1039,22 @@ chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld
             __syncthreads();
             if (tid == 0) {
                 __threadfence();
-                st_release_gpu_s32(fl, tk.j + 1);
+                st_release_gpu_s32(fl, j + 1);
             }
         } else {
-            for (int i = tid; i < DINV_DOUBLES; i += THREADS) Dsm[(i >> 3) * DLD + (i & 7)] = __ldcg(dv + i);
-            __syncthreads();
+            // the four solve chunks need L_jj and the inverted diagonal blocks: diagonal tile j
+            const LateDep late{fl, j + 1, nullptr, 0, reinterpret_cast<const int*>(info + cand), fault, 4 * j};
             const int r0 = tk.rb * PK_TILE;
-            panel_column<false>(pipe, Dsm, M, ld, tk.j, r0 + tk.nb * PK_TILE, &tmap, cand, bars, rel, seq, fg, 1, 0, 0, nullptr, r0);
+            const bool d_ready = ctl[1] != 0;
+            if (d_ready) {
+                for (int i = tid; i < DINV_DOUBLES; i += THREADS) Dsm[(i >> 3) * DLD + (i & 7)] = __ldcg(dv + i);
+                __syncthreads();
+            }
+            panel_column<false>(pipe, Dsm, M, ld, j, r0 + tk.nb * PK_TILE, &tmap, cand, bars, rel, seq, fg, 1, 0, 0, nullptr, r0,
+                                d_ready ? nullptr : &late, d_ready ? nullptr : dv);
             if (tid < tk.nb) {
                 __threadfence();
-                st_release_gpu_s32(fl + 1 + tk.rb + tid, tk.j + 1);
+                st_release_gpu_s32(fl + 1 + tk.rb + tid, j + 1);
             }
         }
     }
@@ -1123,19 +1200,23 @@ cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double
 }
 
 
-// Task list of one candidate for nt block columns (see cta::chol_task_kernel).  Panel passes take row blocks in
-// pairs from the top (128 rows: two DMMA row tiles per warp); a column with at most `single_below` row blocks left
-// is cut into single blocks instead -- the late columns are a chain of short dependent tasks and want the
-// parallelism more than the operand reuse.  Order, with look-ahead: D(0), P(0,first), D(1), P(0,rest), P(1,first),
+// Task list of one candidate for nt block columns (see cta::chol_task_kernel).  A panel task takes up to
+// `blocks_per_task` row blocks from the top (2 = one 128-row pass, two DMMA row tiles per warp; more = several passes
+// streamed through the pipeline without draining it: fewer, longer tasks for large populations, where nobody waits for
+// anybody); a column with at most `single_below` row blocks left is cut into single blocks instead -- the late
+// columns are a chain of short dependent tasks and want the parallelism more than the operand reuse.  Order, with look-ahead: D(0), P(0,first), D(1), P(0,rest), P(1,first),
 // D(2), P(1,rest), ... -- the diagonal tile of column j+1 is claimed as soon as the pass that feeds it is.
-void task_schedule(int nt, int single_below, std::vector<cta::Task>& out) {
+void task_schedule(int nt, int single_below, int blocks_per_task, std::vector<cta::Task>& out) {
     out.clear();
+    if (blocks_per_task < 1) blocks_per_task = 1;
+    if (blocks_per_task > cta::TASK_MAX_BLOCKS) blocks_per_task = cta::TASK_MAX_BLOCKS;
     auto passes = [&](int j, std::vector<cta::Task>& ps) {
         ps.clear();
         const int left = nt - 1 - j;
         int b = j + 1;
         while (b < nt) {
-            const int nb = (left <= single_below || b + 1 >= nt) ? 1 : 2;
+            int nb = (left <= single_below) ? 1 : blocks_per_task;
+            if (b + nb > nt) nb = nt - b;
             ps.push_back(cta::Task{1, j, b, nb});
             b += nb;
         }
@@ -1168,7 +1249,7 @@ bool task_schedule_valid(int nt, const std::vector<cta::Task>& tl) {
             ddone[0] = t.j + 1;
             seen_d[t.j] = 1;
         } else {
-            if (t.nb < 1 || t.nb > 2 || t.rb <= t.j || t.rb + t.nb > nt) return false;
+            if (t.nb < 1 || t.nb > cta::TASK_MAX_BLOCKS || t.rb <= t.j || t.rb + t.nb > nt) return false;
             if (ddone[0] < t.j + 1) return false;
             for (int b = t.rb; b < t.rb + t.nb; ++b) {
                 if (rdone[b] != t.j || seen_p[t.j][b]) return false;
@@ -1185,9 +1266,9 @@ bool task_schedule_valid(int nt, const std::vector<cta::Task>& tl) {
     return true;
 }
 
-bool task_schedule_flat(int nt, int single_below, std::vector<int>& out4) {
+bool task_schedule_flat(int nt, int single_below, int blocks_per_task, std::vector<int>& out4) {
     std::vector<cta::Task> tl;
-    task_schedule(nt, single_below, tl);
+    task_schedule(nt, single_below, blocks_per_task, tl);
     out4.clear();
     for (const cta::Task& t : tl) {
         out4.push_back(t.type);
@@ -1212,10 +1293,23 @@ cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, doubl
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
+    // Granularity (never changes a bit of the result, so it may follow the size of THIS call): few candidates want many
+    // short tasks -- every CTA slot busy, short dependency chains -- a population of several waves wants few long ones.
+    int single_below = h->task_single_below, bpt = h->task_blocks;
+    if (single_below < 0 || bpt <= 0) {
+        const long long slots = 2LL * h->sm_count;
+        int a_sb, a_bpt;
+        if ((long long)C * 5 <= slots) { a_sb = 0; a_bpt = 1; }            // <= 59 candidates: 64-row tasks throughout
+        else if ((long long)C * 3 <= slots * 2) { a_sb = 4; a_bpt = 2; }   // <= 197
+        else if ((long long)C <= slots + slots / 2) { a_sb = 0; a_bpt = 2; }
+        else { a_sb = 0; a_bpt = cta::TASK_MAX_BLOCKS; }
+        if (single_below < 0) single_below = a_sb;
+        if (bpt <= 0) bpt = a_bpt;
+    }
     // per-shape task list, cached on the device
-    if (h->task_nt != nt || h->task_single != h->task_single_below || !h->d_tasks) {
+    if (h->task_nt != nt || h->task_single != single_below || h->task_bpt != bpt || !h->d_tasks) {
         std::vector<cta::Task> tl;
-        task_schedule(nt, h->task_single_below, tl);
+        task_schedule(nt, single_below, bpt, tl);
         if (!task_schedule_valid(nt, tl)) return cudaErrorInvalidValue;
         e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) return e;
@@ -1226,7 +1320,8 @@ cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, doubl
         e = cudaMemcpy(h->d_tasks, tl.data(), sizeof(cta::Task) * tl.size(), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return e;
         h->task_nt = nt;
-        h->task_single = h->task_single_below;
+        h->task_single = single_below;
+        h->task_bpt = bpt;
         h->task_count = (int)tl.size();
     }
     // completion flags (zeroed per launch) + the inverted diagonal blocks
@@ -1250,14 +1345,16 @@ cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, doubl
     unsigned int* queue = h->d_queue + h->queue_slot;
     e = cudaMemsetAsync(queue, 0, sizeof(unsigned int), h->stream);
     if (e != cudaSuccess) return e;
-    const long long total = (long long)C * h->task_count;
+    int skew = h->task_skew;
+    if (skew <= 0) skew = 1;  // measured without effect (profiles/task_sweep_r02_d.jsonl): the CTAs desynchronise on their own
+    const long long total = (long long)C * (h->task_count + skew - 1);
     if (total >= (1LL << 32)) return cudaErrorInvalidValue;  // 32-bit ticket counter
     int S = h->task_cohort > 0 ? h->task_cohort : C;
     if (S > C) S = C;
     const long long slots = 2LL * h->sm_count;
     const int grid = (int)(total < slots ? total : slots);
     cta::chol_task_kernel<<<grid, cta::THREADS, smem, h->stream>>>(tmap, C, nt, s.ld, s.elems(), h->pivot_tol, ws, info, queue,
-                                                               reinterpret_cast<const cta::Task*>(h->d_tasks), h->task_count, S,
+                                                               reinterpret_cast<const cta::Task*>(h->d_tasks), h->task_count, S, skew,
                                                                flags, fstride, dinv, h->d_fault);
     h->launches++;
     return cudaGetLastError();

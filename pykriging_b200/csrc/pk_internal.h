@@ -35,9 +35,11 @@ struct pk_handle {
     // task mode of the persistent Cholesky (cta::chol_task_kernel): per-shape task list + per-launch completion flags
     // and inverted diagonal blocks
     void* d_tasks = nullptr;
-    int task_nt = 0, task_single = -1, task_count = 0;
-    int task_single_below = 4;             // block columns with at most this many row blocks left use 64-row passes
+    int task_nt = 0, task_single = -1, task_bpt = 0, task_count = 0;  // what the cached list was built for
+    int task_single_below = -1;            // block columns with at most this many row blocks left use 64-row tasks (-1 = automatic)
+    int task_blocks = 0;                   // row blocks per panel task (0 = automatic)
     int task_cohort = 0;                   // candidates that walk the task list together (0 = the whole call)
+    int task_skew = 0;                     // member m of a cohort runs m % skew entries behind the step (0 = automatic)
     void* d_taskws = nullptr;
     size_t task_bytes = 0;
     // Psi construction of the NEXT part of a population overlaps the Cholesky of the current one: the Psi
@@ -140,7 +142,7 @@ cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, doub
 cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 // task list of one candidate as (type, j, row block, blocks) quadruples; returns false if it is not a valid order
-bool task_schedule_flat(int nt, int single_below, std::vector<int>& out4);
+bool task_schedule_flat(int nt, int single_below, int blocks_per_task, std::vector<int>& out4);
 int cholesky_gang_size(const pk_handle* h, const TiledShape& s, int64_t Ceff, bool forced);
 cudaError_t launch_nll_epilogue(pk_handle* h, const TiledShape& s, int C, const double* ws, double* out4,
                                 int out_stride, int32_t* info);

@@ -578,44 +578,22 @@ cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, doub
     return cudaGetLastError();
 }
 
-// Variant choice: the persistent kernel keeps one CTA per candidate busy for the whole factorisation,
-// so it wants at least ~2/3 of the SMs' worth of candidates; below that (pk_fit, n = 4096 with a
-// handful of candidates) the per-block-column launches expose the parallelism inside a matrix.
-// Few candidates (at most a third of the CTA slots): the persistent kernel with a GANG of CTAs per candidate wins
-// everywhere (pk_chol_cta.cu, cholesky_gang_size).  Otherwise:
-// Automatic choice between the two Cholesky variants from a cost model fitted to tools/variant_sweep.py on B200
-// (profiles/variant_sweep_r01.jsonl): the persistent kernel runs candidates in waves of 2 CTAs per SM -- a full
-// wave of 2 x SMs candidates takes T2(n), a partial wave with at most one CTA per SM T1(n) ~ 0.5-0.7 T2(n), anything
-// in between T2(n) again -- while the per-block-column kernels cost a(n) + C b(n).  Examples: n = 4096 with 160
-// candidates (regression PSO, regressionkrige.py:378): 153 ms per-block-column against 197 ms persistent; n = 1024
-// with 64: 2.2 ms persistent against 2.8 ms.
-static double interp_log2n(int np, const double (&tab)[5]) {
-    // tab[i] at n = 256 << i, linear in log2 n, clamped
-    const double x = log2((double)np) - 8.0;
-    if (x <= 0.0) return tab[0];
-    if (x >= 4.0) return tab[4];
-    const int i = (int)x;
-    return tab[i] + (tab[i + 1] - tab[i]) * (x - i);
-}
-static int choose_cholesky_variant(int np, int64_t C, int sm_count) {
-    static const double r2_tf[5] = {11.1, 21.4, 29.0, 31.1, 33.0};     // persistent, full wave: TFLOP/s
-    static const double t1_frac[5] = {0.74, 0.66, 0.60, 0.53, 0.52};   // T1 / T2
-    static const double r1_tf[5] = {4.5, 10.6, 17.1, 22.9, 26.9};      // per-block-column: asymptotic TFLOP/s
-    static const double a_ms[5] = {0.26, 0.65, 1.85, 5.6, 17.5};       // per-block-column: launch chain of one matrix
-    const double flop = (double)np * np * np / 3.0;
-    const int64_t wave = 2 * (int64_t)sm_count;
-    const double T2 = (double)wave * flop / (interp_log2n(np, r2_tf) * 1e9);  // ms
-    const double T1 = T2 * interp_log2n(np, t1_frac);
-    const int64_t full = C / wave, rem = C % wave;
-    const double v2 = (double)full * T2 + (rem == 0 ? 0.0 : (rem <= sm_count ? T1 : T2));
-    const double v1 = interp_log2n(np, a_ms) + (double)C * flop / (interp_log2n(np, r1_tf) * 1e9);
-    return (v2 <= v1) ? 2 : 1;
-}
-
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info) {
     int v = h->chol_variant;
     const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;  // the population this call is a slice of
-    if (v == 0) v = (cholesky_gang_size(h, s, Ceff, false) > 1) ? 2 : choose_cholesky_variant(s.np, Ceff, h->sm_count);
+    // Automatic: task mode (pk_chol_cta.cu).  Its tiles are produced by the arithmetic of the one-CTA-per-candidate kernel,
+    // so a candidate's result does not depend on how many candidates it is evaluated with -- a single SLSQP evaluation,
+    // a stencil of 21, a shard of 128 and a population of 1024 agree bit for bit -- and its task granularity follows the
+    // size of the call (profiles/task_sweep_r02_*.jsonl: faster than gangs from 1 candidate up at n = 1024, than one CTA
+    // per candidate for every population that is not a whole number of waves).
+    // One CTA per candidate (bit-identical) is kept where it measured faster: populations of two waves or more whose
+    // last wave is full or nearly so -- C = 1024 at n = 1024: 12.3 against 12.9 ms -- and tiny matrices (n <= 256),
+    // where a task is too short to pay for its ticket.
+    if (v == 0) {
+        const long long slots = 2LL * h->sm_count;
+        const bool whole = (C >= 2 * slots && (C % slots == 0 || C % slots >= slots / 3)) || (s.np <= 256 && C >= h->sm_count);
+        v = whole ? 2 : 4;
+    }
     // pk_fit (one matrix + L^-T rows): the gang kernel, the inverse rows being further panel passes (per-block-column
     // kernels when pinned to variant 1 or when the matrix has fewer than three block columns)
     if (s.with_inverse) v = (h->chol_variant != 1 && cholesky_gang_size(h, s, Ceff, true) > 1) ? 3 : 1;

@@ -510,20 +510,20 @@ def test_task_mode_is_bit_identical_to_one_cta_per_candidate(handle, n, k, C):
         ref = handle.nll_batch(th, p)
         assert (ref["info"] > 0).sum() >= 3 and (ref["info"] == 0).sum() > C // 2
         handle.set_cholesky_variant(4)
-        for single_below, cohort in ((4, 0), (0, 0), (100, 0), (4, 16), (2, 7)):
-            handle.set_task_options(single_below, cohort)
+        for opts in ((-1, 0, 0, 0), (4, 2, 0, 1), (0, 1, 0, 2), (0, 30, 0, 3), (3, 5, 0, 7), (4, 2, 16, 1), (2, 3, 7, 4)):
+            handle.set_task_options(*opts)  # single_below, blocks_per_task, cohort, skew
             got = handle.nll_batch(th, p)
-            assert np.array_equal(got["info"], ref["info"]), (single_below, cohort)
+            assert np.array_equal(got["info"], ref["info"]), opts
             for nm in names:
-                assert np.array_equal(got[nm], ref[nm], equal_nan=True), (nm, single_below, cohort)
-        handle.set_task_options(4, 0)
+                assert np.array_equal(got[nm], ref[nm], equal_nan=True), (nm, opts)
+        handle.set_task_options()
         for lo, hi in ((0, 1), (2, 9), (C // 3, C // 3 + 33), (C - 20, C)):
             part = handle.nll_batch(th[lo:hi], p[lo:hi])
             assert np.array_equal(part["info"], ref["info"][lo:hi])
             for nm in names:
                 assert np.array_equal(part[nm], ref[nm][lo:hi], equal_nan=True), (nm, lo, hi)
     finally:
-        handle.set_task_options(4, 0)
+        handle.set_task_options()
         handle.set_cholesky_variant(0)
 
 

@@ -13,11 +13,15 @@ from pykriging_b200._lib import Handle  # noqa: E402
 
 h = Handle(0)
 dev = torch.device("cuda", 0)
-shapes = [(1024, 10, 0, (21, 64, 128, 148, 296, 300, 1024)), (4096, 6, 1, (8, 64, 150)), (2048, 8, 0, (128, 300))]
+shapes = [(1024, 10, 0, (64, 128, 148, 296, 300, 592, 1024)), (4096, 6, 1, (64, 150)),
+          (2048, 8, 0, (128, 300)), (512, 6, 0, (300, 2048)), (256, 4, 0, (128, 2048))]
 if os.environ.get("PK_SWEEP_QUICK"):
     shapes = [(1024, 10, 0, (128, 300, 1024))]
-configs = [("v2", 2, 4, 0), ("auto", 0, 4, 0), ("task", 4, 4, 0), ("task_sb0", 4, 0, 0), ("task_sb8", 4, 8, 0),
-           ("task_sb100", 4, 100, 0), ("task_c32", 4, 4, 32), ("task_c64", 4, 4, 64), ("task_c148", 4, 4, 148)]
+# (name, cholesky variant, single_below, blocks_per_task, skew)
+configs = [("v2", 2, -1, 0, 0), ("auto", 0, -1, 0, 0), ("t_4_2_s1", 4, 4, 2, 1), ("t_4_2_s2", 4, 4, 2, 2), ("t_4_2_s3", 4, 4, 2, 3),
+           ("t_4_2_s7", 4, 4, 2, 7), ("t_0_30_s1", 4, 0, 30, 1), ("t_0_30_s2", 4, 0, 30, 2), ("t_0_30_s3", 4, 0, 30, 3),
+           ("t_0_30_s5", 4, 0, 30, 5), ("t_0_30_s9", 4, 0, 30, 9), ("t_0_4_s3", 4, 0, 4, 3), ("t_0_4_s9", 4, 0, 4, 9), ("t_0_2_s5", 4, 0, 2, 5),
+           ("t_0_2_s11", 4, 0, 2, 11)]
 for n, k, mode, Cs in shapes:
     rng = np.random.default_rng(n)
     X = np.zeros((n, k))
@@ -34,11 +38,13 @@ for n, k, mode, Cs in shapes:
         info = torch.empty(C, dtype=torch.int32, device=dev)
         row = {"n": n, "C": C}
         base = None
-        for name, variant, sb, cohort in configs:
-            if n >= 4096 and name in ("task_c32", "task_c64", "task_sb100"):
+        for name, variant, sb, bpt, skew in configs:
+            if name == "gang" and C > 98:
+                continue
+            if name == "v2" and n >= 4096 and C < 64:
                 continue
             h.set_cholesky_variant(variant)
-            h.set_task_options(sb, cohort)
+            h.set_task_options(sb, bpt, 0, skew)
             h.set_profiling(True)
             reps = 3 if n < 4096 else 2
             for rep in range(reps + 1):
@@ -50,10 +56,10 @@ for n, k, mode, Cs in shapes:
             ms = h.phase_times()["cholesky"] / reps
             h.set_profiling(False)
             res = out.clone()
-            if base is None:
+            if base is None and name in ("v2", "t_4_2_s1"):
                 base = res
-            same = bool(torch.equal(torch.nan_to_num(res, nan=-1.0), torch.nan_to_num(base, nan=-1.0)))
+            same = base is not None and bool(torch.equal(torch.nan_to_num(res, nan=-1.0), torch.nan_to_num(base, nan=-1.0)))
             row[name] = {"ms": round(ms, 3), "tf": round(C * n ** 3 / 3 / (ms * 1e-3) * 1e-12, 2), "same_bits_as_v2": same}
         print(json.dumps(row), flush=True)
 h.set_cholesky_variant(0)
-h.set_task_options(4, 0)
+h.set_task_options()
