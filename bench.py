@@ -3,8 +3,10 @@
 at n=1024, k=10).
 
     python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
-    torchrun ... bench.py --gpus N ...                       # one rank per GPU, candidates sharded (weak scaling)
+    python bench.py --impl reference --steps K --warmup W    # the unmodified reference on the host cores (oracle/_ref)
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU: `value` = every rank its own population
+                                                             # (weak), `strong` = ONE population of 1024 sharded over
+                                                             # the ranks with the all_gather inside the timed generation
 
 One "step" = one GA/PSO generation: the concentrated negative ln-likelihood of a population of C
 (theta, p) candidates for the n x k sample set -- what ``kriging.fittingObjective`` computes
@@ -116,7 +118,12 @@ def run_predictions(torch, dev, local_rank, rank, world, dist):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    best = float(out[2].max().item())
+    best_local = float(out[2].max().item())
+    # the quantity infill is after: the grid's largest EI and where it is -- ONE all_gather of a (value, index) pair
+    # per rank (sharding.global_argmax), never the arrays
+    from pykriging_b200 import sharding
+
+    best, best_index = sharding.global_argmax(np.array([best_local]), lo + int(out[2].argmax().item()))
     # end to end through the C ABI with HOST buffers (pinned): upload of the query points, kernels and download of
     # yhat / s / EI inside the timed region (chunks of 1 Mi points, copies overlapped with the kernels)
     Xq_h = Xq.cpu().pin_memory()
@@ -138,7 +145,7 @@ def run_predictions(torch, dev, local_rank, rank, world, dist):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    assert float(out_h[2].max().item()) == best
+    assert float(out_h[2].max().item()) == best_local
     e2e = {"value": m_total / (e2e_ms * 1e-3), "unit": "predictions/s", "ms": e2e_ms,
            "h2d_bytes": int(m_total * PRED_K * 8), "d2h_bytes": int(m_total * 3 * 8),
            "api": "pk_predict_batch (C ABI) with pinned host buffers"}
@@ -146,7 +153,9 @@ def run_predictions(torch, dev, local_rank, rank, world, dist):
     return {"value": m_total / (ms * 1e-3), "unit": "predictions/s", "ms": ms, "e2e": e2e, "points": m_total, "n": PRED_N,
             "k": PRED_K, "outputs": "yhat, s, EI per point", "scaling": "strong (grid rows sharded over ranks)",
             "flops_per_point_algorithmic": PRED_N ** 2,
-            "tflops_algorithmic": m_total * PRED_N ** 2 / (ms * 1e-3) * 1e-12, "max_ei": best}
+            "tflops_algorithmic": m_total * PRED_N ** 2 / (ms * 1e-3) * 1e-12, "max_ei": best,
+            "argmax_ei_grid_index": int(best_index),
+            "max_ei_exchange": "one all_gather of (value, index) per rank (sharding.global_argmax)"}, (model, h)
 
 
 def load_traffic():
@@ -218,75 +227,305 @@ class ClockSampler(threading.Thread):
 
 
 # ---- reference arm / CPU baseline (the only place bench.py touches oracle/) -------------------------------
-CPU_BASELINE_SAMPLE = 48  # candidates timed for cpu_baseline: ~10 s at ~4 evals/s on the box's 16 host cores
+CPU_BASELINE_SAMPLE = 48  # candidates timed for cpu_baseline: ~10-20 s of CPU work on the box's host cores
+
+
+def _reference_classes():
+    """The UNMODIFIED reference (oracle/_ref on the GPU box, shipped by the committed recipe oracle/make_ref.py;
+    /root/reference in the build container) behind oracle/ref_loader's import shims, or None when it is absent --
+    the callers then fall back to the NumPy port of the same algorithm (oracle/oracle_np.py)."""
+    try:
+        from oracle import ref_loader
+
+        if ref_loader.reference_available():
+            K, R, _ = ref_loader.load_reference()
+            return K, R
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("reference not loadable (%s): falling back to the oracle port\n" % e)
+    return None
 
 
 def cpu_reference_evals(n_cands, seeds):
-    """Times the reference's CPU algorithm (NumPy restatement in reference order: np.power over the
-    (n,n,k) distance tensor, dpotrf, six dgesv solves -- matrixops.py:24-56) on `n_cands` candidates of
-    the same workload per seed.  Returns list of (seconds, evals)."""
-    from oracle import oracle_np as onp
-
+    """Times the reference's own CPU implementation -- `kriging.fittingObjective` of the unmodified pyKriging classes
+    (krige.py:429-452: per candidate updatePsi = np.power over the (n,n,k) distance tensor + dpotrf, neglikelihood =
+    six dgesv solves, matrixops.py:24-56) -- on `n_cands` candidates of the same workload per seed, all host threads.
+    `updateData` (the O(n^2) Python loop that builds the distance tensor, matrixops.py:18-22) runs once per model and
+    is reported separately.  Returns (list of (seconds, evals), info dict, last fitness list)."""
     X, y = make_samples(N_SAMPLES, K_DIMS)
-    model = onp.OracleKriging(X, y)  # builds the distance tensor once, like matrixops.updateData
-    out = []
+    classes = _reference_classes()
+    t0 = time.perf_counter()
+    if classes is not None:
+        model = classes[0](X, y)  # normalizeData + updateData, like the user's kriging(X, y)
+        kind = "reference"
+        fit = lambda c: model.fittingObjective(c, {})  # noqa: E731
+    else:
+        from oracle import oracle_np as onp
+
+        model = onp.OracleKriging(X, y)
+        kind = "port"
+        fit = model.fittingObjective
+    build_s = time.perf_counter() - t0
+    out, last = [], None
     for s in seeds:
         theta, p = make_candidates(POP, K_DIMS, 1000 + s)
         idx = np.linspace(0, POP - 1, n_cands).astype(int)  # spans both candidate families
         cands = np.concatenate([theta[idx], p[idx]], axis=1).tolist()
         t0 = time.perf_counter()
-        model.fittingObjective(cands)
+        last = (idx, fit(cands))
         out.append((time.perf_counter() - t0, n_cands))
-    return out
+    return out, {"kind": kind, "model_build_s": build_s}, last
 
 
 def cpu_reference_predictions(n_points):
     """predictions/s of the reference's per-point path (predict + predict_var + expimp per query point: the Python
     loop over the samples and the dgesv solves of matrixops.py:68-95, krige.py:201-234) on `n_points` points of the
-    C5 grid, n = 512 model, oracle port in reference order."""
-    from oracle import oracle_np as onp
-
+    C5 grid, n = 512 model.  Returns (dict, points, values)."""
     X, y = make_branin_samples(PRED_N)
-    model = onp.OracleKriging(X, y)
+    classes = _reference_classes()
+    if classes is not None:
+        model = classes[0](X, y)
+        kind = "reference"
+    else:
+        from oracle import oracle_np as onp
+
+        model = onp.OracleKriging(X, y)
+        kind = "port"
     model.update([5.0, 5.0, 1.8, 1.8])
     model.neglikelihood()
     ax = np.linspace(0.0, 1.0, PRED_GRID)
     idx = np.linspace(0, PRED_GRID * PRED_GRID - 1, n_points).astype(np.int64)
     pts = np.stack([ax[idx // PRED_GRID], ax[idx % PRED_GRID]], axis=1)
+    norm_range = model.normRange
+    vals = []
     t0 = time.perf_counter()
     for x in pts:
-        model.predict(x)
-        model.predict_var(x)
-        model.expimp(x)
+        # model-unit grid point -> the real-world point predict()/predict_var() normalise again (krige.py:180-199)
+        xr = np.array([x[d] * (norm_range[d][1] - norm_range[d][0]) + norm_range[d][0] for d in range(PRED_K)])
+        yh = model.predict(np.array(xr))
+        sv = model.predict_var(np.array(xr))
+        ei = model.expimp(np.array(x))
+        vals.append((float(yh), float(sv), float(ei)))
     secs = time.perf_counter() - t0
-    return {"value": n_points / secs, "unit": "predictions/s", "points": int(n_points), "n": PRED_N, "k": PRED_K,
-            "outputs": "yhat, s, EI per point",
-            "sample": "%d points of the 4096 x 4096 grid, one at a time as the reference does" % n_points}
+    res = {"value": n_points / secs, "unit": "predictions/s", "points": int(n_points), "n": PRED_N, "k": PRED_K,
+           "outputs": "yhat, s, EI per point", "kind": kind,
+           "sample": "%d points of the 4096 x 4096 grid, one at a time as the reference does" % n_points}
+    return res, idx, np.array(vals), model
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     sample = 4
-    res = cpu_reference_evals(sample, list(range(args.warmup + args.steps)))
+    res, info, _ = cpu_reference_evals(sample, list(range(args.warmup + args.steps)))
     timed = res[args.warmup:]
     secs = sum(t for t, _ in timed)
     evals = sum(e for _, e in timed)
     value = evals / secs
     cores = os.cpu_count()
-    pred = cpu_reference_predictions(24)
+    pred = cpu_reference_predictions(24)[0]
+    what = ("the unmodified reference (pyKriging.krige.kriging.fittingObjective, shipped under oracle/_ref)"
+            if info["kind"] == "reference" else "NumPy/OpenBLAS oracle port of matrixops.py:24-56")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": info["kind"],
                              "sample": "%d of the %d candidates of each step (evenly spaced over both candidate "
-                                       "families), NumPy/OpenBLAS oracle port of matrixops.py:24-56 with all host "
-                                       "threads" % (sample, POP)},
+                                       "families) through %s with all host threads; kriging(X, y) itself "
+                                       "(normalizeData + the O(n^2) Python loop of updateData) took %.2f s once and "
+                                       "is not in the rate" % (sample, POP, what, info["model_build_s"])},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "predictions": pred,
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ---- BASELINE configs[2] as written: ONE population of 1024 sharded over the ranks -----------------------------
+def run_strong(torch, dist, dev, model, h, rank, world, steps, warmup, weak_ms_per_step):
+    """Strong scaling of the population loop through the PRODUCT path: every rank holds the same model and the same
+    1024 candidates (replicated GA/PSO state), `enable_sharding()` makes `fittingObjective` evaluate this rank's
+    slice and gather the per-candidate scalars with ONE all_gather, which is inside the timed region.  Times are
+    wall clock per generation (the call returns host arrays, so it is synchronous), max over ranks."""
+    from pykriging_b200 import sharding
+
+    C, k = POP, K_DIMS
+    gens = warmup + steps
+    cands = [make_candidates(C, k, 5000 + s) for s in range(gens)]      # identical on every rank
+    lists = [np.concatenate(c, axis=1).tolist() for c in cands[:gens]]  # what inspyred hands to fittingObjective
+    if world > 1:
+        model.enable_sharding()
+
+    def gen_raw(s):
+        return model._pk_nll_population(cands[s][0], cands[s][1], None, 0)
+
+    def gen_api(s):
+        return model.fittingObjective(lists[s], {})
+
+    def sync_all():
+        h.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def timed(fn):
+        for s in range(warmup):
+            fn(s)
+        sync_all()
+        per = []
+        for s in range(warmup, gens):
+            t0 = time.perf_counter()
+            fn(s)
+            per.append((time.perf_counter() - t0) * 1e3)
+        t = torch.tensor(per, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # a generation ends when its slowest rank returns
+        return t.tolist()
+
+    # collectives per generation, counted on the live process group
+    ncoll = {"n": 0}
+    if dist is not None:
+        originals = {}
+        for name in ("all_gather_into_tensor", "all_reduce", "all_gather", "broadcast", "barrier", "reduce_scatter_tensor"):
+            originals[name] = getattr(dist, name)
+
+            def counted(*a, _orig=originals[name], **kw):
+                ncoll["n"] += 1
+                return _orig(*a, **kw)
+
+            setattr(dist, name, counted)
+        gen_raw(0)
+        for name, fn in originals.items():
+            setattr(dist, name, fn)
+    collectives_per_generation = ncoll["n"]
+
+    raw_ms = timed(gen_raw)
+    api_ms = timed(gen_api)
+    # phases of this rank's slice (kernels serialised by the profiling events), the rest is host + collective
+    h.set_profiling(True)
+    h.phase_times()
+    for s in range(warmup, gens):
+        gen_raw(s)
+    ph = h.phase_times()
+    h.set_profiling(False)
+    kernels_ms = (ph["psi"] + ph["cholesky"] + ph["epilogue"]) / steps
+    # bit-equality of the sharded fitness table with the unsharded evaluation of the same population on this GPU
+    sharded = gen_raw(0)
+    model.disable_sharding()
+    single = h.nll_batch(cands[0][0], cands[0][1], None, 0)
+    same = all(np.array_equal(sharded[nm], single[nm], equal_nan=True) for nm in ("nll", "mu", "sigma2", "lndet", "info"))
+    nranks_seen = 1
+    if dist is not None:
+        flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item() == 1.0)
+        ids = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(ids, torch.tensor([float(rank)], dtype=torch.float64, device=dev))
+        nranks_seen = int(len(set(ids.tolist())))
+    med_raw, med_api = float(np.median(raw_ms)), float(np.median(api_ms))
+    return {"what": "ONE population of %d candidates (n=%d, k=%d) per generation, sharded over %d GPU(s) through "
+                    "matrixops.enable_sharding(); per generation: slice -> pk_nll_batch (device outputs) -> one all_gather "
+                    "of 5 doubles per candidate + 1 status word per rank -> one D2H copy" % (C, N_SAMPLES, k, world),
+            "scaling": "strong", "n_gpus": world, "candidates_per_gpu": -(-C // world),
+            "value": C / (med_raw * 1e-3), "unit": UNIT,
+            "ms_per_generation_median": med_raw, "ms_per_generation_mean": float(np.mean(raw_ms)),
+            "api": {"call": "kriging.fittingObjective(list of %d lists, {}) -> list" % C, "value": C / (med_api * 1e-3),
+                    "ms_per_generation_median": med_api},
+            "phase_ms_per_generation": {"psi": ph["psi"] / steps, "cholesky": ph["cholesky"] / steps,
+                                        "epilogue": ph["epilogue"] / steps,
+                                        "gather_and_host": max(0.0, med_raw - kernels_ms)},
+            "one_gpu_ms_per_1024_step": weak_ms_per_step,
+            "speedup_vs_one_gpu_step": weak_ms_per_step / med_raw,
+            "collectives_per_generation": collectives_per_generation,
+            "comm_nranks_ok": nranks_seen == world, "sharded_equals_single": same,
+            "backend": "nccl" if sharding.uses_nccl() else "none (single process)"}
+
+
+# ---- other shapes the reference's defaults produce (driver-run, not only builder probes) ------------------------
+def run_shapes(torch, dev, local_rank, peak):
+    """C4 (regression kriging, n = 4096, k = 6, lambda) with 8 and with 150 candidates (the reference's default
+    regression swarm, regressionkrige.py:376), and the interpolating default population of 300 (krige.py:379,394)
+    at the C3 shape: evals/s, the Cholesky's TFLOP/s and its fraction of the measured DMMA peak."""
+    from pykriging_b200._lib import Handle
+
+    out = {}
+    h = Handle(local_rank)
+    for key, n, k, mode, Cs in (("c4", 4096, 6, 1, (8, 150)), ("pop300", N_SAMPLES, K_DIMS, 0, (300,))):
+        if mode:
+            rng = np.random.default_rng(11)
+            X = np.zeros((n, k))
+            for d in range(k):
+                X[:, d] = (rng.permutation(n) + 0.5) / n
+            y = np.sum((X - 0.25) ** 2, axis=1) + rng.normal(0.0, 0.05, n)
+            y = (y - y.min()) / (y.max() - y.min())
+        else:
+            X, y = make_samples(n, k)
+            y = (y - y.min()) / (y.max() - y.min())
+        h.set_data(X, y)
+        rows = []
+        for C in Cs:
+            rng = np.random.default_rng(100 + C)
+            if mode:
+                th = torch.from_numpy(rng.uniform(1e-4, 100, (C, k))).to(dev)
+                p = torch.from_numpy(rng.uniform(1.81231, 2.0, (C, k))).to(dev)
+                lam = torch.from_numpy(rng.uniform(0, 1, C)).to(dev)
+            else:
+                t_, p_ = make_candidates(C, k, 100 + C)
+                th, p, lam = torch.from_numpy(t_).to(dev), torch.from_numpy(p_).to(dev), None
+            o = torch.empty(4, C, dtype=torch.float64, device=dev)
+            info = torch.empty(C, dtype=torch.int32, device=dev)
+            reps = 3
+            h.nll_batch_raw(C, th, p, lam, mode, o[0], o[1], o[2], o[3], info)
+            h.synchronize()
+            stream = torch.cuda.ExternalStream(h.stream, device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for _ in range(reps):
+                    h.nll_batch_raw(C, th, p, lam, mode, o[0], o[1], o[2], o[3], info)
+                e1.record(stream)
+            h.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            h.set_profiling(True)
+            h.phase_times()
+            for _ in range(reps):
+                h.nll_batch_raw(C, th, p, lam, mode, o[0], o[1], o[2], o[3], info)
+            ph = h.phase_times()
+            h.set_profiling(False)
+            chol_ms = ph["cholesky"] / reps
+            tf = C * n ** 3 / 3.0 / (chol_ms * 1e-3) * 1e-12
+            rows.append({"candidates": C, "evals_per_s": C / (ms * 1e-3), "ms": ms, "psi_ms": ph["psi"] / reps,
+                         "cholesky_ms": chol_ms, "cholesky_tflops": tf, "frac_of_dmma_peak": tf / peak["dmma_tflops"],
+                         "failed": int((info != 0).sum().item())})
+        out[key] = {"n": n, "k": k, "regression": bool(mode), "runs": rows}
+    h.close()
+    return out
+
+
+def run_api(model, steps, warmup):
+    """The reference-facing Python API on one GPU: `kriging.fittingObjective(list of lists, args) -> list` (what
+    inspyred calls once per generation, krige.py:429-452) and a whole seeded `train('ga', pop_size=1024)` at the C3
+    shape (GA generations + SLSQP polish + the lazy refit)."""
+    C, k = POP, K_DIMS
+    lists = [np.concatenate(make_candidates(C, k, 7000 + s), axis=1).tolist() for s in range(warmup + steps)]
+    for s in range(warmup):
+        model.fittingObjective(lists[s], {})
+    per = []
+    for s in range(warmup, warmup + steps):
+        t0 = time.perf_counter()
+        fit = model.fittingObjective(lists[s], {})
+        per.append((time.perf_counter() - t0) * 1e3)
+    assert len(fit) == C
+    med = float(np.median(per))
+    t0 = time.perf_counter()
+    model.train(optimizer='ga', seed=2024, pop_size=C)
+    train_s = time.perf_counter() - t0
+    ea = model._last_ea
+    return {"e2e_api": {"call": "kriging.fittingObjective(list of %d lists of %d floats, {}) -> list of %d floats" % (C, 2 * k, C),
+                        "value": C / (med * 1e-3), "unit": UNIT, "ms_per_step_median": med,
+                        "ms_per_step_mean": float(np.mean(per))},
+            "train_wall_s": train_s,
+            "train": {"call": "kriging.train('ga', seed=2024, pop_size=%d)" % C, "generations": int(ea.num_generations),
+                      "evaluations": int(ea.num_evaluations), "wall_s": train_s}}
 
 
 # ---- this repo's arm -----------------------------------------------------------------------------------------
@@ -347,17 +586,21 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     launches0 = h.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_step = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     sampler.start()
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        for s in range(args.warmup, n_steps):
+        ev_step[0].record(stream)
+        for i, s in enumerate(range(args.warmup, n_steps)):
             step_device(s)
+            ev_step[i + 1].record(stream)
         ev1.record(stream)
     h.synchronize()
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    step_ms = [ev_step[i].elapsed_time(ev_step[i + 1]) for i in range(args.steps)]
     launches = h.launch_count - launches0
     fails = int((info_dev != 0).sum().item())
 
@@ -392,9 +635,20 @@ def run_ours(args, rank, world, local_rank):
     value = evals / (ms_max * 1e-3)
     e2e_value = evals / (e2e_ms_max * 1e-3)
 
+    # ---- BASELINE configs[2]: one population of 1024 sharded over the ranks, all_gather inside the timed step ----
+    h.set_cholesky_variant(0)
+    strong = run_strong(torch, dist, dev, model, h, rank, world, args.steps, args.warmup, ms_max / args.steps)
+    shapes, api = None, None
+    if world == 1 and not args.no_extras:
+        shapes = run_shapes(torch, dev, local_rank, peak)
+        api = run_api(model, min(args.steps, 10), 2)
+    # step 0 of this rank once more for the parity sample (the reference arm evaluates 48 of its candidates below)
+    step0 = h.nll_batch(th_host[0].numpy(), p_host[0].numpy(), None, 0) if rank == 0 else None
+
     pred = None
+    pred_model = None
     if not args.no_predictions:
-        pred = run_predictions(torch, dev, local_rank, rank, world, dist)
+        pred, pred_model = run_predictions(torch, dev, local_rank, rank, world, dist)
     traffic = load_traffic()
     if rank == 0:
         if pred is not None:
@@ -415,14 +669,19 @@ def run_ours(args, rank, world, local_rank):
         psi_gbs = psi_bytes / (phases["psi"] * 1e-3) * 1e-9 if phases["psi"] > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "ms_per_step_median": float(np.median(step_ms)),
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * C * k * 8,
                     "d2h_bytes_per_step": 4 * C * 8 + 4 * C, "api": "pk_nll_batch (C ABI) with pinned host buffers"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "cta::chol_cta_kernel (persistent blocked Cholesky, one CTA per candidate, "
-                                   "DMMA 8x8x4, TMA-fed stages)" if args.chol_variant != 1 else "chol_first_kernel + chol_step_kernel",
+            "roofline": {"kernel": {0: "cta::chol_cta_kernel (persistent blocked Cholesky, one CTA per candidate, DMMA 8x8x4, "
+                                       "TMA-fed stages; what the automatic choice runs for a population of 1024 -- "
+                                       "populations that are not whole waves run cta::chol_task_kernel, see pop300 / c4 / strong)",
+                                    1: "chol_first_kernel + chol_step_kernel",
+                                    2: "cta::chol_cta_kernel (one CTA per candidate)", 3: "cta::chol_cta_kernel (gangs)",
+                                    4: "cta::chol_task_kernel (task mode)"}[args.chol_variant],
                          "bound": "tensor", "achieved": chol_tf, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
                          "frac": (chol_tf / peak["dmma_tflops"]) if chol_tf else None,
                          "traffic": (traffic or {}).get("chol_cta_kernel_dram_bytes_per_launch"),
@@ -446,17 +705,54 @@ def run_ours(args, rank, world, local_rank):
                                                 (phases["psi"] * 1e-3) * 1e-12 / peak["dfma_tflops"])
                              if phases["psi"] > 0 else None},
             "predictions": pred,
+            "strong": strong,
             "fp64_peak": peak, "failed_factorisations_last_step": fails,
         }
+        if shapes is not None:
+            line.update(shapes)
+        if api is not None:
+            line.update(api)
         if world == 1 and not args.no_cpu_baseline:
+            parity = {}
             if pred is not None:
-                pred["cpu_baseline"] = cpu_reference_predictions(24)
-            res = cpu_reference_evals(CPU_BASELINE_SAMPLE, [0])
+                pcpu, pidx, pvals, ref_model = cpu_reference_predictions(24)
+                pred["cpu_baseline"] = pcpu
+                # the same 24 grid points through the CUDA predictor (model units in, model units out; the reference's
+                # predict() de-normalises yhat)
+                pm, ph_ = pred_model
+                ax = np.linspace(0.0, 1.0, PRED_GRID)
+                pts = np.stack([ax[pidx // PRED_GRID], ax[pidx % PRED_GRID]], axis=1)
+                g = ph_.predict_batch(pts, np.array([5.0, 5.0]), np.array([1.8, 1.8]), float(pm.mu), float(pm.SigmaSqr),
+                                      y_min=float(np.min(pm.y)))
+                yh = pm.inversenormy(g["yhat"])
+                sig = float(np.sqrt(pm.SigmaSqr))
+                parity["predictions"] = {"points": int(len(pidx)), "against": pcpu["kind"],
+                                         "yhat_max_rel_err": float(np.max(np.abs(yh - pvals[:, 0]) / np.abs(pvals[:, 0]))),
+                                         "s_max_abs_err_over_sigma": float(np.max(np.abs(g["s"] - pvals[:, 1])) / sig),
+                                         "ei_max_abs_err_over_sigma": float(np.max(np.abs(g["ei"] - pvals[:, 2])) / sig)}
+            res, info, last = cpu_reference_evals(CPU_BASELINE_SAMPLE, [0])
             secs, ev = res[0]
-            line["cpu_baseline"] = {"value": ev / secs, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "%d candidates of step 0 (evenly spaced over both families) through "
-                                              "the NumPy/OpenBLAS oracle port of matrixops.py:24-56, all host "
-                                              "threads (about 10 s of CPU work)" % CPU_BASELINE_SAMPLE}
+            what = ("the unmodified reference (pyKriging.krige.kriging.fittingObjective, shipped under oracle/_ref)"
+                    if info["kind"] == "reference" else "the NumPy/OpenBLAS oracle port of matrixops.py:24-56")
+            line["cpu_baseline"] = {"value": ev / secs, "unit": UNIT, "cores": os.cpu_count(), "kind": info["kind"],
+                                    "sample": "%d candidates of step 0 (evenly spaced over both families) through %s, "
+                                              "all host threads; kriging(X, y) itself (normalizeData + updateData's O(n^2) "
+                                              "Python loop) took %.2f s once and is not in the rate"
+                                              % (CPU_BASELINE_SAMPLE, what, info["model_build_s"])}
+            # the benchmarked inputs, checked: the same candidates of step 0 on the GPU against the reference's values
+            idx, ref_fit = last
+            rel, pen_ref, pen_gpu = [], 0, 0
+            for i, f in zip(idx, ref_fit):
+                bad_ref = isinstance(f, int) and f == 10000
+                bad_gpu = step0["info"][i] != 0
+                pen_ref += bad_ref
+                pen_gpu += bad_gpu
+                if not bad_ref and not bad_gpu:
+                    rel.append(abs(step0["nll"][i] - float(f)) / max(1e-300, abs(float(f))))
+            parity["likelihood"] = {"candidates": int(len(idx)), "against": info["kind"],
+                                    "nll_max_rel_err": float(max(rel)) if rel else None,
+                                    "penalties_reference": int(pen_ref), "penalties_gpu": int(pen_gpu)}
+            line["parity_sample"] = parity
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -471,7 +767,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predictions", action="store_true")
-    ap.add_argument("--chol-variant", type=int, default=0, help="0 auto, 1 per-block-column launches, 2 persistent CTA")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c4 / pop300 / e2e_api / train blocks")
+    ap.add_argument("--chol-variant", type=int, default=0,
+                    help="0 auto, 1 per-block-column launches, 2 one persistent CTA per candidate, 3 gangs, 4 task mode")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -143,6 +143,11 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     _, _, T = load_reference()
     tf = T()
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
+
+    def case_if(name, *a, **kw):
+        if not only or name in only:
+            case(name, *a, **kw)
 
     # ---- C1: 2-D Branin, 20-point optimal LHC (BASELINE configs[0]) ---------------------
     X = load_sampling_plan(2, 20)
@@ -154,7 +159,7 @@ def main():
     rng = np.random.default_rng(7)
     pts = [[0.3, 0.6], [0.0, 0.0], [1.0, 1.0], [0.5, 0.5]] + rng.uniform(0, 1, (12, 2)).tolist()
     pts.append(list(onp.normalize_data(X, y)[0][3]))  # exactly on a sample point (s -> 0)
-    case("c1_branin_n20_k2", X, y, cands, [fixed[0], fixed[4], fixed[7]], pts)
+    case_if("c1_branin_n20_k2", X, y, cands, [fixed[0], fixed[4], fixed[7]], pts)
 
     # ---- C2: 3-D 'squared', 40-point optimal LHC (BASELINE configs[1]) ------------------
     X = load_sampling_plan(3, 40)
@@ -165,7 +170,7 @@ def main():
                      + onp.candidates_loguniform(32, 3, 202, lo=-3.0).tolist())
     rng = np.random.default_rng(8)
     pts = [[0.25, 0.25, 0.25], [0, 0, 0], [1, 1, 1]] + rng.uniform(0, 1, (13, 3)).tolist()
-    case("c2_squared_n40_k3", X, y, cands, [fixed3[1], fixed3[4]], pts)
+    case_if("c2_squared_n40_k3", X, y, cands, [fixed3[1], fixed3[4]], pts)
 
     # ---- regression kriging, small (2-D noisy Branin, 20 pt) ----------------------------
     X = load_sampling_plan(2, 20)
@@ -176,7 +181,7 @@ def main():
     cands = np.array(fixedr + onp.candidates_uniform(25, 2, 301, regression=True).tolist())
     rng = np.random.default_rng(10)
     pts = [[0.3, 0.6], [0.0, 1.0]] + rng.uniform(0, 1, (10, 2)).tolist()
-    case("reg_branin_noise_n20_k2", X, y, cands, [fixedr[3], fixedr[4]], pts, regression=True)
+    case_if("reg_branin_noise_n20_k2", X, y, cands, [fixedr[3], fixedr[4]], pts, regression=True)
 
     # ---- mid size, drives the blocked large-n path: n=300, k=10 (rlh seed) ---------------
     X = onp.rlh(300, 10, 1234)
@@ -185,26 +190,33 @@ def main():
                             np.array([[1e-5] * 10 + [2.0] * 10])])
     rng = np.random.default_rng(11)
     pts = rng.uniform(0, 1, (6, 10)).tolist()
-    case("mid_stybtang_n300_k10", X, y, cands, [cands[8]], pts, store_inputs=False,
+    case_if("mid_stybtang_n300_k10", X, y, cands, [cands[8]], pts, store_inputs=False,
          recipe="X=oracle_np.rlh(300,10,1234); y=oracle_np.f_stybtang_norm(X)")
 
     # ---- mid size regression, n=257 (ragged vs. every tile size), k=6 ---------------------
     X = onp.rlh(257, 6, 11)
     rng = np.random.default_rng(12)
     y = onp.f_squared(X) + rng.normal(0.0, 0.05, 257)
-    cands = onp.candidates_uniform(8, 6, 501, regression=True)
+    # uniform candidates give Psi ~ I (cond < 2: too easy for the tiled regression path); the log-uniform ones with
+    # a small nugget reach cond(Psi) 1e5 .. 1e9, and one candidate without nugget is numerically singular
+    rng = np.random.default_rng(502)
+    hard = np.column_stack([10 ** rng.uniform(-3.5, -0.5, (12, 6)), rng.uniform(1.81231, 2.0, (12, 6)),
+                            10 ** rng.uniform(-9.0, -3.0, 12)])
+    cands = np.concatenate([onp.candidates_uniform(8, 6, 501, regression=True), hard,
+                            np.array([[1e-4] * 6 + [2.0] * 6 + [0.0]])])
     rng = np.random.default_rng(13)
     pts = rng.uniform(0, 1, (6, 6)).tolist()
-    case("mid_reg_squared_n257_k6", X, y, cands, [cands[0]], pts, regression=True, store_inputs=False,
+    case_if("mid_reg_squared_n257_k6", X, y, cands, [cands[0], cands[9]], pts, regression=True, store_inputs=False,
          recipe="X=oracle_np.rlh(257,6,11); y=oracle_np.f_squared(X)+default_rng(12).normal(0,0.05,257)")
 
     # ---- headline shape C3: n=1024, k=10; a handful of candidates through the reference ---
     X = onp.rlh(1024, 10, 1234)
     y = onp.f_stybtang_norm(X)
-    cands = np.concatenate([onp.candidates_uniform(3, 10, 1), onp.candidates_loguniform(5, 10, 2)])
+    cands = np.concatenate([onp.candidates_uniform(3, 10, 1), onp.candidates_loguniform(5, 10, 2),
+                            onp.candidates_loguniform(8, 10, 3, lo=-4.0, hi=0.5)])
     rng = np.random.default_rng(14)
     pts = rng.uniform(0, 1, (3, 10)).tolist()
-    case("c3_stybtang_n1024_k10", X, y, cands, [cands[4]], pts, store_inputs=False,
+    case_if("c3_stybtang_n1024_k10", X, y, cands, [cands[4]], pts, store_inputs=False,
          recipe="X=oracle_np.rlh(1024,10,1234); y=oracle_np.f_stybtang_norm(X)")
 
 

@@ -338,6 +338,27 @@ class OracleKriging(object):
             fitness.append(f)
         return fitness
 
+    # -- krige.py:135-156 ----------------------------------------------------------------
+    def addPoint(self, newX, newy, norm=True):
+        """Append a sample, rebuild the distance tensor (updateData) and refactorise (updateModel).  mu / SigmaSqr
+        are NOT refreshed, exactly as in the reference.  (The reference retrains when updateModel raises; the oracle
+        lets the exception through -- the tests do not go there.)"""
+        if norm:
+            newX = norm_x(newX, self.normRange)
+            newy = norm_y(newy, self.ynormRange)
+        self.X = np.append(self.X, [newX], axis=0)
+        self.y = np.append(self.y, newy)
+        self.n = self.X.shape[0]
+        self.distance = distance_tensor(self.X)
+        self.updateModel()
+
+    # -- krige.py:236-258 ----------------------------------------------------------------
+    def infill_objective_mse(self, candidates, args=None):
+        return [-1 * self.predicterr_normalized(np.asarray(entry, dtype=float)) for entry in candidates]
+
+    def infill_objective_ei(self, candidates, args=None):
+        return [-1 * self.expimp(np.asarray(entry, dtype=float)) for entry in candidates]
+
     # -- predictors -----------------------------------------------------------------------
     def predict_normalized(self, x):
         return predict_normalized_ref(self.X, self.y, self.U, self.mu, self.theta, self.pl, x)

@@ -131,6 +131,7 @@ class Handle(object):
         self.device = int(device)
         self.n = 0
         self.k = 0
+        self.pivot_tol = 2.0 * 2.220446049250313e-16  # the library's default (pk_set_pivot_tolerance)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -273,6 +274,7 @@ class Handle(object):
 
     def set_pivot_tolerance(self, tol):
         self._check(self.lib.pk_set_pivot_tolerance(self._h, float(tol)), "pk_set_pivot_tolerance")
+        self.pivot_tol = float(tol)
 
     def set_cholesky_variant(self, variant):
         """0 auto, 1 per-block-column launches, 2 persistent CTA per candidate, 3 the same with gangs of CTAs per candidate,

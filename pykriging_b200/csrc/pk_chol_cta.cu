@@ -1300,9 +1300,8 @@ cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, doubl
         const long long slots = 2LL * h->sm_count;
         int a_sb, a_bpt;
         if ((long long)C * 5 <= slots) { a_sb = 0; a_bpt = 1; }            // <= 59 candidates: 64-row tasks throughout
-        else if ((long long)C * 3 <= slots * 2) { a_sb = 4; a_bpt = 2; }   // <= 197
-        else if ((long long)C <= slots + slots / 2) { a_sb = 0; a_bpt = 2; }
-        else { a_sb = 0; a_bpt = cta::TASK_MAX_BLOCKS; }
+        else if ((long long)C * 4 <= slots * 3) { a_sb = 4; a_bpt = 2; }   // <= 222: 128-row tasks, 64-row ones in the late columns
+        else { a_sb = 0; a_bpt = cta::TASK_MAX_BLOCKS; }                    // a wave or more: one panel task per block column
         if (single_below < 0) single_below = a_sb;
         if (bpt <= 0) bpt = a_bpt;
     }

@@ -25,6 +25,18 @@ from .optimizers import GA, PSO, Bounder
 from .samplingplan import samplingplan
 
 
+def _scipy_has_workers():
+    """SLSQP's ``workers`` map hook exists from SciPy 1.16 on; older versions would silently ignore it (an
+    OptimizeWarning) and run the stencil sequentially -- same numbers, just slower, so fall back without it."""
+    import scipy
+
+    try:
+        major, minor = (int(v) for v in scipy.__version__.split(".")[:2])
+    except ValueError:
+        return False
+    return (major, minor) >= (1, 16)
+
+
 class kriging(matrixops):
     _pk_mode = _lib.MODE_INTERP
 
@@ -323,7 +335,7 @@ class kriging(matrixops):
         SAME stencil points SciPy generates are handed to the device as one ``fittingObjective`` population
         through SciPy's ``workers`` map hook, so the iterates are those of the sequential run."""
         options = {'disp': False}
-        if self.slsqp_batched:
+        if self.slsqp_batched and _scipy_has_workers():
             options['workers'] = self._pk_stencil_map
         return minimize(self.fittingObjective_local, start, method='SLSQP', bounds=bounds, options=options)
 

@@ -73,7 +73,10 @@ class matrixops(object):
 
         h.set_shard_hint(population=theta.shape[0])
         try:
-            rows = sharding.sharded_rows(theta.shape[0], eval_slice, shard[0])
+            if sharding.uses_nccl(shard[0]):
+                rows = sharding.sharded_nll_device(h, theta, p, lam, mode, shard[0])
+            else:
+                rows = sharding.sharded_rows(theta.shape[0], eval_slice, shard[0], ncols=5)
         finally:
             h.set_shard_hint()
         return {"nll": rows[:, 0].copy(), "mu": rows[:, 1].copy(), "sigma2": rows[:, 2].copy(),
@@ -97,8 +100,23 @@ class matrixops(object):
         if pend is not None:
             self._pending_factor = None
             th, pl, lam, mode = pend
-            _, info = self._pk_handle().fit(th, pl, lam, mode)
-            self._factor_params = (th.copy(), pl.copy(), float(lam), mode) if info == 0 else None
+            h = self._pk_handle()
+            _, info = h.fit(th, pl, lam, mode)
+            if info != 0:
+                # The batch factorised this candidate; pk_fit runs other kernels (gangs, the L^-T rows) and a pivot on
+                # the knife edge of the relative test can come out on the other side.  Retry with LAPACK's literal rule
+                # (pivot <= 0); if even that fails, say so instead of predicting with an older factor.
+                tol = h.pivot_tol
+                h.set_pivot_tolerance(0.0)
+                try:
+                    _, info = h.fit(th, pl, lam, mode)
+                finally:
+                    h.set_pivot_tolerance(tol)
+                if info != 0:
+                    self._factor_params = None
+                    raise _lib.PkError("the factor of the last successfully evaluated candidate could not be re-created "
+                                       "(info = %d): Psi is numerically singular" % info)
+            self._factor_params = (th.copy(), pl.copy(), float(lam), mode)
             self._U_host = None
             self._psi_host = None
 
@@ -236,7 +254,7 @@ class matrixops(object):
 
         h.set_shard_hint(query_points=Xq.shape[0])
         try:
-            rows = sharding.sharded_rows(Xq.shape[0], eval_slice, shard[0])
+            rows = sharding.sharded_rows(Xq.shape[0], eval_slice, shard[0], ncols=len(names))
         finally:
             h.set_shard_hint()
         out = {"yhat": None, "s": None, "ei": None}
@@ -268,3 +286,46 @@ class matrixops(object):
     def predict_all_batch(self, X, w=None):
         y_min = float(np.min(self.y))
         return self._pk_predict(X, ("yhat", "s", "ei"), y_min=y_min, ei_weight=-1.0 if w is None else float(w))
+
+    # -- arg-max over a query set: what infill is after (krige.py:248-258, 292) --------------------------
+    def _pk_argmax(self, X, name, **kw):
+        """(max value, index into X) of one predictor output over the query set X.  With sharding enabled every rank
+        evaluates only ITS rows of X and the ranks exchange one (value, index) pair each -- ONE all_gather of 16 bytes
+        per rank; the full arrays never leave the GPU that computed them.  Ties resolve to the lowest index, as max()
+        over the reference's in-order Python list does."""
+        Xq = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=float)))
+        shard = self.__dict__.get("_pk_shard")
+        if shard is None:
+            vals = self._pk_predict(Xq, (name,), **kw)[name]
+            i = int(np.argmax(vals))
+            return float(vals[i]), i
+        self._pk_ensure_factor()
+        if not self._has_U:
+            raise AttributeError("'NoneType' object has no attribute 'T'")
+        h = self._pk_handle()
+        rank, world = sharding.rank_and_world(shard[0])
+        lo, hi = sharding.shard_bounds(Xq.shape[0], rank, world)
+        h.set_shard_hint(query_points=Xq.shape[0])
+        err, vals = None, np.zeros(0)
+        try:
+            if hi > lo:
+                vals = h.predict_batch(Xq[lo:hi], np.asarray(self.theta, dtype=float), np.asarray(self.pl, dtype=float),
+                                       float(self.mu), float(self.SigmaSqr), want=(name,), **kw)[name]
+        except Exception as e:  # noqa: BLE001 -- reaches every rank through the collective below
+            err = e
+        finally:
+            h.set_shard_hint()
+        try:
+            return sharding.global_argmax(vals, lo, shard[0], failed=err is not None)
+        except sharding.ShardError:
+            if err is not None:
+                raise err
+            raise
+
+    def expimp_argmax(self, X, w=None):
+        """Largest expected improvement over the model-unit points X: (EI, index)."""
+        return self._pk_argmax(X, "ei", y_min=float(np.min(self.y)), ei_weight=-1.0 if w is None else float(w))
+
+    def predicterr_argmax(self, X):
+        """Largest predicted RMSE over the model-unit points X: (s, index)."""
+        return self._pk_argmax(X, "s")

@@ -6,7 +6,9 @@ replicated ``(X, y)`` / a replicated fitted state, so with one process per GPU (
 
   * population: rank r evaluates candidates ``[r*ceil(C/W), (r+1)*ceil(C/W))`` on its GPU and ONE
     ``all_gather`` of the per-candidate scalars (NegLnLike, mu, SigmaSqr, LnDetPsi, info -- 40 bytes per
-    candidate) gives every rank the full fitness vector.  GA/PSO state is evolved redundantly and
+    candidate, plus one status word per rank so that a failure reaches every rank inside the same
+    collective) gives every rank the full fitness vector.  On GPUs the kernels write straight into the
+    send buffer and the collective runs on the handle's stream (``sharded_nll_device``).  GA/PSO state is evolved redundantly and
     deterministically on every rank from the same seed, so nothing else is exchanged;
   * query grid: rank r predicts rows ``[lo, hi)`` of the query array; the arg-max of the expected
     improvement (what ``infill`` needs) is one ``all_gather`` of a (value, index) pair per rank.
@@ -43,75 +45,154 @@ def _comm_device(dist, group):
     return torch.device("cpu")
 
 
-def all_gather_rows(local, count, group=None):
+class ShardError(RuntimeError):
+    """Raised on EVERY rank when the evaluation of some rank's slice failed (the failing rank re-raises its own
+    exception instead): nobody is left waiting in the next collective."""
+
+
+def all_gather_rows(local, count, group=None, ncols=None, status=0.0):
     """``local``: float64 array with this rank's rows (its ``shard_bounds`` slice of ``count`` rows,
-    any number of columns).  Returns the (count, ncols) array of all ranks, identical on every rank."""
+    ``ncols`` columns).  ONE all_gather; returns ((count, ncols) array of all ranks, per-rank status vector),
+    identical on every rank.  ``status`` travels with the rows (one extra row per rank), so that a rank whose
+    evaluation failed can say so inside the same collective."""
     import torch
 
     dist = _dist()
     local = np.ascontiguousarray(np.asarray(local, dtype=np.float64))
     if local.ndim == 1:
         local = local[:, None]
+    if ncols is None:
+        ncols = local.shape[1]
     if dist is None or dist.get_world_size(group) == 1:
-        return local
+        return local.reshape(-1, ncols), np.array([float(status)])
     world = dist.get_world_size(group)
     per = -(-int(count) // world)
-    ncols = local.shape[1]
     dev = _comm_device(dist, group)
-    buf = torch.zeros(per, ncols, dtype=torch.float64, device=dev)
+    buf = torch.zeros(per + 1, ncols, dtype=torch.float64)
     if local.shape[0]:
-        buf[: local.shape[0]] = torch.from_numpy(local).to(dev)
-    out = torch.empty(world * per, ncols, dtype=torch.float64, device=dev)
+        buf[: local.shape[0]] = torch.from_numpy(local.reshape(-1, ncols))
+    buf[per, 0] = float(status)
+    buf = buf.to(dev)
+    out = torch.empty(world * (per + 1), ncols, dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(out, buf, group=group)
-    return out[:count].cpu().numpy()
+    out = out.cpu().numpy().reshape(world, per + 1, ncols)
+    rows = out[:, :per, :].reshape(world * per, ncols)[:count]
+    return np.ascontiguousarray(rows), out[:, per, 0].copy()
 
 
-def sharded_rows(count, eval_slice, group=None):
-    """Evaluate ``eval_slice(lo, hi) -> (hi-lo, ncols) float64`` on this rank's slice and gather."""
+def sharded_rows(count, eval_slice, group=None, ncols=None):
+    """Evaluate ``eval_slice(lo, hi) -> (hi-lo, ncols) float64`` on this rank's slice and gather: ONE collective per
+    call.  ``ncols`` must be given when a rank's slice can be empty (it cannot learn the width from its own result).
+    If ``eval_slice`` raises on any rank, every rank raises (the failing one its own exception, the others
+    ``ShardError``) AFTER the collective, so the process group stays usable."""
     dist = _dist()
     if dist is None or dist.get_world_size(group) == 1:
         return np.asarray(eval_slice(0, count), dtype=np.float64).reshape(count, -1)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = shard_bounds(count, rank, world)
-    local = eval_slice(lo, hi) if hi > lo else np.zeros((0, 1))
-    local = np.asarray(local, dtype=np.float64)
+    err = None
+    local = None
     if hi > lo:
-        local = local.reshape(hi - lo, -1)
-    ncols = _agree_ncols(local.shape[1] if hi > lo else 0, group)
-    if hi <= lo:
-        local = np.zeros((0, ncols))
-    return all_gather_rows(local, count, group)
+        try:
+            local = np.asarray(eval_slice(lo, hi), dtype=np.float64).reshape(hi - lo, -1)
+        except Exception as e:  # noqa: BLE001 -- reported to every rank below
+            err = e
+    if ncols is None:
+        # width unknown to the caller: every rank must have a non-empty, successfully evaluated slice
+        if local is None:
+            raise err if err is not None else ValueError("sharded_rows: pass ncols when a slice can be empty")
+        ncols = local.shape[1]
+    if local is None:
+        local = np.full((hi - lo, ncols), np.nan)
+    rows, status = all_gather_rows(local, count, group, ncols=ncols, status=1.0 if err is not None else 0.0)
+    if err is not None:
+        raise err
+    if np.any(status != 0.0):
+        raise ShardError("evaluation of the slice failed on rank(s) %s" % np.nonzero(status)[0].tolist())
+    return rows
 
 
-def _agree_ncols(ncols, group):
+def sharded_nll_device(handle, theta, p, lam, mode, group=None):
+    """The population path on GPUs (NCCL): this rank's slice goes through ``pk_nll_batch`` with DEVICE outputs, the
+    five per-candidate numbers (NegLnLike, mu, SigmaSqr, LnDetPsi, info) plus a status word are gathered by ONE
+    ``all_gather`` on the handle's stream, and one device-to-host copy returns the (C, 5) table -- no host round trip
+    between the kernels and the collective.  Same contract as ``sharded_rows``."""
     import torch
 
+    from . import _lib
+
     dist = _dist()
-    t = torch.tensor([ncols], dtype=torch.int64, device=_comm_device(dist, group))
-    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    return int(t.item())
+    C = int(theta.shape[0])
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_bounds(C, rank, world)
+    per = -(-C // world)
+    dev = torch.device("cuda", handle.device)
+    stream = torch.cuda.ExternalStream(handle.stream, device=dev)
+    err = None
+    with torch.cuda.device(dev), torch.cuda.stream(stream):
+        loc = torch.full((6, per), float("nan"), dtype=torch.float64, device=dev)
+        info = torch.zeros(per, dtype=torch.int32, device=dev)
+        if hi > lo:
+            try:
+                handle.nll_batch_raw(hi - lo, np.ascontiguousarray(theta[lo:hi]), np.ascontiguousarray(p[lo:hi]),
+                                     None if lam is None else np.ascontiguousarray(lam[lo:hi]), mode,
+                                     loc[0], loc[1], loc[2], loc[3], info)
+            except _lib.PkError as e:
+                err = e
+        loc[4] = info.to(torch.float64)
+        loc[5].fill_(1.0 if err is not None else 0.0)
+        out = torch.empty(world, 6, per, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, loc, group=group)
+        host = out.cpu().numpy()
+    if err is not None:
+        raise err
+    if np.any(host[:, 5, 0] != 0.0):
+        raise ShardError("pk_nll_batch failed on rank(s) %s" % np.nonzero(host[:, 5, 0])[0].tolist())
+    rows = np.ascontiguousarray(host[:, :5, :].transpose(0, 2, 1).reshape(world * per, 5)[:C])
+    if np.any(rows[:, 4] < 0):
+        # info < 0: a spin-wait of the persistent Cholesky timed out on some rank; every rank sees it in the gathered table
+        raise ShardError("a Cholesky spin-wait timed out on the rank that owns candidate(s) %s"
+                         % np.nonzero(rows[:, 4] < 0)[0][:8].tolist())
+    return rows
 
 
-def global_argmax(local_values, lo, group=None):
+def rank_and_world(group=None):
+    dist = _dist()
+    if dist is None:
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def uses_nccl(group=None):
+    dist = _dist()
+    return dist is not None and dist.get_world_size(group) > 1 and str(dist.get_backend(group)).lower() == "nccl"
+
+
+def global_argmax(local_values, lo, group=None, failed=False):
     """Arg-max over a sharded 1-D array: ``local_values`` are this rank's entries, starting at global
     index ``lo``.  Returns (value, global_index), identical on every rank; ties resolve to the lowest
-    global index, as ``max()`` over the reference's in-order Python list would."""
+    global index, as ``max()`` over the reference's in-order Python list would.  ONE all_gather of a
+    (value, index, status) triple per rank; ``failed=True`` on any rank makes every rank raise ShardError."""
     import torch
 
     local_values = np.asarray(local_values, dtype=np.float64)
-    if local_values.size:
+    if local_values.size and not failed:
         i = int(np.argmax(local_values))
-        pair = np.array([[local_values[i], float(lo + i)]])
+        pair = np.array([[local_values[i], float(lo + i), 0.0]])
     else:
-        pair = np.array([[-np.inf, np.inf]])
+        pair = np.array([[-np.inf, np.inf, 1.0 if failed else 0.0]])
     dist = _dist()
     if dist is None or dist.get_world_size(group) == 1:
+        if failed:
+            raise ShardError("evaluation of the slice failed")
         return float(pair[0, 0]), int(pair[0, 1])
     world = dist.get_world_size(group)
     dev = _comm_device(dist, group)
-    out = torch.empty(world, 2, dtype=torch.float64, device=dev)
+    out = torch.empty(world, 3, dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(out, torch.from_numpy(pair).to(dev), group=group)
     pairs = out.cpu().numpy()
+    if np.any(pairs[:, 2] != 0.0):
+        raise ShardError("evaluation of the slice failed on rank(s) %s" % np.nonzero(pairs[:, 2])[0].tolist())
     best = np.max(pairs[:, 0])
     idx = int(np.min(pairs[pairs[:, 0] == best, 1]))
     return float(best), idx

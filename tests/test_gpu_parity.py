@@ -48,13 +48,19 @@ def test_nll_batch_matches_reference_golden(handle, name):
     cands = np.array([fha(r["candidate"]) for r in rows])
     th, p, lam = _split(cands, doc["k"], reg)
     out = handle.nll_batch(th, p, lam, mode=1 if reg else 0)
+    edge = [i for i, row in enumerate(rows) if row["ok"] and row["cond"] > 1e15]
+    if edge:
+        # numerically singular but factorised by the reference's BLAS: outcome is rounding noise there -- counted, with a
+        # floor, instead of compared one by one (see test_failure_agreement_with_lapack_has_a_floor)
+        agree = sum(1 for i in edge if out["info"][i] == 0)
+        assert agree >= len(edge) // 2, (agree, len(edge))
     for i, row in enumerate(rows):
         if not row["ok"]:
             assert out["info"][i] > 0, "reference failed to factorise candidate %d, CUDA path did not" % i
             assert np.isnan(out["nll"][i])
             continue
         if row["cond"] > 1e15:
-            continue  # numerically singular (cond > 1/eps): the reference's own outcome is BLAS-dependent
+            continue  # value comparison is meaningless beyond cond 1/eps (agreement counted above)
         assert out["info"][i] == 0
         tol = tol_for_cond(row["cond"])
         assert rel_err(out["nll"][i], fh(row["nll"])) < tol, (i, row["cond"])
@@ -427,7 +433,7 @@ def test_full_size_c3_population_properties(handle):
         assert np.array_equal(out2[name], out[name][perm], equal_nan=True), name
     assert np.array_equal(out2["info"], out["info"][perm])
     checked = 0
-    for i in (0, 255, 511, 512, 700, 1023):
+    for i in (0, 100, 255, 400, 511, 512, 513, 560, 600, 650, 700, 750, 800, 850, 900, 950, 1000, 1023):
         Psi = onp.psi_fast(Xn, th[i], p[i])
         nll, mu, s2, lndet, info = onp.neglikelihood_fast(Psi, yn)
         if info != 0:
@@ -442,7 +448,7 @@ def test_full_size_c3_population_properties(handle):
         assert rel_err(out["mu"][i], mu) < tol, (i, cond)
         assert rel_err(out["sigma2"][i], s2) < tol, (i, cond)
         checked += 1
-    assert checked >= 3
+    assert checked >= 10
 
 
 def test_full_size_c5_grid_properties(handle):
@@ -525,6 +531,38 @@ def test_task_mode_is_bit_identical_to_one_cta_per_candidate(handle, n, k, C):
     finally:
         handle.set_task_options()
         handle.set_cholesky_variant(0)
+
+
+@pytest.mark.parametrize("n,k,seed,C", [(20, 2, 1, 600), (100, 2, 3, 300), (300, 4, 4, 120)])
+def test_failure_agreement_with_lapack_has_a_floor(handle, n, k, seed, C):
+    """"Cholesky failed" (-> the penalty 10000, krige.py:447-450) must match the reference exactly away from the knife
+    edge and as often as it can ON it: candidates drawn so that a good part of them is numerically singular
+    (theta log-uniform down to 1e-5, half of the exponents exactly 2).  Against LAPACK dpotrf on the same Psi:
+    every candidate with cond(Psi) < 1e15 agrees, every disagreement sits beyond cond 5e16 (where the sign of the
+    computed pivot is rounding noise and differs between BLAS builds too), and overall agreement stays above 92 %
+    (profiles/fail_agreement_r01.jsonl: 94.5 % at the default 2-ulp relative pivot test)."""
+    from scipy.linalg.lapack import dpotrf
+
+    X = onp.rlh(n, k, seed)
+    y = onp.f_squared(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    rng = np.random.default_rng(seed)
+    th = 10 ** rng.uniform(-5, -0.5, (C, k))
+    p = np.where(rng.uniform(size=(C, k)) < 0.5, 2.0, rng.uniform(1.5, 2, (C, k)))
+    Psis = [onp.psi_fast(Xn, th[i], p[i]) for i in range(C)]
+    lap_fail = np.array([dpotrf(P, lower=1)[1] for P in Psis]) > 0
+    conds = np.array([np.linalg.cond(P) for P in Psis])
+    out = handle.nll_batch(th, p)
+    gpu_fail = out["info"] > 0
+    assert np.all(out["info"] >= 0)
+    mism = gpu_fail != lap_fail
+    assert lap_fail.sum() >= C // 20 and (~lap_fail).sum() >= C // 4      # the sample straddles the edge
+    assert not np.any(mism & (conds < 1e15)), "failure outcome differs from dpotrf at cond %.3g" % conds[mism].min()
+    if mism.any():
+        assert conds[mism].min() > 5e16
+    assert (~mism).mean() >= 0.92, (~mism).mean()
+    assert np.all(np.isnan(out["nll"][gpu_fail])) and np.all(np.isfinite(out["nll"][~gpu_fail & (conds < 1e15)]))
 
 
 def test_gang_size_does_not_change_results(handle):

@@ -44,7 +44,35 @@ def _worker(rank, world, port, count, q):
             calls.append((lo, hi))
             return _fake_nll(theta[lo:hi], p[lo:hi])
 
-        rows = sharding.sharded_rows(count, eval_slice)
+        # count every collective the sharded evaluation issues: the contract is ONE all_gather per generation
+        ncoll = {"n": 0}
+        for name in ("all_gather_into_tensor", "all_reduce", "all_gather", "broadcast", "barrier"):
+            orig = getattr(dist, name)
+
+            def counted(*a, _orig=orig, **kw):
+                ncoll["n"] += 1
+                return _orig(*a, **kw)
+
+            setattr(dist, name, counted)
+        rows = sharding.sharded_rows(count, eval_slice, ncols=5)
+        assert ncoll["n"] == 1, ncoll
+        # a failure on ONE rank reaches every rank through the same single collective, and the group stays usable
+        def eval_fail(lo, hi):
+            if rank == world - 1:
+                raise RuntimeError("boom on rank %d" % rank)
+            return _fake_nll(theta[lo:hi], p[lo:hi])
+
+        if count >= world:  # every rank owns a slice
+            ncoll["n"] = 0
+            try:
+                sharding.sharded_rows(count, eval_fail, ncols=5)
+                raise AssertionError("no exception on rank %d" % rank)
+            except RuntimeError as e:  # ShardError is a RuntimeError
+                assert ("boom" in str(e)) == (rank == world - 1), str(e)
+            assert ncoll["n"] == 1, ncoll
+            again = sharding.sharded_rows(count, eval_slice, ncols=5)
+            assert np.array_equal(again, rows)
+            calls[:] = calls[: len(calls) // 2]
         lo, hi = sharding.shard_bounds(count, rank, world)
         vals = rows[lo:hi, 0]
         best = sharding.global_argmax(vals, lo)
