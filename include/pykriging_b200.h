@@ -113,6 +113,33 @@ int pk_get_U(pk_handle *h, double *out);
 int pk_psi_batch(pk_handle *h, int C, const double *theta, const double *p, const double *lambda, int mode,
                  double *out);
 
+/* ---- Device-resident GA / PSO population: the candidate-population loop of kriging.train (krige.py:373-399), which
+ * the reference hands to inspyred.ec.GA / inspyred.swarm.PSO with fittingObjective (krige.py:429-452) as evaluator.
+ * The candidate vectors [theta_1..k, p_1..k(, lambda)] stay in device buffers between generations; per generation only
+ * the per-candidate scalars come back (pk_opt_evaluate) and only index / uniform arrays go up: the host keeps the draws
+ * of Python's Mersenne Twister and the comparisons of fitness values that fix the trajectory under a seed (SURVEY App.
+ * B), the device moves and recombines the vectors.  Buffers (`which`): 0 population (GA) / positions x (PSO),
+ * 1 offspring, 2 previous positions, 3 personal-best archive.  Index arrays are int32, host or device. */
+
+/* Uploads `n` rows of `dims` doubles into buffer `which`; which == 0 (re)defines the population's shape. */
+int pk_opt_set(pk_handle *h, int which, int n, int dims, const double *rows);
+/* Reads rows [row0, row0 + nrows) of buffer `which` (final population, the per-generation post-state rows). */
+int pk_opt_get(pk_handle *h, int which, int row0, int nrows, double *out);
+/* pk_nll_batch on rows [row0, row0 + count) of buffer `which`: the evaluator call of a generation (a rank's slice of
+ * it when the population is sharded over GPUs), no candidate upload. */
+int pk_opt_evaluate(pk_handle *h, int which, int row0, int count, int mode, double *nll, double *mu, double *sigma2,
+                    double *lndet, int32_t *info);
+/* One GA generation (inspyred.ec.GA: rank_selection, n_point_crossover with one cut, generational_replacement):
+ *   keep (n entries or NULL): row i of the NEW population = row keep[i] of the pool [offspring(nc) | old population];
+ *   then, for nsel (even) selected parents: pair i = rows parents[2i], parents[2i+1] of the new population, children
+ *   2i, 2i+1 of the offspring buffer = the parents with everything from position cut[i] on exchanged (cut[i] = 0: copied). */
+int pk_ga_step(pk_handle *h, int nc, const int32_t *keep, int nsel, const int32_t *parents, const int32_t *cut);
+/* One PSO generation (inspyred.swarm.PSO, ring topology): archive[i] = x[i] where improved[i] (NULL: skip), then
+ *   x' = clip(x + inertia (x - x_prev) + cognitive r1 (archive - x) + social r2 (archive[nbest] - x), lo, hi),
+ * r = n x dims x 2 uniforms (r1, r2 interleaved, the order the host draws them), every operation rounded on its own. */
+int pk_pso_step(pk_handle *h, const double *r, const int32_t *nbest, const int32_t *improved, double inertia, double cognitive,
+                double social, const double *lo, const double *hi);
+
 /* Block until all work queued on the handle's stream has finished. */
 int pk_synchronize(pk_handle *h);
 

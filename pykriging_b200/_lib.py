@@ -21,7 +21,8 @@ EXPORTS = [
     "pk_predict_batch", "pk_append_point", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
     "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
     "pk_fp64_peak", "pk_debug_math", "pk_set_cholesky_variant", "pk_set_predict_variant", "pk_set_overlap",
-    "pk_set_shard_hint", "pk_set_task_options", "pk_task_schedule",
+    "pk_set_shard_hint", "pk_set_task_options", "pk_task_schedule", "pk_opt_set", "pk_opt_get", "pk_opt_evaluate",
+    "pk_ga_step", "pk_pso_step",
 ]
 
 _lib = None
@@ -86,6 +87,13 @@ def load():
     lib.pk_set_task_options.restype = ctypes.c_int
     lib.pk_task_schedule.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int]
     lib.pk_task_schedule.restype = ctypes.c_int
+    lib.pk_opt_set.argtypes = [hp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp]
+    lib.pk_opt_get.argtypes = [hp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp]
+    lib.pk_opt_evaluate.argtypes = [hp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]
+    lib.pk_ga_step.argtypes = [hp, ctypes.c_int, c_dp, ctypes.c_int, c_dp, c_dp]
+    lib.pk_pso_step.argtypes = [hp, c_dp, c_dp, c_dp, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_dp, c_dp]
+    for name in ("pk_opt_set", "pk_opt_get", "pk_opt_evaluate", "pk_ga_step", "pk_pso_step"):
+        getattr(lib, name).restype = ctypes.c_int
     for name in ("pk_create", "pk_destroy", "pk_set_data", "pk_nll_batch", "pk_fit", "pk_predict_batch",
                  "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_set_workspace_limit"):
         getattr(lib, name).restype = ctypes.c_int
@@ -238,6 +246,42 @@ class Handle(object):
         self._check(self.lib.pk_psi_batch(self._h, C, _addr(theta), _addr(p), _addr(lam_a), int(mode), _addr(out)),
                     "pk_psi_batch")
         return out
+
+    # -- device-resident optimiser population ------------------------------------------------------
+    OPT_POP, OPT_CHILD, OPT_PREV, OPT_ARCHIVE = 0, 1, 2, 3
+
+    def opt_set(self, which, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        self._check(self.lib.pk_opt_set(self._h, int(which), rows.shape[0], rows.shape[1], _addr(rows)), "pk_opt_set")
+
+    def opt_get(self, which, row0, nrows, dims):
+        out = np.empty((int(nrows), int(dims)), dtype=np.float64)
+        self._check(self.lib.pk_opt_get(self._h, int(which), int(row0), int(nrows), _addr(out)), "pk_opt_get")
+        return out
+
+    def opt_evaluate(self, which, count, mode, row0=0):
+        out = {name: np.empty(count, dtype=np.float64) for name in ("nll", "mu", "sigma2", "lndet")}
+        out["info"] = np.empty(count, dtype=np.int32)
+        self._check(self.lib.pk_opt_evaluate(self._h, int(which), int(row0), int(count), int(mode), _addr(out["nll"]),
+                                             _addr(out["mu"]), _addr(out["sigma2"]), _addr(out["lndet"]), _addr(out["info"])),
+                    "pk_opt_evaluate")
+        return out
+
+    def ga_step(self, nc, keep, parents, cut):
+        keep = None if keep is None else np.ascontiguousarray(keep, dtype=np.int32)
+        parents = np.ascontiguousarray(parents, dtype=np.int32)
+        cut = np.ascontiguousarray(cut, dtype=np.int32)
+        self._check(self.lib.pk_ga_step(self._h, int(nc), _addr(keep), int(parents.shape[0]), _addr(parents), _addr(cut)),
+                    "pk_ga_step")
+
+    def pso_step(self, r, nbest, improved, inertia, cognitive, social, lo, hi):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        nbest = np.ascontiguousarray(nbest, dtype=np.int32)
+        improved = None if improved is None else np.ascontiguousarray(improved, dtype=np.int32)
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        self._check(self.lib.pk_pso_step(self._h, _addr(r), _addr(nbest), _addr(improved), float(inertia), float(cognitive),
+                                         float(social), _addr(lo), _addr(hi)), "pk_pso_step")
 
     # -- misc -----------------------------------------------------------------------------------
     def synchronize(self):

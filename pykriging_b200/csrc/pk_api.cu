@@ -179,7 +179,8 @@ int pk_destroy(pk_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
-                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch, h->d_gang, h->d_gridinfo, h->d_tasks, h->d_taskws, h->d_fault};
+                    h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch, h->d_gang, h->d_gridinfo, h->d_tasks, h->d_taskws, h->d_fault, h->d_opt[0], h->d_opt[1], h->d_opt[2],
+                    h->d_opt[3], h->d_opt[4], h->d_opt_idx, h->d_opt_r};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -744,6 +745,128 @@ int pk_psi_batch(pk_handle* h, int C, const double* theta, const double* p, cons
         }
     }
     if (!out_dev) PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+
+// ---- device-resident optimiser population ---------------------------------------------------------------------------
+static int opt_buffer_ok(pk_handle* h, int which) { return h->opt_n > 0 && which >= 0 && which <= 3 && h->d_opt[which]; }
+
+int pk_opt_set(pk_handle* h, int which, int n, int dims, const double* rows) {
+    if (!h) return 1;
+    if (which < 0 || which > 3 || n < 1 || dims < 1 || !rows) PK_FAIL(h, "pk_opt_set: bad arguments");
+    PK_CUDA(h, cudaSetDevice(h->device));
+    if (which == 0) {
+        const int need = n * dims;
+        if (need > h->opt_cap) {
+            PK_CUDA(h, cudaStreamSynchronize(h->stream));
+            for (int b = 0; b < 5; ++b) PK_CUDA(h, regrow(&h->d_opt[b], (size_t)need));
+            h->opt_cap = need;
+        }
+        h->opt_n = n;
+        h->opt_dims = dims;
+        h->opt_pso_started = false;
+    } else if (n != h->opt_n || dims != h->opt_dims) {
+        PK_FAIL(h, "pk_opt_set: buffer %d must have the population's shape (%d x %d)", which, h->opt_n, h->opt_dims);
+    }
+    PK_CUDA(h, cudaMemcpyAsync(h->d_opt[which], rows, sizeof(double) * (size_t)n * dims, cudaMemcpyDefault, h->stream));
+    if (!is_device_ptr(rows)) PK_CUDA(h, cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer
+    return 0;
+}
+
+int pk_opt_get(pk_handle* h, int which, int row0, int nrows, double* out) {
+    if (!h) return 1;
+    if (!opt_buffer_ok(h, which) || row0 < 0 || nrows < 0 || row0 + nrows > h->opt_n || !out) PK_FAIL(h, "pk_opt_get: bad arguments");
+    if (nrows == 0) return 0;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    PK_CUDA(h, cudaMemcpyAsync(out, h->d_opt[which] + (size_t)row0 * h->opt_dims, sizeof(double) * (size_t)nrows * h->opt_dims,
+                               cudaMemcpyDefault, h->stream));
+    if (!is_device_ptr(out)) PK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pk_opt_evaluate(pk_handle* h, int which, int row0, int count, int mode, double* nll, double* mu, double* sigma2,
+                    double* lndet, int32_t* info) {
+    if (!h) return 1;
+    if (!opt_buffer_ok(h, which) || row0 < 0 || count < 0 || row0 + count > h->opt_n) PK_FAIL(h, "pk_opt_evaluate: bad arguments");
+    if (h->n == 0) PK_FAIL(h, "pk_opt_evaluate: pk_set_data has not been called");
+    const int k = h->k;
+    if (h->opt_dims != 2 * k + (mode == PK_MODE_REGRESSION ? 1 : 0))
+        PK_FAIL(h, "pk_opt_evaluate: candidates of %d numbers do not fit k = %d in mode %d", h->opt_dims, k, mode);
+    if (count == 0) return 0;
+    PK_CUDA(h, cudaSetDevice(h->device));
+    if (ensure_candidates(h, count)) return 1;
+    PK_CUDA(h, pk::launch_opt_split(h, h->d_opt[which] + (size_t)row0 * h->opt_dims, count, k, h->opt_dims, h->d_theta, h->d_p,
+                                    mode == PK_MODE_REGRESSION ? h->d_lambda : nullptr));
+    return pk_nll_batch(h, count, h->d_theta, h->d_p, mode == PK_MODE_REGRESSION ? h->d_lambda : nullptr, mode, nll, mu, sigma2,
+                        lndet, info);
+}
+
+static int opt_upload_idx(pk_handle* h, const int32_t* const* src, const int* count, int parts, int32_t** dst) {
+    size_t total = 0;
+    for (int i = 0; i < parts; ++i) total += (size_t)(src[i] ? count[i] : 0);
+    if (total > h->opt_idx_cap) {
+        PK_CUDA(h, cudaStreamSynchronize(h->stream));
+        PK_CUDA(h, regrow(&h->d_opt_idx, total));
+        h->opt_idx_cap = total;
+    }
+    size_t off = 0;
+    bool host = false;
+    for (int i = 0; i < parts; ++i) {
+        dst[i] = nullptr;
+        if (!src[i] || count[i] == 0) continue;
+        dst[i] = h->d_opt_idx + off;
+        PK_CUDA(h, cudaMemcpyAsync(dst[i], src[i], sizeof(int32_t) * (size_t)count[i], cudaMemcpyDefault, h->stream));
+        host |= !is_device_ptr(src[i]);
+        off += (size_t)count[i];
+    }
+    if (host) PK_CUDA(h, cudaStreamSynchronize(h->stream));  // pageable sources may be reused by the caller
+    return 0;
+}
+
+int pk_ga_step(pk_handle* h, int nc, const int32_t* keep, int nsel, const int32_t* parents, const int32_t* cut) {
+    if (!h) return 1;
+    if (!opt_buffer_ok(h, 0) || nc < 0 || nc > h->opt_n || nsel < 0 || nsel > h->opt_n || (nsel & 1) || (nsel > 0 && (!parents || !cut)))
+        PK_FAIL(h, "pk_ga_step: bad arguments");
+    PK_CUDA(h, cudaSetDevice(h->device));
+    const int n = h->opt_n, dims = h->opt_dims;
+    const int32_t* src[3] = {keep, parents, cut};
+    const int cnt[3] = {n, nsel, nsel / 2};
+    int32_t* dev[3];
+    if (opt_upload_idx(h, src, cnt, 3, dev)) return 1;
+    if (keep) {
+        // generational replacement: the survivors of [offspring | old population], in their new (best-first) order
+        PK_CUDA(h, pk::launch_opt_gather(h, h->d_opt[4], h->d_opt[1], h->d_opt[0], dev[0], nc, n, dims));
+        double* t = h->d_opt[0];
+        h->d_opt[0] = h->d_opt[4];
+        h->d_opt[4] = t;
+    }
+    if (nsel > 0) PK_CUDA(h, pk::launch_ga_cross(h, h->d_opt[1], h->d_opt[0], dev[1], dev[2], nsel / 2, dims));
+    return 0;
+}
+
+int pk_pso_step(pk_handle* h, const double* r, const int32_t* nbest, const int32_t* improved, double inertia, double cognitive,
+                double social, const double* lo, const double* hi) {
+    if (!h) return 1;
+    if (!opt_buffer_ok(h, 0) || !r || !nbest || !lo || !hi) PK_FAIL(h, "pk_pso_step: bad arguments");
+    PK_CUDA(h, cudaSetDevice(h->device));
+    const int n = h->opt_n, dims = h->opt_dims;
+    const size_t nr = (size_t)n * dims * 2, need = nr + 2 * (size_t)dims;
+    if (need > h->opt_r_cap) {
+        PK_CUDA(h, cudaStreamSynchronize(h->stream));
+        PK_CUDA(h, regrow(&h->d_opt_r, need));
+        h->opt_r_cap = need;
+    }
+    PK_CUDA(h, cudaMemcpyAsync(h->d_opt_r, r, sizeof(double) * nr, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(h->d_opt_r + nr, lo, sizeof(double) * dims, cudaMemcpyDefault, h->stream));
+    PK_CUDA(h, cudaMemcpyAsync(h->d_opt_r + nr + dims, hi, sizeof(double) * dims, cudaMemcpyDefault, h->stream));
+    const int32_t* src[2] = {nbest, improved};
+    const int cnt[2] = {n, n};
+    int32_t* dev[2];
+    if (opt_upload_idx(h, src, cnt, 2, dev)) return 1;
+    PK_CUDA(h, pk::launch_pso_step(h, h->d_opt[0], h->d_opt[2], h->d_opt[3], h->d_opt_r, dev[0], dev[1], h->opt_pso_started ? 0 : 1,
+                                   inertia, cognitive, social, h->d_opt_r + nr, h->d_opt_r + nr + dims, n, dims));
+    h->opt_pso_started = true;
     return 0;
 }
 

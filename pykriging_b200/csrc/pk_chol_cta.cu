@@ -1216,6 +1216,9 @@ void task_schedule(int nt, int single_below, int blocks_per_task, std::vector<ct
         int b = j + 1;
         while (b < nt) {
             int nb = (left <= single_below) ? 1 : blocks_per_task;
+            // the first task of a column stays one pass: it is what diagonal tile j+1 waits for (a task publishes its row
+            // blocks when it ends), so a coarse list keeps the look-ahead
+            if (b == j + 1 && nb > 2) nb = 2;
             if (b + nb > nt) nb = nt - b;
             ps.push_back(cta::Task{1, j, b, nb});
             b += nb;

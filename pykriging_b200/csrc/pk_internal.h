@@ -97,6 +97,14 @@ struct pk_handle {
     bool fit_valid = false;
     size_t fit_bytes = 0;
 
+    // device-resident optimiser population (pk_opt_*, pk_ga_step, pk_pso_step): rows of `opt_dims` doubles
+    int opt_n = 0, opt_dims = 0, opt_cap = 0;   // cap in doubles per buffer
+    double* d_opt[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // 0 population / x, 1 offspring, 2 previous x, 3 archive (pbest), 4 scratch
+    int32_t* d_opt_idx = nullptr;               // index / mask uploads of a step
+    double* d_opt_r = nullptr;                  // uniforms + bounds of a PSO step
+    size_t opt_idx_cap = 0, opt_r_cap = 0;
+    bool opt_pso_started = false;
+
     // staging for predict
     double* d_q = nullptr;    // query chunk
     double* d_qout = nullptr; // 3 x chunk
@@ -160,6 +168,14 @@ cudaError_t launch_append_point(pk_handle* h, const TiledShape& s, const double*
                                 double* scratch, int32_t* info);
 cudaError_t launch_append_psi_copy(pk_handle* h, int n, double diag, const double* old, const double* psi, double* out);
 cudaError_t measure_fp64_peak(pk_handle* h, double* dmma, double* dfma);
+cudaError_t launch_opt_gather(pk_handle* h, double* dst, const double* child, const double* pop, const int32_t* keep, int nc,
+                              int n, int dims);
+cudaError_t launch_ga_cross(pk_handle* h, double* child, const double* pop, const int32_t* parents, const int32_t* cut,
+                            int npairs, int dims);
+cudaError_t launch_pso_step(pk_handle* h, double* x, double* prev, double* arch, const double* r, const int32_t* nbest,
+                            const int32_t* improved, int first, double inertia, double cognitive, double social,
+                            const double* lo, const double* hi, int n, int dims);
+cudaError_t launch_opt_split(pk_handle* h, const double* cand, int n, int k, int dims, double* theta, double* p, double* lambda);
 
 // phase timing helpers (no-ops unless h->profiling)
 void phase_begin(pk_handle* h, int phase);

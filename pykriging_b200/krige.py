@@ -21,7 +21,7 @@ from scipy.optimize import minimize
 
 from . import _lib
 from .matrixops import matrixops
-from .optimizers import GA, PSO, Bounder
+from .optimizers import GA, PSO, Bounder, DeviceGA, DevicePSO
 from .samplingplan import samplingplan
 
 
@@ -274,6 +274,7 @@ class kriging(matrixops):
 
     # -- krige.py:355-427 -------------------------------------------------------------------------------
     _train_pop = {'pso': 300, 'ga': 300}
+    device_optimizer = True  # GA / PSO population resident on the GPU (False: host arrays, one upload per generation)
 
     def _bounds(self):
         lowerBound = [self.thetamin] * self.k + [self.pmin] * self.k
@@ -286,8 +287,11 @@ class kriging(matrixops):
         self.updateData()
         lowerBound, upperBound = self._bounds()
         rnd = Random(seed) if seed is not None else Random()
+        # population resident on the GPU (pk_ga_step / pk_pso_step) unless switched off or the population is sharded
+        # over ranks (every rank then evolves the replicated host population and evaluates its slice)
+        on_device = self.device_optimizer and self.__dict__.get("_pk_shard") is None
         if optimizer == 'pso':
-            ea = PSO(rnd)
+            ea = DevicePSO(rnd, self._pk_handle(), self._pk_device_objective) if on_device else PSO(rnd)
             ea.terminator = self.no_improvement_termination
             final_pop = ea.evolve(generator=self.generate_population,
                                   evaluator=self.fittingObjective,
@@ -299,7 +303,7 @@ class kriging(matrixops):
                                   num_inputs=self.k)
             final_pop.sort(reverse=True)
         elif optimizer == 'ga':
-            ea = GA(rnd)
+            ea = DeviceGA(rnd, self._pk_handle(), self._pk_device_objective) if on_device else GA(rnd)
             ea.terminator = self.no_improvement_termination
             final_pop = ea.evolve(generator=self.generate_population,
                                   evaluator=self.fittingObjective,
@@ -361,23 +365,39 @@ class kriging(matrixops):
         k = self.k
         out = self._pk_nll_population(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
                                       None, _lib.MODE_INTERP)
-        fitness = []
-        last_ok = -1
-        for i in range(len(cands)):
-            if out["info"][i] != 0:
-                fitness.append(10000)
-            else:
-                fitness.append(np.float64(out["nll"][i]))
-                last_ok = i
-        # post-state of the reference loop: theta/pl = LAST candidate; mu/SigmaSqr/NegLnLike/U = last
-        # successfully evaluated one
-        self._set_hyper(cands[-1])
-        if last_ok >= 0:
-            vals = (out["nll"][last_ok], out["mu"][last_ok], out["sigma2"][last_ok], out["lndet"][last_ok])
-            self._pk_record_batch_state(vals, (cands[last_ok, :k], cands[last_ok, k:2 * k], 0.0), _lib.MODE_INTERP)
+        return self._pk_fitness_poststate(out, lambda i: cands[i])
+
+    def _pk_fitness_poststate(self, out, get_cand):
+        """Fitness list + post-state of the reference's candidate loop from the per-candidate scalars of one batched
+        evaluation.  ``get_cand(i)`` returns candidate i (a host row, or a row read back from the device-resident
+        population): theta/pl = LAST candidate; mu/SigmaSqr/NegLnLike/U = last successfully evaluated one."""
+        k = self.k
+        info = out["info"]
+        fitness = list(out["nll"])               # np.float64 scalars, as self.NegLnLike is in the reference
+        bad = np.nonzero(info != 0)[0]
+        for i in bad:
+            fitness[i] = 10000                   # krige.py:447-450: the Python int
+        ok = np.nonzero(info == 0)[0]
+        last = get_cand(len(fitness) - 1)
+        self._set_hyper(last)
+        if len(ok):
+            j = int(ok[-1])
+            c = last if j == len(fitness) - 1 else get_cand(j)
+            vals = (out["nll"][j], out["mu"][j], out["sigma2"][j], out["lndet"][j])
+            self._pk_record_batch_state(vals, (np.array(c[:k], dtype=float), np.array(c[k:2 * k], dtype=float), 0.0),
+                                        _lib.MODE_INTERP)
         else:
             self._pk_record_batch_state(None, None, _lib.MODE_INTERP)
         return fitness
+
+    def _pk_device_objective(self, which, count):
+        """The evaluator of a device-resident GA / PSO generation (optimizers.DeviceGA / DevicePSO): the candidates are
+        rows of a GPU buffer, only the per-candidate scalars come back; same fitness list and post-state as
+        ``fittingObjective``."""
+        h = self._pk_handle()
+        out = h.opt_evaluate(which, count, self._pk_mode)
+        dims = 2 * self.k + (1 if self._pk_mode == _lib.MODE_REGRESSION else 0)
+        return self._pk_fitness_poststate(out, lambda i: h.opt_get(which, i, 1, dims)[0])
 
     def fittingObjective_local(self, entry):
         """krige.py:454-472.  A population of one through the same device path as the batched objective, so

@@ -77,20 +77,31 @@ class regression_kriging(kriging):
         k = self.k
         out = self._pk_nll_population(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
                                       np.ascontiguousarray(cands[:, -1]), _lib.MODE_REGRESSION)
-        fitness = []
-        last_ok = -1
-        # factor present before this call? (then a failed candidate repeats ITS likelihood)
-        current = np.float64(self._fit_vals[0]) if self._has_U else None
-        for i in range(len(cands)):
-            if out["info"][i] == 0:
-                current = np.float64(out["nll"][i])
-                last_ok = i
-            fitness.append(10000 if current is None else current)
-        self._set_hyper(cands[-1])
-        self.Lambda = cands[-1][-1]
-        if last_ok >= 0:
-            vals = (out["nll"][last_ok], out["mu"][last_ok], out["sigma2"][last_ok], out["lndet"][last_ok])
-            self._pk_record_batch_state(vals, (cands[last_ok, :k], cands[last_ok, k:2 * k], cands[last_ok, -1]),
+        return self._pk_fitness_poststate(out, lambda i: cands[i])
+
+    def _pk_fitness_poststate(self, out, get_cand):
+        """regressionkrige.py:163-172, 428-452: a failed factorisation is swallowed, so the candidate repeats the
+        likelihood of the most recent successful one (possibly from before this call); the literal 10000 appears only
+        while no factorisation has succeeded on this instance at all."""
+        k = self.k
+        info, nll = out["info"], out["nll"]
+        C = len(nll)
+        okmask = info == 0
+        prev = np.maximum.accumulate(np.where(okmask, np.arange(C), -1))   # index of the last success at or before i
+        before = np.float64(self._fit_vals[0]) if self._has_U else None    # factor present before this call?
+        fitness = [None] * C
+        vals = list(nll)
+        for i in range(C):
+            j = prev[i]
+            fitness[i] = vals[j] if j >= 0 else (10000 if before is None else before)
+        last = get_cand(C - 1)
+        self._set_hyper(last)
+        self.Lambda = last[-1]
+        if okmask.any():
+            j = int(prev[-1])
+            c = last if j == C - 1 else get_cand(j)
+            v = (out["nll"][j], out["mu"][j], out["sigma2"][j], out["lndet"][j])
+            self._pk_record_batch_state(v, (np.array(c[:k], dtype=float), np.array(c[k:2 * k], dtype=float), c[-1]),
                                         _lib.MODE_REGRESSION)
         else:
             self._pk_record_batch_state(None, None, _lib.MODE_REGRESSION)

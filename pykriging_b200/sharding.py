@@ -112,11 +112,39 @@ def sharded_rows(count, eval_slice, group=None, ncols=None):
     return rows
 
 
+_NLL_BUFFERS = {}
+
+
+def _nll_buffers(handle, per, world):
+    """Send / receive / pinned host buffers of the sharded population path, cached per (handle, slice size, world).
+    One rank's record: 4 x per doubles (NegLnLike | mu | SigmaSqr | LnDetPsi), per int32 (info), one int32 status word,
+    padded to 8 bytes -- gathered as raw bytes, so the kernels' outputs go out exactly as pk_nll_batch wrote them."""
+    import torch
+
+    key = (id(handle), handle.stream, handle.device, per, world)
+    buf = _NLL_BUFFERS.get(key)
+    if buf is None:
+        _NLL_BUFFERS.clear()  # one live configuration is all a training run needs
+        dev = torch.device("cuda", handle.device)
+        nbytes = (4 * per * 8 + per * 4 + 4 + 7) // 8 * 8
+        loc = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        f64 = loc[: 4 * per * 8].view(torch.float64)
+        buf = {"nbytes": nbytes, "loc": loc, "rows": [f64[i * per:(i + 1) * per] for i in range(4)],
+               "info": loc[4 * per * 8: 4 * per * 8 + per * 4].view(torch.int32),
+               "status": loc[4 * per * 8 + per * 4: 4 * per * 8 + per * 4 + 4].view(torch.int32),
+               "out": torch.empty(world * nbytes, dtype=torch.uint8, device=dev),
+               "host": torch.empty(world * nbytes, dtype=torch.uint8).pin_memory(),
+               "stream": torch.cuda.ExternalStream(handle.stream, device=dev), "dev": dev}
+        _NLL_BUFFERS[key] = buf
+    return buf
+
+
 def sharded_nll_device(handle, theta, p, lam, mode, group=None):
-    """The population path on GPUs (NCCL): this rank's slice goes through ``pk_nll_batch`` with DEVICE outputs, the
-    five per-candidate numbers (NegLnLike, mu, SigmaSqr, LnDetPsi, info) plus a status word are gathered by ONE
-    ``all_gather`` on the handle's stream, and one device-to-host copy returns the (C, 5) table -- no host round trip
-    between the kernels and the collective.  Same contract as ``sharded_rows``."""
+    """The population path on GPUs (NCCL): this rank's slice goes through ``pk_nll_batch`` with DEVICE outputs that
+    ARE the send buffer, the per-candidate numbers (NegLnLike, mu, SigmaSqr, LnDetPsi, info) plus a status word per
+    rank are gathered by ONE ``all_gather`` on the handle's stream, and one copy into pinned host memory returns the
+    (C, 5) table -- no host round trip and no extra kernel between the likelihood epilogue and the collective.
+    Same contract as ``sharded_rows``."""
     import torch
 
     from . import _lib
@@ -126,29 +154,33 @@ def sharded_nll_device(handle, theta, p, lam, mode, group=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = shard_bounds(C, rank, world)
     per = -(-C // world)
-    dev = torch.device("cuda", handle.device)
-    stream = torch.cuda.ExternalStream(handle.stream, device=dev)
+    buf = _nll_buffers(handle, per, world)
     err = None
-    with torch.cuda.device(dev), torch.cuda.stream(stream):
-        loc = torch.full((6, per), float("nan"), dtype=torch.float64, device=dev)
-        info = torch.zeros(per, dtype=torch.int32, device=dev)
+    with torch.cuda.device(buf["dev"]), torch.cuda.stream(buf["stream"]):
         if hi > lo:
             try:
+                r = buf["rows"]
                 handle.nll_batch_raw(hi - lo, np.ascontiguousarray(theta[lo:hi]), np.ascontiguousarray(p[lo:hi]),
                                      None if lam is None else np.ascontiguousarray(lam[lo:hi]), mode,
-                                     loc[0], loc[1], loc[2], loc[3], info)
+                                     r[0], r[1], r[2], r[3], buf["info"])
             except _lib.PkError as e:
                 err = e
-        loc[4] = info.to(torch.float64)
-        loc[5].fill_(1.0 if err is not None else 0.0)
-        out = torch.empty(world, 6, per, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(out, loc, group=group)
-        host = out.cpu().numpy()
+                buf["status"].fill_(1)
+        dist.all_gather_into_tensor(buf["out"], buf["loc"], group=group)
+        buf["host"].copy_(buf["out"], non_blocking=True)
+        if err is not None:
+            buf["status"].fill_(0)
+        buf["stream"].synchronize()
+    raw = buf["host"].numpy().reshape(world, buf["nbytes"])
+    status = raw[:, 4 * per * 8 + per * 4: 4 * per * 8 + per * 4 + 4].copy().view(np.int32)[:, 0]
     if err is not None:
         raise err
-    if np.any(host[:, 5, 0] != 0.0):
-        raise ShardError("pk_nll_batch failed on rank(s) %s" % np.nonzero(host[:, 5, 0])[0].tolist())
-    rows = np.ascontiguousarray(host[:, :5, :].transpose(0, 2, 1).reshape(world * per, 5)[:C])
+    if np.any(status != 0):
+        raise ShardError("pk_nll_batch failed on rank(s) %s" % np.nonzero(status)[0].tolist())
+    rows = np.empty((world * per, 5))
+    rows[:, :4] = raw[:, : 4 * per * 8].copy().view(np.float64).reshape(world, 4, per).transpose(0, 2, 1).reshape(world * per, 4)
+    rows[:, 4] = raw[:, 4 * per * 8: 4 * per * 8 + per * 4].copy().view(np.int32).reshape(world * per)
+    rows = rows[:C]
     if np.any(rows[:, 4] < 0):
         # info < 0: a spin-wait of the persistent Cholesky timed out on some rank; every rank sees it in the gathered table
         raise ShardError("a Cholesky spin-wait timed out on the rank that owns candidate(s) %s"

@@ -231,6 +231,38 @@ def test_train_selects_same_best_under_fixed_seed(optimizer, case, pop, regressi
         assert np.allclose(got, res.x, rtol=1e-3, atol=1e-4) or abs(f_got - res.fun) <= 1e-6 * max(1.0, abs(res.fun))
 
 
+@pytest.mark.parametrize("optimizer,regression", [("ga", False), ("pso", False), ("ga", True), ("pso", True)])
+def test_device_resident_population_equals_host_population(optimizer, regression):
+    """N1: train() with the GA / PSO population resident on the GPU (pk_ga_step / pk_pso_step: only index arrays or
+    uniforms go up, only per-candidate scalars come back) against the same run with the population in host arrays
+    (one candidate upload per generation): same generation-by-generation best, same final hyper-parameters, bit for
+    bit -- the kernels recombine / move the vectors exactly as the host code does."""
+    K, R = _classes()
+    X = onp.rlh(150, 3, 77)
+    rng = np.random.default_rng(6)
+    y = onp.f_squared(X) + (rng.normal(0, 0.03, 150) if regression else 0.0)
+    runs = []
+    for on_device in (True, False):
+        m = (R if regression else K)(X, y)
+        m.device_optimizer = on_device
+        trace = []
+        m.no_improvement_termination = _trace_hook(type(m).no_improvement_termination.__get__(m), trace)
+        m.train(optimizer=optimizer, seed=99, pop_size=64, max_evaluations=2000)
+        runs.append((m, trace))
+    (a, ta), (b, tb) = runs
+    assert type(a._last_ea).__name__.startswith("Device") and not type(b._last_ea).__name__.startswith("Device")
+    assert len(ta) == len(tb) and len(ta) > 3
+    for g, ((ca, fa), (cb, fb)) in enumerate(zip(ta, tb)):
+        assert np.array_equal(ca, cb) and (fa == fb), "generation %d" % g
+    assert a._last_ea.num_evaluations == b._last_ea.num_evaluations
+    assert np.array_equal(a.theta, b.theta) and np.array_equal(a.pl, b.pl)
+    if regression:
+        assert a.Lambda == b.Lambda
+    fa = [(list(i.candidate), i.fitness) for i in a._last_ea.population]
+    fb = [(list(map(float, i.candidate)), i.fitness) for i in b._last_ea.population]
+    assert fa == fb
+
+
 def test_regression_train_runs_and_predicts():
     _, R = _classes()
     doc = load_case("reg_branin_noise_n20_k2")

@@ -67,3 +67,42 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("oracle/", ""), fn
+
+
+@pytest.mark.parametrize("nt", [1, 2, 3, 5, 16, 17, 64, 129])
+@pytest.mark.parametrize("single_below,blocks_per_task", [(0, 1), (4, 2), (0, 2), (0, 30), (3, 5), (100, 7)])
+def test_task_schedule_is_a_valid_dependency_order(lib, nt, single_below, blocks_per_task):
+    """Task mode of the persistent Cholesky (csrc/pk_chol_cta.cu) hands out the tile tasks of a candidate in the order
+    of this list, one ticket after the other; a task only ever waits for tasks of the same candidate that come EARLIER,
+    which is what makes the device-side spin-waits deadlock free.  Re-checked here, independently of the library's own
+    validator: every tile is produced exactly once, a diagonal tile follows the panel task that produces column j-1 of
+    its row block, a panel task follows its diagonal tile and column j-1 of all its row blocks, and no task is longer
+    than the 30 row blocks a warp can watch."""
+    from pykriging_b200 import _lib
+
+    tasks = _lib.task_schedule(nt, single_below, blocks_per_task)
+    ddone = 0
+    rdone = [0] * nt           # finished block columns per row block
+    produced = set()
+    for typ, j, rb, nb in tasks.tolist():
+        if typ == 0:
+            assert j == ddone, "diagonal tiles in order"
+            if j > 0:
+                assert rdone[j] == j, "row block %d is not complete up to column %d" % (j, j - 1)
+            ddone = j + 1
+            produced.add(("D", j))
+        else:
+            assert 1 <= nb <= 30 and j < rb and rb + nb <= nt
+            assert ddone >= j + 1, "panel task of column %d before its diagonal tile" % j
+            for b in range(rb, rb + nb):
+                assert rdone[b] == j, "row block %d: column %d before column %d" % (b, j, rdone[b])
+                rdone[b] = j + 1
+                assert ("P", j, b) not in produced
+                produced.add(("P", j, b))
+    assert ddone == nt
+    assert len(produced) == nt + nt * (nt - 1) // 2
+    # look-ahead: the diagonal tile of column j+1 is handed out right after the FIRST panel task of column j
+    for i, (typ, j, rb, nb) in enumerate(tasks.tolist()):
+        if typ == 0 and j >= 1:
+            prev = tasks[i - 1].tolist()
+            assert prev[0] == 1 and prev[1] == j - 1 and prev[2] == j
