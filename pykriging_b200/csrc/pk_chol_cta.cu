@@ -333,7 +333,12 @@ __device__ __forceinline__ void panel_column(double* pipe, double* Dsm_w, double
         const int ps = (int)((seq + (unsigned)c) % STAGES);
         unsigned long long* bar = bars + ps;
         const int nbox = (G == 1 && rows - r0 > BOX_ROWS) ? 2 : 1;
-        mbar_arrive_expect_tx(bar, (unsigned)((nbox + 1) * BOX_DOUBLES * sizeof(double)));
+        // task mode: the inverted diagonal blocks diagonal tile j's task left in the global scratch travel with the FIRST
+        // solve chunk of the task (one more bulk copy counted on the same mbarrier): whoever has waited for that chunk
+        // has them -- no extra barrier, no exposed L2 latency
+        const bool with_dinv = (dinv_g != nullptr) && (c == nk_gemm);
+        mbar_arrive_expect_tx(bar, (unsigned)((nbox + 1) * BOX_DOUBLES * sizeof(double)) + (with_dinv ? (unsigned)(D_DOUBLES * sizeof(double)) : 0u));
+        if (with_dinv) bulk_g2s(Dsm_w, dinv_g, (unsigned)(D_DOUBLES * sizeof(double)), bar);
         double* as = As + ps * A_STAGE;
         tma_load_3d(as, tmap, k_idx * KC, r0, cidx, bar);
         if (nbox == 2) tma_load_3d(as + BOX_DOUBLES, tmap, k_idx * KC, r0 + BOX_ROWS, cidx, bar);
@@ -374,12 +379,6 @@ __device__ __forceinline__ void panel_column(double* pipe, double* Dsm_w, double
     // stage refills it.  Warps on different schedulers may be up to STAGES - 1 chunks apart.
     for (int g = 0; g < total; ++g) {
         mbar_wait(bars + cs, cpar);  // chunk g has landed
-        if (dinv_g != nullptr && ck == nk_gemm && cb == 0) {
-            // task mode, first solve chunk of the pass: its copies were issued behind the wait for diagonal tile j, so
-            // the inverted diagonal blocks that tile's task left in the global scratch are complete -- fetch them
-            for (int i = tid; i < 8 * 8 * 8; i += THREADS) Dsm_w[(i >> 3) * DLD + (i & 7)] = __ldcg(dinv_g + i);
-            __syncthreads();
-        }
         PK_TL(0)
         PK_TL(1)
         const double* as = As + cs * A_STAGE;
@@ -915,7 +914,7 @@ chol_cta_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int row
 struct Task {
     int type, j, rb, nb;  // type 0 = D(j), 1 = P(j, rb, nb)
 };
-constexpr int DINV_DOUBLES = 8 * 8 * 8;  // the eight inverted diagonal blocks of a tile, dense
+constexpr int DINV_DOUBLES = D_DOUBLES;  // the eight inverted diagonal blocks of a tile, as they lie in shared memory
 constexpr int TASK_MAX_BLOCKS = 30;      // row blocks of one panel task (one lane of warp 0 watches each)
 
 
@@ -1002,11 +1001,9 @@ chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld
             if (tk.type == 0) {
                 // block columns 0 .. j-2 of row block j and of the augmented rows
                 if (j >= 2) ok = task_wait(fl, j - 1, fl + 1 + j, 1, j - 1, info + cand, fault, lane);
-            } else {
+            } else if (j >= 1) {
                 // block columns 0 .. j-1 of the pass's row blocks and of row block j (the B operand)
-                if (j >= 1) ok = task_wait(fl + 1 + j, j, fl + 1 + tk.rb, tk.nb, j, info + cand, fault, lane);
-                // diagonal tile j already there (the usual case in a large population)?  then no late wait at all
-                if (lane == 0) ctl[1] = (ld_acquire_gpu_s32(fl) >= j + 1) ? 1 : 0;
+                ok = task_wait(fl + 1 + j, j, fl + 1 + tk.rb, tk.nb, j, info + cand, fault, lane);
             }
             if (lane == 0) ctl[2] = ok;
         }
@@ -1035,7 +1032,7 @@ chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld
                 }
                 continue;
             }
-            for (int i = tid; i < DINV_DOUBLES; i += THREADS) dv[i] = Dsm[(i >> 3) * DLD + (i & 7)];
+            for (int i = tid; i < DINV_DOUBLES; i += THREADS) dv[i] = Dsm[i];  // as it lies in shared memory (padded rows)
             __syncthreads();
             if (tid == 0) {
                 __threadfence();
@@ -1045,13 +1042,10 @@ chol_task_kernel(const __grid_constant__ CUtensorMap tmap, int C, int nt, int ld
             // the four solve chunks need L_jj and the inverted diagonal blocks: diagonal tile j
             const LateDep late{fl, j + 1, nullptr, 0, reinterpret_cast<const int*>(info + cand), fault, 4 * j};
             const int r0 = tk.rb * PK_TILE;
-            const bool d_ready = ctl[1] != 0;
-            if (d_ready) {
-                for (int i = tid; i < DINV_DOUBLES; i += THREADS) Dsm[(i >> 3) * DLD + (i & 7)] = __ldcg(dv + i);
-                __syncthreads();
-            }
             panel_column<false>(pipe, Dsm, M, ld, j, r0 + tk.nb * PK_TILE, &tmap, cand, bars, rel, seq, fg, 1, 0, 0, nullptr, r0,
-                                d_ready ? nullptr : &late, d_ready ? nullptr : dv);
+                                &late, dv);
+            // A task publishes its row blocks when it ends.  (Publishing every pass of a multi-pass task on its own --
+            // a device-scope fence per warp and pass -- was measured: nothing at 300 candidates, 4 % slower at 1024.)
             if (tid < tk.nb) {
                 __threadfence();
                 st_release_gpu_s32(fl + 1 + tk.rb + tid, j + 1);
@@ -1216,9 +1210,6 @@ void task_schedule(int nt, int single_below, int blocks_per_task, std::vector<ct
         int b = j + 1;
         while (b < nt) {
             int nb = (left <= single_below) ? 1 : blocks_per_task;
-            // the first task of a column stays one pass: it is what diagonal tile j+1 waits for (a task publishes its row
-            // blocks when it ends), so a coarse list keeps the look-ahead
-            if (b == j + 1 && nb > 2) nb = 2;
             if (b + nb > nt) nb = nt - b;
             ps.push_back(cta::Task{1, j, b, nb});
             b += nb;
@@ -1304,7 +1295,12 @@ cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, doubl
         int a_sb, a_bpt;
         if ((long long)C * 5 <= slots) { a_sb = 0; a_bpt = 1; }            // <= 59 candidates: 64-row tasks throughout
         else if ((long long)C * 4 <= slots * 3) { a_sb = 4; a_bpt = 2; }   // <= 222: 128-row tasks, 64-row ones in the late columns
-        else { a_sb = 0; a_bpt = cta::TASK_MAX_BLOCKS; }                    // a wave or more: one panel task per block column
+        else {                                                              // a wave or more: long tasks, about 8 passes each
+            a_sb = 0;
+            a_bpt = 128 / nt;
+            if (a_bpt < 2) a_bpt = 2;
+            if (a_bpt > cta::TASK_MAX_BLOCKS) a_bpt = cta::TASK_MAX_BLOCKS;
+        }
         if (single_below < 0) single_below = a_sb;
         if (bpt <= 0) bpt = a_bpt;
     }

@@ -59,6 +59,7 @@ class matrixops(object):
 
     def disable_sharding(self):
         self.__dict__.pop("_pk_shard", None)
+        sharding.release_buffers()
 
     def _pk_nll_population(self, theta, p, lam, mode):
         """NegLnLike / mu / SigmaSqr / LnDetPsi / info of a population (dict of arrays), sharded if enabled."""

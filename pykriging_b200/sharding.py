@@ -115,6 +115,17 @@ def sharded_rows(count, eval_slice, group=None, ncols=None):
 _NLL_BUFFERS = {}
 
 
+def release_buffers():
+    """Frees the cached send / receive / pinned buffers (also registered with atexit: torch's pinned-memory allocator
+    records a CUDA event when such a tensor dies, which must happen while the context is still alive)."""
+    _NLL_BUFFERS.clear()
+
+
+import atexit  # noqa: E402
+
+atexit.register(release_buffers)
+
+
 def _nll_buffers(handle, per, world):
     """Send / receive / pinned host buffers of the sharded population path, cached per (handle, slice size, world).
     One rank's record: 4 x per doubles (NegLnLike | mu | SigmaSqr | LnDetPsi), per int32 (info), one int32 status word,

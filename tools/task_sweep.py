@@ -13,15 +13,13 @@ from pykriging_b200._lib import Handle  # noqa: E402
 
 h = Handle(0)
 dev = torch.device("cuda", 0)
-shapes = [(1024, 10, 0, (64, 128, 148, 296, 300, 592, 1024)), (4096, 6, 1, (64, 150)),
-          (2048, 8, 0, (128, 300)), (512, 6, 0, (300, 2048)), (256, 4, 0, (128, 2048))]
+shapes = [(1024, 10, 0, (1, 21, 64, 128, 148, 200, 300, 444, 1024)), (4096, 6, 1, (8, 150)),
+          (2048, 8, 0, (128, 300)), (512, 6, 0, (300,))]
 if os.environ.get("PK_SWEEP_QUICK"):
     shapes = [(1024, 10, 0, (128, 300, 1024))]
 # (name, cholesky variant, single_below, blocks_per_task, skew)
-configs = [("v2", 2, -1, 0, 0), ("auto", 0, -1, 0, 0), ("t_4_2_s1", 4, 4, 2, 1), ("t_4_2_s2", 4, 4, 2, 2), ("t_4_2_s3", 4, 4, 2, 3),
-           ("t_4_2_s7", 4, 4, 2, 7), ("t_0_30_s1", 4, 0, 30, 1), ("t_0_30_s2", 4, 0, 30, 2), ("t_0_30_s3", 4, 0, 30, 3),
-           ("t_0_30_s5", 4, 0, 30, 5), ("t_0_30_s9", 4, 0, 30, 9), ("t_0_4_s3", 4, 0, 4, 3), ("t_0_4_s9", 4, 0, 4, 9), ("t_0_2_s5", 4, 0, 2, 5),
-           ("t_0_2_s11", 4, 0, 2, 11)]
+configs = [("v2", 2, -1, 0, 0), ("auto", 0, -1, 0, 0), ("t_0_1", 4, 0, 1, 1), ("t_4_2", 4, 4, 2, 1), ("t_0_2", 4, 0, 2, 1),
+           ("t_0_4", 4, 0, 4, 1), ("t_0_30", 4, 0, 30, 1)]
 for n, k, mode, Cs in shapes:
     rng = np.random.default_rng(n)
     X = np.zeros((n, k))
@@ -56,7 +54,7 @@ for n, k, mode, Cs in shapes:
             ms = h.phase_times()["cholesky"] / reps
             h.set_profiling(False)
             res = out.clone()
-            if base is None and name in ("v2", "t_4_2_s1"):
+            if base is None and name in ("v2", "t_0_1"):
                 base = res
             same = base is not None and bool(torch.equal(torch.nan_to_num(res, nan=-1.0), torch.nan_to_num(base, nan=-1.0)))
             row[name] = {"ms": round(ms, 3), "tf": round(C * n ** 3 / 3 / (ms * 1e-3) * 1e-12, 2), "same_bits_as_v2": same}
