@@ -72,7 +72,7 @@ def make_branin_samples(n, seed=5):
     return X, y
 
 
-def run_predictions(torch, dev, local_rank, rank, world, dist):
+def run_predictions(torch, dev, local_rank, rank, world, dist, contraction=0):
     """predictions/s (the second half of BASELINE.json's metric): yhat, s and EI for this rank's rows of
     the 16 Mi-point query grid on a fitted n = 512 model, query points resident in HBM."""
     from pykriging_b200.krige import kriging
@@ -82,6 +82,7 @@ def run_predictions(torch, dev, local_rank, rank, world, dist):
     model.update([5.0, 5.0, 1.8, 1.8])
     model.neglikelihood()
     h = model._pk_handle()
+    h.set_predict_contraction(contraction)
     m_total = PRED_GRID * PRED_GRID
     per = -(-m_total // world)
     lo, hi = min(rank * per, m_total), min((rank + 1) * per, m_total)
@@ -648,7 +649,7 @@ def run_ours(args, rank, world, local_rank):
     pred = None
     pred_model = None
     if not args.no_predictions:
-        pred, pred_model = run_predictions(torch, dev, local_rank, rank, world, dist)
+        pred, pred_model = run_predictions(torch, dev, local_rank, rank, world, dist, args.predict_contraction)
     traffic = load_traffic()
     if rank == 0:
         if pred is not None:
@@ -767,6 +768,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predictions", action="store_true")
+    ap.add_argument("--predict-contraction", type=int, default=0,
+                    help="|L^-1 psi|^2 of the split predictor: 0 automatic (INT8 tensor cores), 1 FP64 DMMA, 2 INT8")
     ap.add_argument("--no-extras", action="store_true", help="skip the c4 / pop300 / e2e_api / train blocks")
     ap.add_argument("--chol-variant", type=int, default=0,
                     help="0 auto, 1 per-block-column launches, 2 one persistent CTA per candidate, 3 gangs, 4 task mode")

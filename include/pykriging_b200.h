@@ -193,6 +193,13 @@ int pk_task_schedule(int nt, int single_below, int blocks_per_task, int32_t *out
  * 4 = 3 with that detection switched off. */
 int pk_set_predict_variant(pk_handle *h, int variant);
 
+/* The dense contraction |L^-1 psi|^2 of the split predictor (variant 3 / 4; predicterr_normalized, matrixops.py:79-95):
+ * 0 = automatic, 1 = FP64 tensor pipe (mma.sync DMMA), 2 = INT8 tensor cores (tcgen05.mma.kind::i8 with TMEM accumulators):
+ * psi and L^-1 are split into 8 signed 7-bit digits of a row-scaled fixed-point number, the 36 digit-pair products are
+ * exact INT32 sums, the levels are added in FP64 -- an FP64 dot product without rounding inside the sum, at twice the
+ * DMMA rate.  Automatic = 2. */
+int pk_set_predict_contraction(pk_handle *h, int mode);
+
 /* Multi-GPU sharding (the reference has one Python loop over the whole population,
  * krige.py:436-451, and one over the query points, krige.py:243-257): tells the handle that its next
  * pk_nll_batch / pk_predict_batch calls evaluate a SLICE of a population of `population` candidates / of a query

@@ -22,7 +22,7 @@ EXPORTS = [
     "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
     "pk_fp64_peak", "pk_debug_math", "pk_set_cholesky_variant", "pk_set_predict_variant", "pk_set_overlap",
     "pk_set_shard_hint", "pk_set_task_options", "pk_task_schedule", "pk_opt_set", "pk_opt_get", "pk_opt_evaluate",
-    "pk_ga_step", "pk_pso_step",
+    "pk_ga_step", "pk_pso_step", "pk_set_predict_contraction",
 ]
 
 _lib = None
@@ -83,6 +83,8 @@ def load():
     lib.pk_set_shard_hint.restype = ctypes.c_int
     lib.pk_set_overlap.argtypes = [hp, ctypes.c_int]
     lib.pk_set_overlap.restype = ctypes.c_int
+    lib.pk_set_predict_contraction.argtypes = [hp, ctypes.c_int]
+    lib.pk_set_predict_contraction.restype = ctypes.c_int
     lib.pk_set_task_options.argtypes = [hp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.pk_set_task_options.restype = ctypes.c_int
     lib.pk_task_schedule.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int]
@@ -341,6 +343,10 @@ class Handle(object):
         """0 auto, 1 shared-memory psi tile kernel, 2 register-resident kernel (n <= 512), 3 split pipeline, 4 split
         pipeline without the device-side grid detection."""
         self._check(self.lib.pk_set_predict_variant(self._h, int(variant)), "pk_set_predict_variant")
+
+    def set_predict_contraction(self, mode):
+        """The |L^-1 psi|^2 contraction of the split predictor: 0 automatic, 1 FP64 DMMA, 2 INT8 tensor cores (tcgen05)."""
+        self._check(self.lib.pk_set_predict_contraction(self._h, int(mode)), "pk_set_predict_contraction")
 
     def set_shard_hint(self, population=0, query_points=0):
         """The next calls evaluate a slice of a population / query set of these sizes (0 = no hint): kernel

@@ -180,7 +180,7 @@ int pk_destroy(pk_handle* h) {
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
                     h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch, h->d_gang, h->d_gridinfo, h->d_tasks, h->d_taskws, h->d_fault, h->d_opt[0], h->d_opt[1], h->d_opt[2],
-                    h->d_opt[3], h->d_opt[4], h->d_opt_idx, h->d_opt_r};
+                    h->d_opt[3], h->d_opt[4], h->d_opt_idx, h->d_opt_r, h->d_linv_i8, h->d_linv_scale, h->d_psi_i8};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -258,6 +258,12 @@ int pk_set_predict_variant(pk_handle* h, int variant) {
     return 0;
 }
 
+int pk_set_predict_contraction(pk_handle* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return 1;
+    h->predict_contraction = mode;
+    return 0;
+}
+
 int pk_debug_math(pk_handle* h, int64_t m, const double* d, const double* p, double* out_pow, double* out_expneg) {
     if (!h || m < 0 || !d || !p || !out_pow || !out_expneg) return 1;
     if (m == 0) return 0;
@@ -324,6 +330,7 @@ int pk_set_data(pk_handle* h, int n, int k, const double* X, const double* y) {
     h->k = k;
     h->fit_valid = false;  // a cached factor belongs to the previous data set
     h->w_valid = false;
+    h->linv_i8_valid = false;
     h->psi_n = 0;          // and so does the Psi copy
     h->psi_matches_fit = false;
     return 0;
@@ -494,6 +501,7 @@ static int ensure_fit_buffers(pk_handle* h, const pk::TiledShape& s) {
     h->fit_np = s.np;
     h->fit_valid = false;
     h->w_valid = false;
+    h->linv_i8_valid = false;
     return 0;
 }
 
@@ -541,6 +549,7 @@ int pk_fit(pk_handle* h, const double* theta, const double* p, double lambda, in
         h->fit_valid = true;
         h->fit_n = h->n;
         h->w_valid = false;
+    h->linv_i8_valid = false;
         h->psi_matches_fit = true;
     }
     if (out4) PK_CUDA(h, cudaMemcpy(out4, host4, sizeof(host4), cudaMemcpyDefault));
@@ -581,6 +590,7 @@ int pk_append_point(pk_handle* h, const double* x_new, double y_new, double* out
     h->fit_n = n + 1;
     h->psi_n = n + 1;
     h->w_valid = false;
+    h->linv_i8_valid = false;
     const pk::TiledShape s1 = pk::tiled_shape(n + 1, true);
     PK_CUDA(h, pk::launch_nll_epilogue(h, s1, 1, h->d_fit, h->d_out, h->cap_C, h->d_info));
     double host4[4];

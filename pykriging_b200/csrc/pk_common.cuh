@@ -56,6 +56,18 @@ __device__ __forceinline__ double corr_exponent(const double* __restrict__ x, co
     return sum_numpy_order(k, [&](int d) { return theta[d] * pow_abs(fabs(x[d] - z[d]), p[d]); });
 }
 
+// Expected improvement / weighted expected improvement exactly as krige.py:207-217 / 227-233 (operation order kept):
+// S <= 0 -> 0;  u = y_min - yhat;  EI = u (0.5 + 0.5 erf(u / (S sqrt 2))) + S / sqrt(2 pi) exp(-u^2 / (2 S^2)); w >= 0
+// weights the two terms with w and 1 - w.
+__device__ __forceinline__ double expected_improvement(double yhat, double S, double y_min, double w) {
+    if (S <= 0.0) return 0.0;
+    const double u = y_min - yhat;
+    const double one = u * (0.5 + 0.5 * erf((1.0 / sqrt(2.0)) * (u / S)));
+    const double two = (S * (1.0 / sqrt(2.0 * CUDART_PI))) * exp(-(1.0 / 2.0) * ((u * u) / (S * S)));
+    if (w < 0.0) return one + two;
+    return w * one + (1.0 - w) * two;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

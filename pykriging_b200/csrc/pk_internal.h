@@ -113,6 +113,14 @@ struct pk_handle {
     double* d_hp = nullptr;   // 2 x PK_MAX_K (theta | p) for predict
     int* d_gridinfo = nullptr;     // {period P, ok}: verdict of the device-side grid detection (pk_predict2.cu)
     int predict_grid_mode = 1;     // 0: never use the grid-mode psi kernel (tests compare the two)
+    // INT8-tensor-core contraction of the split predictor (pk_predict_i8.cu): digit planes of L^-1 (+ row scales) and of psi
+    int8_t* d_linv_i8 = nullptr;
+    double* d_linv_scale = nullptr;
+    size_t cap_linv_i8 = 0;
+    bool linv_i8_valid = false;
+    int8_t* d_psi_i8 = nullptr;
+    size_t cap_psi_i8 = 0;
+    int predict_contraction = 0;   // 0 automatic (INT8 tensor cores), 1 FP64 DMMA (tn::trinorm_kernel), 2 INT8
     double* d_pscratch = nullptr;  // psi slabs of predict_big_kernel (np > 2944): grid x 32 x (np + 4)
     size_t cap_pscratch = 0;
 };
@@ -163,6 +171,8 @@ cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const doub
 cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
                                  double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
                                  double* ei);
+cudaError_t launch_trinorm_i8(pk_handle* h, const double* psi, int64_t mc, int64_t mcap, double sigma2, double y_min,
+                              double ei_weight, double var_extra, const double* yhat, double* sout, double* ei);
 cudaError_t launch_extract_U(pk_handle* h, const TiledShape& s, double* out);
 cudaError_t launch_append_point(pk_handle* h, const TiledShape& s, const double* xnew_dev, double y_new, double diag,
                                 double* scratch, int32_t* info);

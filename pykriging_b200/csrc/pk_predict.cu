@@ -184,16 +184,6 @@ constexpr int PSLD = PKC + 4;     // 20
 constexpr int PSTAGES = 3;
 constexpr int PRED_THREADS = 256;
 
-// EI exactly as krige.py:207-217 / 227-233 (operation order kept).
-__device__ __forceinline__ double expected_improvement(double yhat, double S, double y_min, double w) {
-    if (S <= 0.0) return 0.0;
-    const double u = y_min - yhat;
-    const double one = u * (0.5 + 0.5 * erf((1.0 / sqrt(2.0)) * (u / S)));
-    const double two = (S * (1.0 / sqrt(2.0 * CUDART_PI))) * exp(-(1.0 / 2.0) * ((u * u) / (S * S)));
-    if (w < 0.0) return one + two;
-    return w * one + (1.0 - w) * two;
-}
-
 template <int QT>
 __global__ void __launch_bounds__(PRED_THREADS)
 predict_kernel(int n, int np, int k, int64_t m, const double* __restrict__ X, const double* __restrict__ Xq,

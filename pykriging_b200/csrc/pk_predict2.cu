@@ -23,16 +23,6 @@
 
 namespace pk {
 
-// expected_improvement: same formula as pk_predict.cu (krige.py:207-217 / 227-233, operation order kept)
-__device__ __forceinline__ double expected_improvement2(double yhat, double S, double y_min, double w) {
-    if (S <= 0.0) return 0.0;
-    const double u = y_min - yhat;
-    const double one = u * (0.5 + 0.5 * erf((1.0 / sqrt(2.0)) * (u / S)));
-    const double two = (S * (1.0 / sqrt(2.0 * CUDART_PI))) * exp(-(1.0 / 2.0) * ((u * u) / (S * S)));
-    if (w < 0.0) return one + two;
-    return w * one + (1.0 - w) * two;
-}
-
 // ---- kernel A: psi rows + yhat -----------------------------------------------------------------------
 // ISSUE bound like psi_pop_kernel (an FP64 instruction holds a scheduler's dispatch port for two cycles, anything
 // else for one: profiles/ncu_psi_rows_r01_s4.txt, 2 x 79 + 132 = 290 cycles per warp and psi value at k = 2), so
@@ -571,7 +561,7 @@ trinorm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                         const double ssqr = sigma2 * (1.0 + var_extra - qs);
                         const double S = sqrt(fabs(ssqr));
                         if (s_out) s_out[q0 + row] = S;
-                        if (ei_out) ei_out[q0 + row] = expected_improvement2(yhat[q0 + row], S, y_min, ei_weight);
+                        if (ei_out) ei_out[q0 + row] = expected_improvement(yhat[q0 + row], S, y_min, ei_weight);
                     }
                 }
             }
@@ -721,6 +711,13 @@ cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, cons
         }
         if (e != cudaSuccess) return e;
         if (!need_s) continue;
+        if (h->predict_contraction != 1) {
+            // the contraction on the INT8 tensor cores (pk_predict_i8.cu): exact digit products, twice the DMMA peak
+            e = launch_trinorm_i8(h, psi, mc, mcap, sigma2, y_min, ei_weight, var_extra, yh, sout ? sout + q0 : nullptr,
+                                  ei ? ei + q0 : nullptr);
+            if (e != cudaSuccess) return e;
+            continue;
+        }
         CUtensorMap tmapA;
         e = tn::encode_2d(&tmapA, psi, (uint64_t)np, (uint64_t)mc);
         if (e != cudaSuccess) return e;
