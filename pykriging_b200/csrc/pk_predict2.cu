@@ -156,6 +156,13 @@ psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, 
         }
         const bool use_memo = (KK > 0) && lean && memo_dims > 0;
         const double* xqg = Xq + q * k;
+        // a NaN coordinate must poison the whole psi row (np.power / np.exp propagate it, matrixops.py:70): the
+        // table-driven pow treats a distance that is not >= tiny like 0, so the query is flagged here (warp uniform)
+        bool qnan = false;
+        for (int d = 0; d < k; ++d) {
+            const double c = __ldg(xqg + d);
+            qnan |= (c != c);
+        }
         auto S_any = [&](int r) {
             return sum_numpy_order(k, [&](int d) {
                 const double xr = xt_staged ? Xt[d * np + r] : __ldg(X + (size_t)r * k + d);
@@ -211,6 +218,7 @@ psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, 
             double v0 = expneg_4k(S0, tab_saddr), v1 = expneg_4k(S1, tab_saddr);
             v0 = (r0 < n) ? v0 : 0.0;
             v1 = (r1 < n) ? v1 : 0.0;
+            if (qnan) v0 = v1 = CUDART_NAN;
             ys0 = fma(v0, __ldg(w + c0), ys0);
             ys1 = fma(v1, __ldg(w + c1), ys1);
             if (prow) {

@@ -4,13 +4,14 @@
 //
 // There is no FP64 path on the 5th-generation tensor cores (DMMA runs on the legacy pipe: 37 TFLOP/s on B200), but their
 // INT8 path does 4.5 POPS with exact INT32 accumulation.  Ozaki splitting turns an FP64 product into integer ones: every
-// operand is written as a sum of S = 8 signed 7-bit digits of a row-scaled fixed-point number,
-//     x = 2^e (d_1 2^-7 + d_2 2^-14 + ... + d_8 2^-56),   |d_t| <= 64,
-// which is EXACT for the 56 bits below the row's leading bit (psi lies in [0, 1]: e = 1 for all of it; a row of L^-1 takes
-// the exponent of its largest entry).  The digit-pair products with t + u <= 9 (36 of 64; the rest lie below 2^-63 of
-// the row scales) are INT8 MMAs whose INT32 sums are exact and order independent; pairs of equal weight share one TMEM
-// accumulator (8 levels x 64 columns = all 512 TMEM columns), and the epilogue adds the 8 levels in FP64, squares and
-// accumulates.  Result: the accuracy of an FP64 dot product with NO rounding inside the sum (tools/ozaki_probe.cu: max
+// operand is written as a sum of S = 7 balanced base-256 digits of a row-scaled fixed-point number,
+//     x = 2^e (d_1 2^-8 + d_2 2^-16 + ... + d_7 2^-56),   -128 <= d_t <= 127,
+// which is EXACT for the 56 bits below 2^e (psi lies in [0, 1]: e = 2 for all of it, so the leading digit stays below 64; a
+// row of L^-1 takes the exponent of its largest entry).  The digit-pair products with t + u <= 8 (28 of 49; the rest lie
+// below 2^-58 of the row scales) are INT8 MMAs whose INT32 sums are exact and order independent; pairs of equal weight
+// share one TMEM accumulator (7 levels x 64 columns = 448 of the 512 TMEM columns), and the epilogue adds the levels in
+// FP64, squares and accumulates.  (Base 256 instead of 128: 7 digits and 28 products instead of 8 and 36 -- the kernel is
+// bound by the tensor cores' shared-memory operand reads, 6 KB per MMA, so every product saved is time saved.)  Result: the accuracy of an FP64 dot product with NO rounding inside the sum (tools/ozaki_probe.cu: max
 // error 1.9e-15 on sums of magnitude 32 at K = 512, below FP64's own eps sqrt K) at 73 FP64-equivalent TFLOP/s -- twice
 // the DMMA peak.  A query's result depends on its own psi row only, so tiles, blocks and shards stay bit-identical.
 //
@@ -19,6 +20,8 @@
 // bytes each) and 8 of L^-1 (64 x 64 bytes), loaded by TMA with 64-byte swizzle into 2 stages of 96 KB; ONE thread issues
 // the 72 MMAs of a chunk (128 x 64 x 32 each) and commits them to the stage's mbarrier; four epilogue warps (one TMEM
 // lane = one query per thread) read the 8 levels, rebuild v in FP64 and add v^2.  After the last block: s and EI.
+// (Eight epilogue warps since the accumulators cannot be double buffered -- they fill the TMEM -- and the MMAs of the
+// next block wait for the epilogue: two warps share a lane quarter, each takes half of the columns.)
 #include <cuda.h>
 
 #include "pk_internal.h"
@@ -26,26 +29,28 @@
 namespace pk {
 namespace i8 {
 
-constexpr int S = 8;                 // digits per operand
+constexpr int S = 7;                 // digits per operand (base 256)
 constexpr int BM = 128;              // queries per tile (TMEM lanes)
 constexpr int BN = 64;               // rows of L^-1 per block (TMEM columns per level)
 constexpr int BK = 64;               // samples (bytes) per pipeline chunk: one 64-byte swizzle row
 constexpr int STAGES = 2;
 constexpr int A_SLICE = BM * BK, B_SLICE = BN * BK;
 constexpr int STAGE_BYTES = S * (A_SLICE + B_SLICE);   // 96 KB
-constexpr int THREADS = 192;         // warps 0-3: epilogue (TMEM lanes 32 w .. 32 w + 31); warp 4: TMA + TMEM allocation; warp 5: MMA
-constexpr double PSI_SCALE = 0.5;    // psi in [0, 1] -> [0, 0.5]: first digit <= 64
+constexpr int THREADS = 320;         // warps 0-3 and 6-9: epilogue (a warp reads the TMEM lanes 32 (w % 4) .. + 31: two warps per
+                                     // lane quarter, 32 of the 64 columns each); warp 4: TMA + TMEM allocation; warp 5: MMA
+constexpr int EPI_THREADS = 256;
+constexpr double PSI_SCALE = 0.25;   // psi in [0, 1] -> [0, 0.25]: leading digit <= 64
 
-// x (|x| <= 0.5) -> 8 balanced base-128 digits of round(x 2^56), most significant first
-__device__ __forceinline__ void digits8(double x, int (&d)[S]) {
+// x (|x| <= 0.25) -> 7 balanced base-256 digits of round(x 2^56), most significant first
+__device__ __forceinline__ void digits(double x, int (&d)[S]) {
     long long X = __double2ll_rn(x * 72057594037927936.0);  // 2^56
 #pragma unroll
     for (int t = S - 1; t >= 1; --t) {
-        const int r = (int)((X + 64) & 127) - 64;
+        const int r = (int)((X + 128) & 255) - 128;
         d[t] = r;
-        X = (X - r) >> 7;
+        X = (X - r) >> 8;
     }
-    d[0] = (int)X;  // what is left: at most 64 in magnitude (x = 0.5 exactly -- a query ON a sample, psi = 1 -- gives +64, no wrap)
+    d[0] = (int)X;  // what is left: at most 64 in magnitude
 }
 
 // psi rows (mc x np doubles) -> planes[t][q][k] (int8), 8 consecutive samples per thread
@@ -62,7 +67,7 @@ psi_slice_kernel(const double* __restrict__ psi, int64_t mc, int np, size_t plan
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             int d[S];
-            digits8(v[e] * PSI_SCALE, d);
+            digits(v[e] * PSI_SCALE, d);
 #pragma unroll
             for (int t = 0; t < S; ++t) packed[t] |= (unsigned long long)(unsigned char)(signed char)d[t] << (8 * e);
         }
@@ -71,7 +76,7 @@ psi_slice_kernel(const double* __restrict__ psi, int64_t mc, int np, size_t plan
     }
 }
 
-// L^-1 (np x np, row-major, lower) -> planes[t][i][k] and the row scales 2 * 2^e_i (the 2 undoes PSI_SCALE): one warp per row
+// L^-1 (np x np, row-major, lower) -> planes[t][i][k] and the row scales 2^e_i / PSI_SCALE: one warp per row
 __global__ void __launch_bounds__(256)
 linv_slice_kernel(const double* __restrict__ linv, int np, int8_t* __restrict__ planes, double* __restrict__ rowscale) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -81,13 +86,13 @@ linv_slice_kernel(const double* __restrict__ linv, int np, int8_t* __restrict__ 
     for (int k = lane; k < np; k += 32) amax = fmax(amax, fabs(src[k]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    // amax 2^-e in [0.25, 0.5): every entry of the row scaled by 2^-e is at most 0.5 in magnitude
-    const int e = (amax > 0.0 && amax < CUDART_INF) ? ilogb(amax) + 2 : 0;
+    // amax 2^-e in [0.125, 0.25): every entry of the row scaled by 2^-e is below 0.25 in magnitude
+    const int e = (amax > 0.0 && amax < CUDART_INF) ? ilogb(amax) + 3 : 0;
     const double down = ldexp(1.0, -e);
     for (int k = lane; k < np; k += 32) {
         int d[S];
         const double x = src[k] * down;  // exact (power of two)
-        digits8((fabs(x) <= 0.5) ? x : 0.0, d);  // NaN / inf rows (a failed fit never gets here) -> zeros
+        digits((fabs(x) <= 0.25) ? x : 0.0, d);  // NaN / inf rows (a failed fit never gets here) -> zeros
 #pragma unroll
         for (int t = 0; t < S; ++t) planes[((size_t)t * np + row) * np + k] = (int8_t)d[t];
     }
@@ -129,6 +134,7 @@ trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __shared__ unsigned long long full[STAGES], empty[STAGES], tmem_full, tmem_empty;
     __shared__ uint32_t tmem_base_s;
     __shared__ double scale_s[2][BN];
+    __shared__ double qhalf_s[BM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -136,10 +142,11 @@ trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(empty + s, 1);
         }
         mbar_init(&tmem_full, 1);
-        mbar_init(&tmem_empty, 128);
+        mbar_init(&tmem_empty, EPI_THREADS);
         mbar_fence_init();
     }
     if (warp == 4) {
+        // 7 levels x 64 columns = 448; allocations are powers of two
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(
             (unsigned)__cvta_generic_to_shared(&tmem_base_s)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -191,7 +198,7 @@ trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int t = 0; t < S; ++t) {
 #pragma unroll
                             for (int u = 0; u + t < S; ++u) {
-                                // digits t+1 of psi and u+1 of L^-1, weight 2^-7(t+u+2): level t + u.  In the first chunk of a
+                                // digits t+1 of psi and u+1 of L^-1, weight 2^-8(t+u+2): level t + u.  In the first chunk of a
                                 // block the pairs with t = 0 touch every level first and overwrite it.
                                 umma_i8(tmem_base + (t + u) * BN, smem_desc_k_sw64(sa + t * A_SLICE + kk * 32),
                                         smem_desc_k_sw64(sb + u * B_SLICE + kk * 32), idesc, (kb == 0 && kk == 0 && t == 0) ? 0u : 1u);
@@ -203,54 +210,70 @@ trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 umma_commit(&tmem_full);      // ... and the block's accumulators are complete
             }
         }
-    } else if (warp < 4) {
-        // ---- epilogue: one query per thread ----
+    } else if (warp < 4 || warp >= 6) {
+        // ---- epilogue: one query per thread pair; the thread of warps 0-3 takes columns 0-31 of a block, its partner in
+        // warps 6-9 columns 32-63 ----
+        const int quarter = warp & 3;                 // the TMEM lanes this warp may read
+        const int colhalf = (warp < 4) ? 0 : 1;
+        const int etid = (warp < 4) ? tid : tid - 64; // 0 .. 255 over the epilogue threads
+        const int row = quarter * 32 + lane;          // query within the tile
         unsigned ch = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t q = tile * BM + warp * 32 + lane;
+            const int64_t q = tile * BM + row;
             double qs = 0.0;
             for (int c = 0; c < nb; ++c, ++ch) {
-                // the block's row scales, double buffered in shared memory (128 threads, 64 values)
-                if (tid < BN) scale_s[ch & 1][tid] = rowscale[c * BN + tid];
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                // the block's row scales, double buffered in shared memory
+                if (etid < BN) scale_s[ch & 1][etid] = rowscale[c * BN + etid];
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 mbar_wait(&tmem_full, ch & 1);
                 tc_fence_after();
-                const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+                const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + colhalf * 32;
 #pragma unroll 1
-                for (int part = 0; part < BN / 16; ++part) {
-                    // levels pairwise in integer arithmetic: (acc_L << 7) + acc_{L+1} has at most 33 bits
+                for (int part = 0; part < 2; ++part) {
+                    // smallest weights first; levels pairwise in integer arithmetic: (acc_L << 8) + acc_{L+1} has at most 39 bits
                     double v[16];
+                    {
+                        uint32_t last[16];
+                        tmem_ld16(lane_base + (S - 1) * BN + part * 16, last);
+                        tmem_ld_wait();
+                        const double w = ldexp(1.0, -8 * (S + 1));  // weight of level S - 1
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0.0;
+                        for (int j = 0; j < 16; ++j) v[j] = (double)(int)last[j] * w;
+                    }
 #pragma unroll
-                    for (int lp = S / 2 - 1; lp >= 0; --lp) {  // smallest weights first
+                    for (int lp = (S - 1) / 2 - 1; lp >= 0; --lp) {
                         uint32_t hi[16], lo[16];
                         tmem_ld16(lane_base + (2 * lp) * BN + part * 16, hi);
                         tmem_ld16(lane_base + (2 * lp + 1) * BN + part * 16, lo);
                         tmem_ld_wait();
-                        const double w = ldexp(1.0, -7 * (2 * lp + 3));  // weight of level 2 lp + 1
+                        const double w = ldexp(1.0, -8 * (2 * lp + 3));  // weight of level 2 lp + 1
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const long long both = ((long long)(int)hi[j] << 7) + (long long)(int)lo[j];
+                            const long long both = ((long long)(int)hi[j] << 8) + (long long)(int)lo[j];
                             v[j] = fma((double)both, w, v[j]);
                         }
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const double x = v[j] * scale_s[ch & 1][part * 16 + j];
+                        const double x = v[j] * scale_s[ch & 1][colhalf * 32 + part * 16 + j];
                         qs = fma(x, x, qs);
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(&tmem_empty);
             }
-            if (q < mc) {
+            // the two halves of a query's sum meet in shared memory (fixed order: columns 0-31 first)
+            if (colhalf == 1) qhalf_s[row] = qs;
+            asm volatile("bar.sync 2, 256;\n" ::: "memory");
+            if (colhalf == 0 && q < mc) {
+                qs += qhalf_s[row];
                 if (yhat[q] != yhat[q]) qs = yhat[q];  // a NaN query has no digits: let the NaN of its yhat through
                 const double ssqr = sigma2 * (1.0 + var_extra - qs);
                 const double Sd = sqrt(fabs(ssqr));
                 if (s_out) s_out[q] = Sd;
                 if (ei_out) ei_out[q] = expected_improvement(yhat[q], Sd, y_min, ei_weight);
             }
+            asm volatile("bar.sync 2, 256;\n" ::: "memory");  // qhalf_s may be overwritten by the next tile
         }
     }
     tc_fence_before();

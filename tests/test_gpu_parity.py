@@ -283,6 +283,67 @@ def _predict_large_batch(handle, n):
     assert np.array_equal(only["yhat"], got["yhat"]) and only["s"] is None
 
 
+@pytest.mark.parametrize("n,k,theta0,regression", [(200, 2, 5.0, False), (512, 2, 5.0, False), (777, 3, 0.3, False),
+                                                   (1024, 6, 0.05, True), (2100, 4, 2.0, False)])
+def test_predict_int8_contraction_matches_dmma_and_oracle(handle, n, k, theta0, regression):
+    """|L^-1 psi|^2 on the INT8 tensor cores (tcgen05.mma.kind::i8, 8-digit splitting of psi and of the rows of L^-1, exact
+    INT32 digit products) against the same contraction on the FP64 tensor pipe and against the oracle: well and badly
+    conditioned models (cond(Psi) 1e2 .. 1e9, L^-1 entries up to 1e4: the row scaling), padded orders (n not a multiple of
+    64), queries exactly on samples (psi = 1: the largest digit), the regression nugget (`var_extra`), and a NaN query."""
+    X = onp.rlh(n, k, 50 + n)
+    rng = np.random.default_rng(n)
+    y = onp.f_squared(X) + (rng.normal(0, 0.02, n) if regression else 0.0)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    theta, p = np.full(k, theta0), np.full(k, 1.9)
+    lam = 1e-6 if regression else 0.0
+    out4, info = handle.fit(theta, p, lam, mode=1 if regression else 0)
+    assert info == 0
+    m = 6000
+    Xq = rng.uniform(0, 1, (m, k))
+    Xq[:50] = Xn[:50]                   # on the samples: psi_k = 1 for one k, 1 - |v|^2 cancels completely
+    Xq[50:60] = Xn[:10] + 1e-9          # and right next to them
+    y_min = float(np.min(yn))
+    extra = lam if regression else 0.0
+    res = {}
+    for mode in (1, 2):
+        handle.set_predict_contraction(mode)
+        try:
+            res[mode] = handle.predict_batch(Xq, theta, p, out4[1], out4[2], y_min=y_min, var_extra=extra)
+        finally:
+            handle.set_predict_contraction(0)
+    dmma, i8 = res[1], res[2]
+    assert np.array_equal(dmma["yhat"], i8["yhat"])             # yhat comes from the psi kernel in both
+    Psi = onp.psi_fast(Xn, theta, p, lam if regression else onp.EPS_DIAG)
+    cond = np.linalg.cond(Psi)
+    vtol = out4[2] * max(1e-12, 100.0 * cond * 2.2e-16)
+    ref = onp.predict_batch_fast(Xn, yn, theta, p, lam if regression else onp.EPS_DIAG, Xq, y_min=y_min)
+    ref_var = ref["s"] ** 2 + (out4[2] * extra if regression else 0.0)   # oracle s has no var_extra: add sigma^2 * extra
+    for name, got in (("dmma", dmma), ("int8", i8)):
+        if regression:
+            assert np.max(np.abs(got["s"] ** 2 - np.abs(ref_var))) < vtol * 10, (name, cond)
+        else:
+            assert np.max(np.abs(got["s"] ** 2 - ref["s"] ** 2)) < vtol, (name, cond, np.max(np.abs(got["s"] ** 2 - ref["s"] ** 2)))
+    # the two contractions agree far inside the oracle tolerance, and the INT8 one is no further from the oracle
+    assert np.max(np.abs(i8["s"] ** 2 - dmma["s"] ** 2)) < vtol
+    if not regression:
+        e_i8 = np.max(np.abs(i8["s"] ** 2 - ref["s"] ** 2))
+        e_dm = np.max(np.abs(dmma["s"] ** 2 - ref["s"] ** 2))
+        assert e_i8 <= 4.0 * e_dm + 1e-14 * out4[2], (e_i8, e_dm)
+    assert np.all(i8["s"] >= 0.0) and np.all(np.isfinite(i8["ei"]))
+    # a NaN query poisons its own outputs only
+    Xq2 = Xq[:4500].copy()
+    Xq2[17] = np.nan
+    handle.set_predict_contraction(2)
+    try:
+        bad = handle.predict_batch(Xq2, theta, p, out4[1], out4[2], y_min=y_min, var_extra=extra)
+    finally:
+        handle.set_predict_contraction(0)
+    assert np.isnan(bad["yhat"][17]) and np.isnan(bad["s"][17])
+    keep = np.arange(4500) != 17
+    assert np.array_equal(bad["s"][keep], i8["s"][:4500][keep]) and np.array_equal(bad["ei"][keep], i8["ei"][:4500][keep])
+
+
 @pytest.mark.parametrize("n,k,special", [(300, 5, False), (300, 5, True), (520, 10, False), (130, 1, False)])
 def test_predict_split_pipeline_general_k(handle, n, k, special):
     """Split pipeline for k outside the compile-time cases, with exponents that are exactly 1 / 2 (exact d, d*d as
