@@ -171,8 +171,9 @@ cudaError_t launch_predict(pk_handle* h, int64_t m, const double* Xq, const doub
 cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, const double* hp, double mu, double sigma2,
                                  double y_min, double ei_weight, double var_extra, double* yhat, double* sout,
                                  double* ei);
-cudaError_t launch_trinorm_i8(pk_handle* h, const double* psi, int64_t mc, int64_t mcap, double sigma2, double y_min,
-                              double ei_weight, double var_extra, const double* yhat, double* sout, double* ei);
+cudaError_t psi_planes_i8(pk_handle* h, int64_t mcap, uint8_t** planes, size_t* plane_stride);
+cudaError_t launch_trinorm_i8(pk_handle* h, int64_t mc, int64_t mcap, double sigma2, double y_min, double ei_weight,
+                              double var_extra, const double* yhat, double* sout, double* ei);
 cudaError_t launch_extract_U(pk_handle* h, const TiledShape& s, double* out);
 cudaError_t launch_append_point(pk_handle* h, const TiledShape& s, const double* xnew_dev, double y_new, double diag,
                                 double* scratch, int32_t* info);

@@ -18,6 +18,7 @@
 // grid of config C5, 21 ms of HBM time hidden under 200 ms of arithmetic.
 #include <cuda.h>
 
+#include "pk_i8.cuh"
 #include "pk_internal.h"
 #include "pk_math.cuh"
 
@@ -94,7 +95,8 @@ template <int KK>
 __global__ void __launch_bounds__(PA_THREADS, 1)
 psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, const double* __restrict__ Xq,
                 const double* __restrict__ hp, const double* __restrict__ w, double mu, int xt_staged, int memo_dims,
-                double* __restrict__ psi_out, double* __restrict__ yhat_out, const int* __restrict__ gridinfo) {
+                double* __restrict__ psi_out, double* __restrict__ yhat_out, const int* __restrict__ gridinfo,
+                uint8_t* __restrict__ planes, size_t plane_stride) {
     if (gridinfo && gridinfo[1]) return;  // the query set is a row-major grid: psi_rows_grid_kernel does this block
     extern __shared__ __align__(16) double pa_smem[];
     double* ltab = pa_smem;                                   // 3 x 64 x 16
@@ -225,6 +227,17 @@ psi_rows_kernel(int n, int np, int k, int64_t mc, const double* __restrict__ X, 
                 prow[r0] = v0;
                 prow[r1] = v1;
             }
+            if (planes) {
+                // the 7 bytes of round(psi 2^54): the digit planes the INT8 contraction reads (pk_i8.cuh); a warp writes 32
+                // consecutive bytes per plane
+                const unsigned long long X0 = i8::psi_fixed(v0), X1 = i8::psi_fixed(v1);
+                uint8_t* pq = planes + (size_t)q * np;
+#pragma unroll
+                for (int t = 0; t < i8::S; ++t) {
+                    pq[(size_t)t * plane_stride + r0] = i8::psi_digit(X0, t);
+                    pq[(size_t)t * plane_stride + r1] = i8::psi_digit(X1, t);
+                }
+            }
         }
         if constexpr (KK > 0) {
             if (use_memo && !hit) {
@@ -283,7 +296,8 @@ constexpr int PG_RMAX = 16;
 __global__ void __launch_bounds__(PA_THREADS, 1)
 psi_rows_grid_kernel(int n, int np, int k, int64_t m, int64_t q0, int64_t mc, int R, const double* __restrict__ X,
                      const double* __restrict__ Xq, const double* __restrict__ hp, const double* __restrict__ w, double mu,
-                     const int* __restrict__ gridinfo, double* __restrict__ psi_out, double* __restrict__ yhat_out) {
+                     const int* __restrict__ gridinfo, double* __restrict__ psi_out, double* __restrict__ yhat_out,
+                     uint8_t* __restrict__ planes, size_t plane_stride) {
     if (!gridinfo[1]) return;
     const int P = gridinfo[0];
     extern __shared__ __align__(16) double pa_smem[];
@@ -358,6 +372,15 @@ psi_rows_grid_kernel(int n, int np, int k, int64_t m, int64_t q0, int64_t mc, in
                 if (prow) {
                     prow[r0] = v0;
                     prow[r1] = v1;
+                }
+                if (planes) {
+                    const unsigned long long X0 = i8::psi_fixed(v0), X1 = i8::psi_fixed(v1);
+                    uint8_t* pq = planes + (size_t)(g - q0) * np;
+#pragma unroll
+                    for (int t = 0; t < i8::S; ++t) {
+                        pq[(size_t)t * plane_stride + r0] = i8::psi_digit(X0, t);
+                        pq[(size_t)t * plane_stride + r1] = i8::psi_digit(X1, t);
+                    }
                 }
             }
             const double ys = warp_sum(ys0 + ys1);
@@ -605,7 +628,7 @@ static cudaError_t encode_2d(CUtensorMap* tmap, const double* base, uint64_t col
 
 template <int KK>
 static cudaError_t launch_psi_rows(pk_handle* h, int64_t mc, const double* Xq, const double* hp, double mu,
-                                   double* psi_out, double* yhat_out, const int* gridinfo) {
+                                   double* psi_out, double* yhat_out, const int* gridinfo, uint8_t* planes, size_t plane_stride) {
     const int k = h->k, np = h->fit_np;
     const int xt = (k * np <= PA_XT_MAX) ? 1 : 0;
     // memoised leading dimensions (compile-time k only): as many of the first k - 1 as fit beside the tables
@@ -630,7 +653,7 @@ static cudaError_t launch_psi_rows(pk_handle* h, int64_t mc, const double* Xq, c
     const int64_t want = (mc + PA_WARPS - 1) / PA_WARPS;
     const int grid = (int)((want < (int64_t)h->sm_count) ? want : (int64_t)h->sm_count);
     psi_rows_kernel<KK><<<grid, PA_THREADS, smem, h->stream>>>(h->n, np, k, mc, h->dX, Xq, hp, h->d_w, mu, xt, memo_dims,
-                                                               psi_out, yhat_out, gridinfo);
+                                                               psi_out, yhat_out, gridinfo, planes, plane_stride);
     h->launches++;
     return cudaGetLastError();
 }
@@ -641,12 +664,16 @@ cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, cons
                                  double* ei) {
     const int np = h->fit_np, k = h->k;
     const bool need_s = (sout != nullptr || ei != nullptr);
+    // the contraction |L^-1 psi|^2: INT8 tensor cores (pk_predict_i8.cu; the psi kernels then write digit planes, 7 bytes
+    // per entry, instead of doubles) or the FP64 tensor pipe (tn::trinorm_kernel on an FP64 psi scratch)
+    const bool use_i8 = need_s && h->predict_contraction != 1;
     // queries per block: psi scratch of at most 1 GiB, at least one wave of 64-query tiles
     int64_t mcap = ((int64_t)1 << 30) / ((int64_t)np * 8);
-    mcap = (mcap / 64) * 64;
-    if (mcap < 64 * (int64_t)h->sm_count) mcap = 64 * (int64_t)h->sm_count;
-    if (mcap > m) mcap = ((m + 63) / 64) * 64;
-    const size_t need = need_s ? (size_t)mcap * np + (size_t)mcap : 0;  // psi rows + yhat (when the caller wants none)
+    mcap = (mcap / 128) * 128;
+    if (mcap < 128 * (int64_t)h->sm_count) mcap = 128 * (int64_t)h->sm_count;
+    if (mcap > m) mcap = ((m + 127) / 128) * 128;
+    // FP64 scratch: psi rows (DMMA contraction only) + yhat (when the caller wants none)
+    const size_t need = need_s ? (use_i8 ? 0 : (size_t)mcap * np) + (size_t)mcap : 0;
     if (need > h->cap_pscratch) {
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) return e;
@@ -657,11 +684,17 @@ cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, cons
         if (e != cudaSuccess) return e;
         h->cap_pscratch = need;
     }
-    double* psi = h->d_pscratch;
-    double* ytmp = need_s ? h->d_pscratch + (size_t)mcap * np : nullptr;
+    double* psi = (need_s && !use_i8) ? h->d_pscratch : nullptr;
+    double* ytmp = need_s ? h->d_pscratch + (use_i8 ? 0 : (size_t)mcap * np) : nullptr;
+    uint8_t* planes = nullptr;
+    size_t plane_stride = 0;
+    if (use_i8) {
+        cudaError_t e = psi_planes_i8(h, mcap, &planes, &plane_stride);
+        if (e != cudaSuccess) return e;
+    }
     CUtensorMap tmapB;
     const size_t smemB = sizeof(double) * (size_t)tn::SMEM_DOUBLES + tn::SMEM_ALIGN;
-    if (need_s) {
+    if (need_s && !use_i8) {
         cudaError_t e = tn::encode_2d(&tmapB, h->d_linv, (uint64_t)np, (uint64_t)np);
         if (e != cudaSuccess) return e;
         static bool attr_done_dev[PK_MAX_DEVICES] = {};
@@ -706,22 +739,22 @@ cudaError_t launch_predict_split(pk_handle* h, int64_t m, const double* Xq, cons
             const size_t smem = ((pa_small_bytes(0, 0) + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000 +
                                 (size_t)2 * R * np * sizeof(double);
             psi_rows_grid_kernel<<<h->sm_count, PA_THREADS, smem, h->stream>>>(h->n, np, k, m, q0, mc, R, h->dX, Xq, hp, h->d_w, mu,
-                                                                              gridinfo, need_s ? psi : nullptr, yh);
+                                                                              gridinfo, psi, yh, planes, plane_stride);
             h->launches++;
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
         }
         switch (k) {
-#define PK_PA(KK_) case KK_: e = launch_psi_rows<KK_>(h, mc, Xq + q0 * k, hp, mu, need_s ? psi : nullptr, yh, gridinfo); break;
+#define PK_PA(KK_) case KK_: e = launch_psi_rows<KK_>(h, mc, Xq + q0 * k, hp, mu, psi, yh, gridinfo, planes, plane_stride); break;
             PK_PA(1) PK_PA(2) PK_PA(3)
 #undef PK_PA
-            default: e = launch_psi_rows<0>(h, mc, Xq + q0 * k, hp, mu, need_s ? psi : nullptr, yh, gridinfo); break;
+            default: e = launch_psi_rows<0>(h, mc, Xq + q0 * k, hp, mu, psi, yh, gridinfo, planes, plane_stride); break;
         }
         if (e != cudaSuccess) return e;
         if (!need_s) continue;
-        if (h->predict_contraction != 1) {
+        if (use_i8) {
             // the contraction on the INT8 tensor cores (pk_predict_i8.cu): exact digit products, twice the DMMA peak
-            e = launch_trinorm_i8(h, psi, mc, mcap, sigma2, y_min, ei_weight, var_extra, yh, sout ? sout + q0 : nullptr,
+            e = launch_trinorm_i8(h, mc, mcap, sigma2, y_min, ei_weight, var_extra, yh, sout ? sout + q0 : nullptr,
                                   ei ? ei + q0 : nullptr);
             if (e != cudaSuccess) return e;
             continue;

@@ -6,8 +6,8 @@
 // INT8 path does 4.5 POPS with exact INT32 accumulation.  Ozaki splitting turns an FP64 product into integer ones: every
 // operand is written as a sum of S = 7 balanced base-256 digits of a row-scaled fixed-point number,
 //     x = 2^e (d_1 2^-8 + d_2 2^-16 + ... + d_7 2^-56),   -128 <= d_t <= 127,
-// which is EXACT for the 56 bits below 2^e (psi lies in [0, 1]: e = 2 for all of it, so the leading digit stays below 64; a
-// row of L^-1 takes the exponent of its largest entry).  The digit-pair products with t + u <= 8 (28 of 49; the rest lie
+// which is EXACT for the 56 bits below 2^e (a row of L^-1 takes the exponent of its largest entry; psi lies in [0, 1] and
+// simply contributes the 7 bytes of round(psi 2^54) as UNSIGNED digits -- the psi kernels write them instead of doubles).  The digit-pair products with t + u <= 8 (28 of 49; the rest lie
 // below 2^-58 of the row scales) are INT8 MMAs whose INT32 sums are exact and order independent; pairs of equal weight
 // share one TMEM accumulator (7 levels x 64 columns = 448 of the 512 TMEM columns), and the epilogue adds the levels in
 // FP64, squares and accumulates.  (Base 256 instead of 128: 7 digits and 28 products instead of 8 and 36 -- the kernel is
@@ -24,12 +24,12 @@
 // next block wait for the epilogue: two warps share a lane quarter, each takes half of the columns.)
 #include <cuda.h>
 
+#include "pk_i8.cuh"
 #include "pk_internal.h"
 
 namespace pk {
 namespace i8 {
 
-constexpr int S = 7;                 // digits per operand (base 256)
 constexpr int BM = 128;              // queries per tile (TMEM lanes)
 constexpr int BN = 64;               // rows of L^-1 per block (TMEM columns per level)
 constexpr int BK = 64;               // samples (bytes) per pipeline chunk: one 64-byte swizzle row
@@ -39,7 +39,6 @@ constexpr int STAGE_BYTES = S * (A_SLICE + B_SLICE);   // 96 KB
 constexpr int THREADS = 320;         // warps 0-3 and 6-9: epilogue (a warp reads the TMEM lanes 32 (w % 4) .. + 31: two warps per
                                      // lane quarter, 32 of the 64 columns each); warp 4: TMA + TMEM allocation; warp 5: MMA
 constexpr int EPI_THREADS = 256;
-constexpr double PSI_SCALE = 0.25;   // psi in [0, 1] -> [0, 0.25]: leading digit <= 64
 
 // x (|x| <= 0.25) -> 7 balanced base-256 digits of round(x 2^56), most significant first
 __device__ __forceinline__ void digits(double x, int (&d)[S]) {
@@ -51,29 +50,6 @@ __device__ __forceinline__ void digits(double x, int (&d)[S]) {
         X = (X - r) >> 8;
     }
     d[0] = (int)X;  // what is left: at most 64 in magnitude
-}
-
-// psi rows (mc x np doubles) -> planes[t][q][k] (int8), 8 consecutive samples per thread
-__global__ void __launch_bounds__(256)
-psi_slice_kernel(const double* __restrict__ psi, int64_t mc, int np, size_t plane_stride, int8_t* __restrict__ planes) {
-    const int64_t groups = mc * (np / 8);
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-        const double4* src = reinterpret_cast<const double4*>(psi + g * 8);
-        const double4 lo = src[0], hi = src[1];
-        const double v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        unsigned long long packed[S];
-#pragma unroll
-        for (int t = 0; t < S; ++t) packed[t] = 0ull;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int d[S];
-            digits(v[e] * PSI_SCALE, d);
-#pragma unroll
-            for (int t = 0; t < S; ++t) packed[t] |= (unsigned long long)(unsigned char)(signed char)d[t] << (8 * e);
-        }
-#pragma unroll
-        for (int t = 0; t < S; ++t) *reinterpret_cast<unsigned long long*>(planes + (size_t)t * plane_stride + g * 8) = packed[t];
-    }
 }
 
 // L^-1 (np x np, row-major, lower) -> planes[t][i][k] and the row scales 2^e_i / PSI_SCALE: one warp per row
@@ -178,7 +154,8 @@ trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 5 && lane == 0) {
         // ---- MMA issuer ----
-        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // D = S32; A (psi digits) unsigned 8 bit, B (L^-1 digits) signed 8 bit, both K-major; N = 64, M = 128
+        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         unsigned it = 0, ch = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int c = 0; c < nb; ++c, ++ch) {
@@ -281,7 +258,7 @@ trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base));
 }
 
-static cudaError_t encode_planes(CUtensorMap* tm, const int8_t* base, uint64_t cols, uint64_t rows, uint64_t plane_stride,
+static cudaError_t encode_planes(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t plane_stride,
                                  uint32_t box_rows) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -299,7 +276,7 @@ static cudaError_t encode_planes(CUtensorMap* tm, const int8_t* base, uint64_t c
     const cuuint64_t gstride[2] = {(cuuint64_t)cols, (cuuint64_t)plane_stride};
     const cuuint32_t box[3] = {(cuuint32_t)BK, box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), gdim, gstride, box, estr,
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
@@ -337,16 +314,13 @@ cudaError_t ensure_linv_i8(pk_handle* h) {
     return cudaSuccess;
 }
 
-// s / EI of `mc` queries whose psi rows lie in `psi` (mc x np doubles): digit planes of psi, then the INT8 contraction.
-cudaError_t launch_trinorm_i8(pk_handle* h, const double* psi, int64_t mc, int64_t mcap, double sigma2, double y_min,
-                              double ei_weight, double var_extra, const double* yhat, double* sout, double* ei) {
-    const int np = h->fit_np;
-    cudaError_t e = ensure_linv_i8(h);
-    if (e != cudaSuccess) return e;
-    const size_t plane_stride = (size_t)mcap * np;
-    const size_t need = (size_t)i8::S * plane_stride;
+// Digit planes of psi for a block of up to `mcap` queries: (plane pointer, bytes between planes).  The psi kernels of the
+// split pipeline write them directly.
+cudaError_t psi_planes_i8(pk_handle* h, int64_t mcap, uint8_t** planes, size_t* plane_stride) {
+    const size_t stride = (size_t)mcap * h->fit_np;
+    const size_t need = (size_t)i8::S * stride;
     if (need > h->cap_psi_i8) {
-        e = cudaStreamSynchronize(h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) return e;
         if (h->d_psi_i8) cudaFree(h->d_psi_i8);
         h->d_psi_i8 = nullptr;
@@ -355,6 +329,18 @@ cudaError_t launch_trinorm_i8(pk_handle* h, const double* psi, int64_t mc, int64
         if (e != cudaSuccess) return e;
         h->cap_psi_i8 = need;
     }
+    *planes = reinterpret_cast<uint8_t*>(h->d_psi_i8);
+    *plane_stride = stride;
+    return cudaSuccess;
+}
+
+// s / EI of `mc` queries whose psi digit planes are in place (psi_planes_i8): the INT8 contraction.
+cudaError_t launch_trinorm_i8(pk_handle* h, int64_t mc, int64_t mcap, double sigma2, double y_min, double ei_weight,
+                              double var_extra, const double* yhat, double* sout, double* ei) {
+    const int np = h->fit_np;
+    cudaError_t e = ensure_linv_i8(h);
+    if (e != cudaSuccess) return e;
+    const size_t plane_stride = (size_t)mcap * np;
     const size_t smem = (size_t)i8::STAGES * i8::STAGE_BYTES + 1024;
     static bool attr_done_dev[PK_MAX_DEVICES] = {};
     bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
@@ -363,10 +349,6 @@ cudaError_t launch_trinorm_i8(pk_handle* h, const double* psi, int64_t mc, int64
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    i8::psi_slice_kernel<<<8 * h->sm_count, 256, 0, h->stream>>>(psi, mc, np, plane_stride, h->d_psi_i8);
-    h->launches++;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
     CUtensorMap tmA, tmB;
     e = i8::encode_planes(&tmA, h->d_psi_i8, (uint64_t)np, (uint64_t)mc, (uint64_t)plane_stride, i8::BM);
     if (e != cudaSuccess) return e;
