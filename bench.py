@@ -653,8 +653,19 @@ def run_ours(args, rank, world, local_rank):
     traffic = load_traffic()
     if rank == 0:
         if pred is not None:
-            pred["kernels"] = ("psi_rows_kernel<2> (psi rows + yhat, FP64 ALU, HBM scratch) + tn::trinorm_kernel "
-                               "(|L^-1 psi|^2 on the DMMA pipe, TMA-fed, + s + EI)")
+            if args.predict_contraction == 1:
+                pred["kernels"] = ("psi_rows_grid_kernel / psi_rows_kernel<2> (psi rows + yhat, FP64 ALU, FP64 scratch in HBM) + "
+                                   "tn::trinorm_kernel (|L^-1 psi|^2 on the FP64 tensor pipe, DMMA, TMA-fed, + s + EI)")
+            else:
+                pred["kernels"] = ("psi_rows_grid_kernel / psi_rows_kernel<2> (psi + yhat, FP64 ALU; psi leaves as 7 unsigned "
+                                   "base-256 digit planes) + i8::trinorm_i8_kernel (|L^-1 psi|^2 on the INT8 tensor cores: "
+                                   "tcgen05.mma.kind::i8, accumulators in TMEM, 28 exact digit-pair products per FP64 product, "
+                                   "levels recombined in FP64, + s + EI)")
+                # 28 INT8 MMAs of 2 ops per multiply-add and FP64-equivalent multiply-add; triangular: n^2 / 2 multiply-adds per point
+                pred["int8_tops"] = pred["tflops_algorithmic"] * 28.0
+                pred["frac_of_int8_peak_nominal"] = pred["int8_tops"] / (4500.0 * world)
+            # FP64-equivalent algorithmic rate of the WHOLE pipeline (psi kernel included) against the FP64 tensor peak: the
+            # INT8 path exceeds it -- that is the point of it
             pred["frac_of_dmma_peak"] = pred["tflops_algorithmic"] / (peak["dmma_tflops"] * world)  # whole-job TFLOP/s over N GPUs
         n = N_SAMPLES
         flops_chol = (n ** 3) / 3.0 * C * args.steps
