@@ -40,18 +40,6 @@ constexpr int THREADS = 320;         // warps 0-3 and 6-9: epilogue (a warp read
                                      // lane quarter, 32 of the 64 columns each); warp 4: TMA + TMEM allocation; warp 5: MMA
 constexpr int EPI_THREADS = 256;
 
-// x (|x| <= 0.25) -> 7 balanced base-256 digits of round(x 2^56), most significant first
-__device__ __forceinline__ void digits(double x, int (&d)[S]) {
-    long long X = __double2ll_rn(x * 72057594037927936.0);  // 2^56
-#pragma unroll
-    for (int t = S - 1; t >= 1; --t) {
-        const int r = (int)((X + 128) & 255) - 128;
-        d[t] = r;
-        X = (X - r) >> 8;
-    }
-    d[0] = (int)X;  // what is left: at most 64 in magnitude
-}
-
 // L^-1 (np x np, row-major, lower) -> planes[t][i][k] and the row scales 2^e_i / PSI_SCALE: one warp per row
 __global__ void __launch_bounds__(256)
 linv_slice_kernel(const double* __restrict__ linv, int np, int8_t* __restrict__ planes, double* __restrict__ rowscale) {
@@ -68,38 +56,12 @@ linv_slice_kernel(const double* __restrict__ linv, int np, int8_t* __restrict__ 
     for (int k = lane; k < np; k += 32) {
         int d[S];
         const double x = src[k] * down;  // exact (power of two)
-        digits((fabs(x) <= 0.25) ? x : 0.0, d);  // NaN / inf rows (a failed fit never gets here) -> zeros
+        balanced_digits((fabs(x) <= 0.25) ? x : 0.0, d);  // NaN / inf rows (a failed fit never gets here) -> zeros
 #pragma unroll
         for (int t = 0; t < S; ++t) planes[((size_t)t * np + row) * np + k] = (int8_t)d[t];
     }
     if (lane == 0) rowscale[row] = ldexp(1.0, e) / PSI_SCALE;
 }
-
-// K-major tile, rows of 64 bytes, SWIZZLE_64B (what TMA writes with CU_TENSOR_MAP_SWIZZLE_64B): 8-row groups 512 bytes apart
-__device__ __forceinline__ uint64_t smem_desc_k_sw64(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 1)
 trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int np, int64_t mc,
@@ -154,8 +116,8 @@ trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 5 && lane == 0) {
         // ---- MMA issuer ----
-        // D = S32; A (psi digits) unsigned 8 bit, B (L^-1 digits) signed 8 bit, both K-major; N = 64, M = 128
-        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // A (psi digits) unsigned, B (L^-1 digits) signed
+        const uint32_t idesc = idesc_i8(false, true, BM, BN);
         unsigned it = 0, ch = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int c = 0; c < nb; ++c, ++ch) {
@@ -207,29 +169,8 @@ trinorm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + colhalf * 32;
 #pragma unroll 1
                 for (int part = 0; part < 2; ++part) {
-                    // smallest weights first; levels pairwise in integer arithmetic: (acc_L << 8) + acc_{L+1} has at most 39 bits
                     double v[16];
-                    {
-                        uint32_t last[16];
-                        tmem_ld16(lane_base + (S - 1) * BN + part * 16, last);
-                        tmem_ld_wait();
-                        const double w = ldexp(1.0, -8 * (S + 1));  // weight of level S - 1
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = (double)(int)last[j] * w;
-                    }
-#pragma unroll
-                    for (int lp = (S - 1) / 2 - 1; lp >= 0; --lp) {
-                        uint32_t hi[16], lo[16];
-                        tmem_ld16(lane_base + (2 * lp) * BN + part * 16, hi);
-                        tmem_ld16(lane_base + (2 * lp + 1) * BN + part * 16, lo);
-                        tmem_ld_wait();
-                        const double w = ldexp(1.0, -8 * (2 * lp + 3));  // weight of level 2 lp + 1
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const long long both = ((long long)(int)hi[j] << 8) + (long long)(int)lo[j];
-                            v[j] = fma((double)both, w, v[j]);
-                        }
-                    }
+                    levels_to_fp64(lane_base, part * 16, BN, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const double x = v[j] * scale_s[ch & 1][colhalf * 32 + part * 16 + j];
