@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libpykriging_b200.so")
-SOURCES = ["pk_api.cu", "pk_small.cu", "pk_tiled.cu", "pk_chol_cta.cu", "pk_predict.cu", "pk_predict2.cu", "pk_psi.cu", "pk_peak.cu", "pk_opt.cu", "pk_predict_i8.cu"]
+SOURCES = ["pk_api.cu", "pk_small.cu", "pk_tiled.cu", "pk_chol_cta.cu", "pk_predict.cu", "pk_predict2.cu", "pk_psi.cu", "pk_peak.cu", "pk_opt.cu", "pk_predict_i8.cu", "pk_chol_i8.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

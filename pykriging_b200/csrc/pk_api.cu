@@ -213,7 +213,7 @@ int pk_set_pivot_tolerance(pk_handle* h, double tol) {
 }
 
 int pk_set_cholesky_variant(pk_handle* h, int variant) {
-    if (!h || variant < 0 || variant > 4) return 1;
+    if (!h || variant < 0 || variant > 5) return 1;
     h->chol_variant = variant;
     return 0;
 }
@@ -423,7 +423,9 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
     } else {
         const pk::TiledShape s = pk::tiled_shape(h->n, false);
         int chunk = 0;
-        if (ensure_workspace(h, s.elems() * sizeof(double), C, &chunk)) return 1;
+        const size_t plane_bytes = pk::cholesky_i8_plane_bytes(s);
+        if (ensure_workspace(h, s.elems() * sizeof(double) + plane_bytes, C, &chunk)) return 1;
+        int8_t* planes0 = reinterpret_cast<int8_t*>(h->d_ws + (size_t)chunk * s.elems());  // behind the chunk's FP64 matrices
         for (int c0 = 0; c0 < C; c0 += chunk) {
             const int cc = (C - c0 < chunk) ? (C - c0) : chunk;
             // Parts of the resident chunk: Psi of part i+1 (stream2) runs while part i is factorised (stream).
@@ -458,7 +460,7 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
                 }
                 h->queue_slot = (int)(pi % PK_QUEUE_SLOTS);
                 pk::phase_begin(h, 1);
-                PK_CUDA(h, pk::launch_cholesky(h, s, pc, wsp, h->d_info + a0));
+                PK_CUDA(h, pk::launch_cholesky(h, s, pc, wsp, h->d_info + a0, planes0 + (size_t)o * plane_bytes));
                 pk::phase_end(h);
                 pk::phase_begin(h, 2);
                 PK_CUDA(h, pk::launch_nll_epilogue(h, s, pc, wsp, h->d_out + a0, h->cap_C, h->d_info + a0));

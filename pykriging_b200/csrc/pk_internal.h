@@ -23,7 +23,7 @@ struct pk_handle {
     std::vector<int> ev_phase;          // phase id of every event pair
     size_t ev_used = 0;
     double pivot_tol = 2.0 * PK_EPS_DIAG;  // relative pivot threshold, 2 ulps (see pk_set_pivot_tolerance)
-    int chol_variant = 0;                  // 0 auto, 1 one launch per block column, 2 persistent CTA per candidate
+    int chol_variant = 0;                  // 0 auto, 1 one launch per block column, 2 persistent CTA per candidate, 3 gangs, 4 task mode, 5 INT8 tensor cores
     int predict_variant = 0;               // 0 auto, 1 shared-memory psi tile kernel, 2 register-resident (n <= 512), 3 split (psi rows kernel + TMA-fed DMMA kernel)
     // this handle's calls are slices of a population / query set of these sizes (pk_set_shard_hint; 0 = no hint):
     // automatic kernel selection uses them, so a shard computes bit for bit what the unsharded call would
@@ -153,7 +153,10 @@ cudaError_t launch_small_nll(pk_handle* h, int C, const double* theta, const dou
 
 cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
                              const double* lambda, int mode, double* ws, int32_t* info);
-cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
+// planes: digit planes of the INT8-tensor-core Cholesky (cholesky_i8_plane_bytes per candidate) or null (DMMA kernels only)
+cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info, int8_t* planes = nullptr);
+size_t cholesky_i8_plane_bytes(const TiledShape& s);
+cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double* ws, int8_t* planes, int32_t* info);
 cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_cholesky_cta(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 cudaError_t launch_cholesky_task(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
