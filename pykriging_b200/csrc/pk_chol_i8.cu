@@ -28,6 +28,9 @@
 // exponent of a row grows.  FP64 L itself is never stored (the diagonal is, for ln|Psi|).
 #include <cuda.h>
 
+#include <cstdio>
+#include <vector>
+
 #include "pk_chol_tile.cuh"
 #include "pk_i8.cuh"
 #include "pk_internal.h"
@@ -142,29 +145,42 @@ __device__ __forceinline__ void solve(double (&acc)[2][8][2], const double* Tl, 
 #pragma unroll
     for (int cb = 0; cb < 8; ++cb) {
         const double d0 = Dsm[(cb * 8 + fr) * DLD + q], d1 = Dsm[(cb * 8 + fr) * DLD + 4 + q];
-        double ax[NMI][2];
+        double ax[NMI][2], x[NMI][2];
+        // the two row tiles are independent chains: their steps alternate so that a DMMA never waits for its neighbour
 #pragma unroll
         for (int mi = 0; mi < NMI; ++mi) {
+            cta::acc_to_afrag(acc[mi][cb][0], acc[mi][cb][1], lane, ax[mi][0], ax[mi][1]);
+            x[mi][0] = x[mi][1] = 0.0;
+        }
+#pragma unroll
+        for (int mi = 0; mi < NMI; ++mi) dmma884(x[mi][0], x[mi][1], ax[mi][0], d0);
+#pragma unroll
+        for (int mi = 0; mi < NMI; ++mi) dmma884(x[mi][0], x[mi][1], ax[mi][1], d1);
+#pragma unroll
+        for (int mi = 0; mi < NMI; ++mi) {
+            acc[mi][cb][0] = x[mi][0];
+            acc[mi][cb][1] = x[mi][1];
             double a0, a1;
-            cta::acc_to_afrag(acc[mi][cb][0], acc[mi][cb][1], lane, a0, a1);
-            double x0 = 0.0, x1 = 0.0;
-            dmma884(x0, x1, a0, d0);
-            dmma884(x0, x1, a1, d1);
-            acc[mi][cb][0] = x0;
-            acc[mi][cb][1] = x1;
-            cta::acc_to_afrag(x0, x1, lane, a0, a1);
+            cta::acc_to_afrag(x[mi][0], x[mi][1], lane, a0, a1);
             ax[mi][0] = cta::negd(a0);
             ax[mi][1] = cta::negd(a1);
         }
+        if (cb < 7) {
+            double b0[7], b1[7];
 #pragma unroll
-        for (int gb = cb + 1; gb < 8; ++gb) {
-            const double b0 = Tl[(gb * 8 + fr) * TS + cb * 8 + q];
-            const double b1 = Tl[(gb * 8 + fr) * TS + cb * 8 + 4 + q];
-#pragma unroll
-            for (int mi = 0; mi < NMI; ++mi) {
-                dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][0], b0);
-                dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][1], b1);
+            for (int gb = cb + 1; gb < 8; ++gb) {
+                b0[gb - 1] = Tl[(gb * 8 + fr) * TS + cb * 8 + q];
+                b1[gb - 1] = Tl[(gb * 8 + fr) * TS + cb * 8 + 4 + q];
             }
+            // first k-step of every block, then the second: the two DMMAs of an accumulator are 2 (8 - cb) instructions apart
+#pragma unroll
+            for (int gb = cb + 1; gb < 8; ++gb)
+#pragma unroll
+                for (int mi = 0; mi < NMI; ++mi) dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][0], b0[gb - 1]);
+#pragma unroll
+            for (int gb = cb + 1; gb < 8; ++gb)
+#pragma unroll
+                for (int mi = 0; mi < NMI; ++mi) dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][1], b1[gb - 1]);
         }
     }
 }
@@ -245,10 +261,21 @@ __device__ __forceinline__ void aug_store(double (&acc)[2][8][2], double* __rest
     }
 }
 
+// TIMING: lane 0 of FP64 warp 3 (rows of both kinds of pass) accumulates clock64() per phase into dbg[8 * blockIdx.x ..]:
+// {prefetch + wait for the MMAs, drain, tile factorisation, solve, digits, end of column, candidates}
+template <bool TIMING>
 __global__ void __launch_bounds__(THREADS, 1)
 chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int C, int nt, int ld,
                size_t elems, size_t plane_stride, size_t cand_stride, double piv_tol, double* __restrict__ ws,
-               int8_t* __restrict__ planes, int32_t* __restrict__ info, unsigned int* __restrict__ queue) {
+               int8_t* __restrict__ planes, int32_t* __restrict__ info, unsigned int* __restrict__ queue, long long* __restrict__ dbg) {
+    long long tmv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+    const bool tmw = TIMING && threadIdx.x == 96;
+#define PK_TM(i)                          \
+    if (tmw) {                            \
+        const long long tn_ = clock64();  \
+        tmv[i] += tn_ - tprev;            \
+        tprev = tn_;                      \
+    }
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024 - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023)) & 1023);
     double* T = reinterpret_cast<double*>(smem + STAGES * STAGE_BYTES);
@@ -378,6 +405,10 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const double down = ldexp(1.0, 56 - e);
             const double sc2 = -ldexp(1.0, 2 * e);
             bool dead = false;  // the candidate failed: only the handshakes are kept up
+            if (tmw) {
+                tprev = clock64();
+                tmv[6] += 1;
+            }
             for (int j = 0; j < nt; ++j) {
                 const int row0 = j * PK_TILE;
                 const int npass = (np + PK_AUG_ROWS - row0 + BM - 1) / BM;
@@ -404,6 +435,7 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (j > 0) {
                         mbar_wait(&tmem_full, mp & 1);
                         tc_fence_after();
+                        PK_TM(0)
                         if (nmi == 2) {
                             drain<2>(acc, tlane, sc2, sc2);
                         } else if (nmi == 1) {
@@ -414,6 +446,7 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tc_fence_before();
                         mbar_arrive(&tmem_empty);
                         ++mp;
+                        PK_TM(1)
                     }
                     if (dead) continue;
                     const bool in_tile = (p == 0 && wrow < PK_TILE);
@@ -437,11 +470,14 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             continue;
                         }
                         if (tid < PK_TILE) M[(size_t)(row0 + tid) * ld + row0 + tid] = T[tid * TS + tid];  // L_ii: ln|Psi| (nll_epilogue_kernel)
+                        PK_TM(2)
                     }
                     if (in_tile || nmi == 0) continue;
                     if (nmi == 2) {
                         solve<2>(acc, T, Dsm, lane);
+                        PK_TM(3)
                         slice_store(acc, down, stg, P, plane_stride, np, rbase, row0, lane);
+                        PK_TM(4)
                     } else {
                         solve<1>(acc, T, Dsm, lane);
                         aug_store(acc, M, P, plane_stride, np, ld, row0, ctl, lane);
@@ -451,8 +487,13 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 fence_proxy_async();
                 mbar_arrive(&col_done);
                 wbar();  // L_jj, D and the exponents of the augmented rows are free / visible for the next column
+                PK_TM(5)
             }
         }
+    }
+#undef PK_TM
+    if (tmw) {
+        for (int i = 0; i < 8; ++i) dbg[8 * blockIdx.x + i] = tmv[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -497,7 +538,9 @@ cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double*
     bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     cudaError_t e;
     if (!attr_done) {
-        e = cudaFuncSetAttribute(ci8::chol_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(ci8::chol_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ci8::chol_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -510,8 +553,28 @@ cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double*
     e = cudaMemsetAsync(queue, 0, sizeof(unsigned int), h->stream);
     if (e != cudaSuccess) return e;
     const int grid = (C < h->sm_count) ? C : h->sm_count;
-    ci8::chol_i8_kernel<<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride, cand_stride,
-                                                              h->pivot_tol, ws, planes, info, queue);
+    if (h->env_cta_timing) {  // diagnostic (PK_CTA_TIMING): per-phase cycle counts of one FP64 warp, printed to stderr
+        long long* dbg = nullptr;
+        cudaMalloc((void**)&dbg, sizeof(long long) * 8 * grid);
+        cudaMemset(dbg, 0, sizeof(long long) * 8 * grid);
+        ci8::chol_i8_kernel<true><<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride, cand_stride,
+                                                                        h->pivot_tol, ws, planes, info, queue, dbg);
+        cudaStreamSynchronize(h->stream);
+        std::vector<long long> host(8 * (size_t)grid);
+        cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < grid; ++b)
+            for (int i = 0; i < 8; ++i) sum[i] += (double)host[8 * b + i];
+        const double nc = sum[6] > 0 ? sum[6] : 1;
+        fprintf(stderr,
+                "[pk i8 timing] grid %d, candidates %.0f; cycles per candidate (warp 3): wait for MMAs %.0f, drain %.0f, tile "
+                "factorisation %.0f, solve %.0f, digits %.0f, end of column %.0f\n",
+                grid, sum[6], sum[0] / nc, sum[1] / nc, sum[2] / nc, sum[3] / nc, sum[4] / nc, sum[5] / nc);
+    } else {
+        ci8::chol_i8_kernel<false><<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride,
+                                                                         cand_stride, h->pivot_tol, ws, planes, info, queue, nullptr);
+    }
     h->launches++;
     return cudaGetLastError();
 }

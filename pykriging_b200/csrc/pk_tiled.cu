@@ -590,6 +590,9 @@ cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws
     // One CTA per candidate (bit-identical) is kept where it measured faster: populations of two waves or more whose
     // last wave is full or nearly so -- C = 1024 at n = 1024: 12.3 against 12.9 ms -- and tiny matrices (n <= 256),
     // where a task is too short to pay for its ticket.
+    // Populations (from 64 candidates, matrices of four block columns or more): the INT8-tensor-core kernel
+    // (pk_chol_i8.cu), one CTA per candidate -- a candidate's bits do not depend on the size of the call or of its shard.
+    if (v == 0 && planes && !s.with_inverse && Ceff >= 64 && s.np >= 256) v = 5;
     if (v == 0) {
         const long long slots = 2LL * h->sm_count;
         const bool whole = (C >= 2 * slots && (C % slots == 0 || C % slots >= slots / 3)) || (s.np <= 256 && C >= h->sm_count);

@@ -160,11 +160,11 @@ def test_tiled_path_matches_oracle_on_seeded_inputs(handle, n, k, seed):
         assert rel_err(out["sigma2"][i], s2) < tol, (i, cond)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("n,k,seed", [(130, 4, 3), (333, 7, 5), (640, 10, 6), (1024, 10, 7)])
 def test_cholesky_variants_match_oracle(handle, variant, n, k, seed):
     """The blocked-Cholesky variants (1 per-block-column launches / 2 persistent CTA per candidate / 3 the same
-    kernel with a gang of CTAs per candidate / 4 task mode) against the oracle, including candidates whose Psi is not positive
+    kernel with a gang of CTAs per candidate / 4 task mode / 5 INT8 tensor cores) against the oracle, including candidates whose Psi is not positive
     definite and the info convention."""
     X = onp.rlh(n, k, seed)
     y = onp.f_stybtang_norm(X)
