@@ -168,6 +168,52 @@ def load_traffic():
         return None
 
 
+def roofline_block(args, chol_tf, peak, traffic, n, C, phases):
+    """Roofline of the dominant kernel (the Cholesky).  The automatic choice (variants 0 / 5) is the INT8-tensor-core kernel:
+    FP64-equivalent flop rate against the tensor peak it runs on -- the measured dense bf16 rate of MEASURED_PEAKS.json
+    times two (INT8 issues at twice the bf16 rate) divided by the 28 digit-pair products an FP64 product costs -- with the
+    fraction of the FP64 (DMMA) peak beside it.  The DMMA variants are measured against the DMMA peak."""
+    i8 = args.chol_variant in (0, 5)
+    names = {0: "ci8::chol_i8_kernel (INT8 tensor cores: tcgen05.mma.kind::i8 over 7 base-256 digit planes of L, accumulators in "
+                "TMEM, FP64 tile factorisation / triangular solve on DMMA; one persistent CTA per candidate and SM)",
+             1: "chol_first_kernel + chol_step_kernel", 2: "cta::chol_cta_kernel (one CTA per candidate, DMMA)",
+             3: "cta::chol_cta_kernel (gangs, DMMA)", 4: "cta::chol_task_kernel (task mode, DMMA)"}
+    names[5] = names[0]
+    key = "chol_i8_kernel" if i8 else "chol_cta_kernel"
+    tr = (traffic or {}).get(key + "_dram_bytes_per_launch")
+    out = {"kernel": names[args.chol_variant], "bound": "tensor", "achieved": chol_tf, "unit": "TFLOP/s",
+           "traffic": tr, "traffic_source": (traffic or {}).get(key + "_source", (traffic or {}).get("source")),
+           "algorithmic": "n^3/3 FP64 flop per eval = %.4g flop x %d evals per step" % (n ** 3 / 3.0, C),
+           "timing": "CUDA events around every launch of the kernel on its stream, over the same %d steps as the timed "
+                     "region, run once more with the phases serialised (pk_set_profiling) so that the duration is the "
+                     "kernel's own" % args.steps,
+           "phase_ms_per_step": {kk: v / args.steps for kk, v in phases.items()},
+           "frac_of_dmma_peak": (chol_tf / peak["dmma_tflops"]) if chol_tf else None,
+           "dmma_peak_tflops": peak["dmma_tflops"]}
+    if i8:
+        bf16, src = 1650.0, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16, src = float(json.load(f)["bf16_tflops"]), "measured"
+        except Exception:
+            pass
+        int8_peak = 2.0 * bf16
+        out["peak"] = int8_peak / 28.0
+        out["frac"] = (chol_tf / out["peak"]) if chol_tf else None
+        out["int8_tops"] = chol_tf * 28.0 if chol_tf else None
+        out["int8_peak_tops"] = int8_peak
+        out["peak_source"] = ("INT8 tensor peak = 2 x the %s dense bf16 rate of MEASURED_PEAKS.json (%.1f TFLOP/s), divided by the 28 "
+                              "INT8 digit-pair products one FP64 product costs; frac_of_dmma_peak = against the FP64 tensor "
+                              "peak measured in this process (pk_fp64_peak)" % (src, bf16))
+        if tr and phases.get("cholesky", 0) > 0:
+            out["dram_gbs"] = tr / (phases["cholesky"] / args.steps * 1e-3) * 1e-9
+    else:
+        out["peak"] = peak["dmma_tflops"]
+        out["frac"] = out["frac_of_dmma_peak"]
+        out["peak_source"] = "FP64 DMMA peak measured in this process (pk_fp64_peak; MEASURED_PEAKS.json has no FP64 entry)"
+    return out
+
+
 def config_dict(n_gpus):
     return {"workload": "C3: 10-D synthetic (rlh seed 1234, Styblinski-Tang), n=1024 samples, population of "
                         "1024 (theta,p) candidates per GPU per step (512 uniform + 512 log-uniform theta)",
@@ -688,24 +734,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * C * k * 8,
                     "d2h_bytes_per_step": 4 * C * 8 + 4 * C, "api": "pk_nll_batch (C ABI) with pinned host buffers"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": {0: "cta::chol_cta_kernel (persistent blocked Cholesky, one CTA per candidate, DMMA 8x8x4, "
-                                       "TMA-fed stages; what the automatic choice runs for a population of 1024 -- "
-                                       "populations that are not whole waves run cta::chol_task_kernel, see pop300 / c4 / strong)",
-                                    1: "chol_first_kernel + chol_step_kernel",
-                                    2: "cta::chol_cta_kernel (one CTA per candidate)", 3: "cta::chol_cta_kernel (gangs)",
-                                    4: "cta::chol_task_kernel (task mode)"}[args.chol_variant],
-                         "bound": "tensor", "achieved": chol_tf, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-                         "frac": (chol_tf / peak["dmma_tflops"]) if chol_tf else None,
-                         "traffic": (traffic or {}).get("chol_cta_kernel_dram_bytes_per_launch"),
-                         "traffic_source": (traffic or {}).get("source"),
-                         "algorithmic": "n^3/3 flop per eval = %.4g flop x %d evals per step" % (n ** 3 / 3.0, C),
-                         "peak_source": "FP64 DMMA peak measured in this process (pk_fp64_peak; "
-                                        "MEASURED_PEAKS.json has no FP64 entry)",
-                         "timing": "CUDA events around every launch of the kernel on its stream, over the same %d "
-                                   "steps as the timed region, run once more with the Psi/Cholesky overlap "
-                                   "switched off (pk_set_profiling) so that the duration is the kernel's own"
-                                   % args.steps,
-                         "phase_ms_per_step": {kk: v / args.steps for kk, v in phases.items()}},
+            "roofline": roofline_block(args, chol_tf, peak, traffic, n, C, phases),
             "roofline_psi": {"kernel": "psi_pop_kernel<10,1>", "bound": "hbm", "achieved": psi_gbs, "peak": hbm_peak,
                              "unit": "GB/s", "frac": (psi_gbs / hbm_peak) if psi_gbs else None,
                              "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)",
@@ -783,7 +812,7 @@ def main():
                     help="|L^-1 psi|^2 of the split predictor: 0 automatic (INT8 tensor cores), 1 FP64 DMMA, 2 INT8")
     ap.add_argument("--no-extras", action="store_true", help="skip the c4 / pop300 / e2e_api / train blocks")
     ap.add_argument("--chol-variant", type=int, default=0,
-                    help="0 auto, 1 per-block-column launches, 2 one persistent CTA per candidate, 3 gangs, 4 task mode")
+                    help="0 auto, 1 per-block-column launches, 2 one persistent CTA per candidate, 3 gangs, 4 task mode, 5 INT8 tensor cores")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -149,6 +149,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, in
         "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"((unsigned)__cvta_generic_to_shared(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
 // orders this thread's earlier generic-proxy accesses (global and shared) before later async-proxy ones
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 

@@ -34,6 +34,10 @@ __device__ __forceinline__ void balanced_digits(double x, int (&d)[S]) {
 __device__ __forceinline__ uint64_t smem_desc_k_sw64(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
+// K-major tile, rows of 32 bytes, SWIZZLE_32B (CU_TENSOR_MAP_SWIZZLE_32B): 8-row groups 256 bytes apart
+__device__ __forceinline__ uint64_t smem_desc_k_sw32(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
 // instruction descriptor: D = S32, A / B 8-bit (signed flags), both K-major, M x N
 __host__ __device__ constexpr uint32_t idesc_i8(bool a_signed, bool b_signed, int M, int N) {
     return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
