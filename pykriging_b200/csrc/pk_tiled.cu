@@ -580,7 +580,7 @@ cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, doub
 
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info, int8_t* planes) {
     int v = h->chol_variant;
-    if (v == 5 && (!planes || s.with_inverse)) v = 0;  // the INT8 kernel factorises populations only (pk_fit: gangs)
+    if (v == 5 && (!planes || s.with_inverse || s.np > 16384)) v = 0;  // INT32 level sums: 7 x 2^14 x K < 2^31  // the INT8 kernel factorises populations only (pk_fit: gangs)
     const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;  // the population this call is a slice of
     // Automatic: task mode (pk_chol_cta.cu).  Its tiles are produced by the arithmetic of the one-CTA-per-candidate kernel,
     // so a candidate's result does not depend on how many candidates it is evaluated with -- a single SLSQP evaluation,
@@ -592,7 +592,7 @@ cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws
     // where a task is too short to pay for its ticket.
     // Populations (from 64 candidates, matrices of four block columns or more): the INT8-tensor-core kernel
     // (pk_chol_i8.cu), one CTA per candidate -- a candidate's bits do not depend on the size of the call or of its shard.
-    if (v == 0 && planes && !s.with_inverse && Ceff >= 64 && s.np >= 256) v = 5;
+    if (v == 0 && planes && !s.with_inverse && Ceff >= 64 && s.np >= 256 && s.np <= 16384) v = 5;
     if (v == 0) {
         const long long slots = 2LL * h->sm_count;
         const bool whole = (C >= 2 * slots && (C % slots == 0 || C % slots >= slots / 3)) || (s.np <= 256 && C >= h->sm_count);

@@ -594,6 +594,88 @@ def test_task_mode_is_bit_identical_to_one_cta_per_candidate(handle, n, k, C):
         handle.set_cholesky_variant(0)
 
 
+@pytest.mark.parametrize("n,k,C,regression", [(200, 3, 70, False), (640, 5, 150, True), (1024, 10, 300, False), (1100, 4, 131, True)])
+def test_int8_cholesky_bits_do_not_depend_on_the_call(handle, n, k, C, regression):
+    """The INT8-tensor-core Cholesky (variant 5; the automatic choice from 64 candidates) factorises every candidate in ONE
+    CTA with exact integer product sums, so the four scalars and info[] of a candidate are the same BIT FOR BIT in the whole
+    population, in any slice of it (what a shard of a population spread over GPUs evaluates) and in any order -- with
+    failing candidates and a nugget in the mix -- and they agree with the DMMA kernel (variant 2) to the rounding level of
+    either: the digits carry 2^-56 of the scale, the DMMA path rounds every partial sum."""
+    X = onp.rlh(n, k, 200 + n)
+    y = onp.f_stybtang_norm(X) if k != 3 else onp.f_squared(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    cands = np.concatenate([onp.candidates_uniform(C // 2, k, n + 1), onp.candidates_loguniform(C - C // 2, k, n + 2, lo=-4)])
+    for i in (3, C // 2, C - 1):  # numerically singular: fail at different block columns
+        cands[i, :k] = 1e-5
+        cands[i, k:] = 2.0
+    th, p = np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:])
+    lam = np.ascontiguousarray(10.0 ** np.random.default_rng(n).uniform(-6, 0, C)) if regression else None
+    if regression:
+        lam[[3, C // 2, C - 1]] = 0.0  # no nugget: these stay singular
+    mode = 1 if regression else 0
+    names = ("nll", "mu", "sigma2", "lndet")
+    try:
+        handle.set_cholesky_variant(2)
+        dmma = handle.nll_batch(th, p, lam, mode)
+        handle.set_cholesky_variant(5)
+        ref = handle.nll_batch(th, p, lam, mode)
+        handle.set_cholesky_variant(0)
+        auto = handle.nll_batch(th, p, lam, mode)   # C >= 64: the automatic choice is the INT8 kernel
+        assert np.array_equal(auto["info"], ref["info"])
+        for nm in names:
+            assert np.array_equal(auto[nm], ref[nm], equal_nan=True), nm
+        handle.set_cholesky_variant(5)
+        for lo, hi in ((0, 1), (2, 9), (C // 3, C // 3 + 33), (C - 20, C)):
+            part = handle.nll_batch(th[lo:hi], p[lo:hi], None if lam is None else lam[lo:hi], mode)
+            assert np.array_equal(part["info"], ref["info"][lo:hi])
+            for nm in names:
+                assert np.array_equal(part[nm], ref[nm][lo:hi], equal_nan=True), (nm, lo, hi)
+        perm = np.random.default_rng(7).permutation(C)
+        shuf = handle.nll_batch(th[perm], p[perm], None if lam is None else lam[perm], mode)
+        for nm in names:
+            assert np.array_equal(shuf[nm], ref[nm][perm], equal_nan=True), nm
+    finally:
+        handle.set_cholesky_variant(0)
+    ok = (ref["info"] == 0) & (dmma["info"] == 0)
+    assert ok.sum() > C // 2 and (ref["info"] > 0).sum() >= 3
+    assert np.array_equal(ref["info"] > 0, dmma["info"] > 0)
+    # lndet is a sum of log pivots: 1e-10 relative leaves room for cond(Psi) up to 1e6 x eps in both kernels
+    for nm, tol in (("lndet", 1e-10), ("nll", 1e-8), ("mu", 1e-7), ("sigma2", 1e-7)):
+        err = np.abs(ref[nm][ok] - dmma[nm][ok]) / np.maximum(1.0, np.abs(dmma[nm][ok]))
+        assert np.median(err) < 1e-12 and err.max() < tol, (nm, float(err.max()))
+
+
+def test_int8_cholesky_right_hand_sides_rescale(handle):
+    """The augmented rows (a = L^-1 1, d = L^-1 y) of the INT8 kernel carry their own growing exponent and all their digits
+    are cut again when it grows: a response with entries over twelve orders of magnitude and candidates whose L^-1 1
+    grows along the row must still reproduce the oracle's mu / sigma^2."""
+    n, k = 700, 4
+    X = onp.rlh(n, k, 77)
+    rng = np.random.default_rng(5)
+    y = onp.f_stybtang_norm(X) * 10.0 ** rng.uniform(-6, 6, n)
+    handle.set_data(X, y)
+    cands = np.concatenate([onp.candidates_uniform(40, k, 5), onp.candidates_loguniform(40, k, 6, lo=-2)])
+    try:
+        handle.set_cholesky_variant(5)
+        out = handle.nll_batch(cands[:, :k], cands[:, k:])
+    finally:
+        handle.set_cholesky_variant(0)
+    checked = 0
+    for i in range(0, 80, 5):
+        Psi = onp.psi_fast(X, cands[i, :k], cands[i, k:])
+        nll, mu, s2, lndet, info = onp.neglikelihood_fast(Psi, y)
+        cond = np.linalg.cond(Psi)
+        if info != 0 or cond > 1e10:
+            continue
+        tol = tol_for_cond(cond)
+        assert out["info"][i] == 0
+        assert rel_err(out["nll"][i], nll) < tol and rel_err(out["sigma2"][i], s2) < tol, (i, cond)
+        assert abs(out["mu"][i] - mu) < tol * max(1.0, np.abs(y).max()), (i, cond)
+        checked += 1
+    assert checked >= 6
+
+
 @pytest.mark.parametrize("n,k,seed,C", [(20, 2, 1, 600), (100, 2, 3, 300), (300, 4, 4, 120)])
 def test_failure_agreement_with_lapack_has_a_floor(handle, n, k, seed, C):
     """"Cholesky failed" (-> the penalty 10000, krige.py:447-450) must match the reference exactly away from the knife
