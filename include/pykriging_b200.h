@@ -163,8 +163,12 @@ int pk_set_pivot_tolerance(pk_handle *h, double tol);
  * matrices), 4 = TASK mode: the persistent CTAs pull tile tasks (diagonal tile / one 64- or 128-row panel pass of one
  * candidate) from a ticket counter, dependencies through per-candidate completion counters in global memory -- every
  * SM stays busy whatever the population size (128 candidates per GPU of a sharded population, the default 300, a
- * 150-particle swarm at n = 4096) and the results are bit-identical to variant 2.
- * Automatic: gangs for up to a third of the CTA slots, task mode otherwise. */
+ * 150-particle swarm at n = 4096) and the results are bit-identical to variant 2; 5 = the INT8-TENSOR-CORE kernel
+ * (pk_nll_batch only): the product sums of the factorisation as tcgen05.mma.kind::i8 over 7 base-256 digit planes of L
+ * (exact INT32 sums, accumulators in TMEM), tile factorisation and triangular solves in FP64; one persistent CTA per
+ * candidate, so a candidate's bits do not depend on the size or order of the call.
+ * Automatic: the INT8 kernel for populations (64 candidates or more -- counted on the whole population when the call
+ * is a shard, pk_set_shard_hint -- and n > 192), task mode for fewer candidates, gangs for pk_fit. */
 int pk_set_cholesky_variant(pk_handle *h, int variant);
 
 /* Tuning knobs of task mode (variant 4); none of them changes a bit of the result.  A panel task takes up to
