@@ -167,8 +167,9 @@ int pk_set_pivot_tolerance(pk_handle *h, double tol);
  * (pk_nll_batch only): the product sums of the factorisation as tcgen05.mma.kind::i8 over 7 base-256 digit planes of L
  * (exact INT32 sums, accumulators in TMEM), tile factorisation and triangular solves in FP64; one persistent CTA per
  * candidate, so a candidate's bits do not depend on the size or order of the call.
- * Automatic: the INT8 kernel for populations (64 candidates or more -- counted on the whole population when the call
- * is a shard, pk_set_shard_hint -- and n > 192), task mode for fewer candidates, gangs for pk_fit. */
+ * Automatic: the INT8 kernel for populations that fill their waves of one candidate per SM to 60 % or more (42 % from
+ * n = 1473 on; counted on the whole population when the call is a shard, pk_set_shard_hint) at n > 704, task mode
+ * otherwise, gangs for pk_fit. */
 int pk_set_cholesky_variant(pk_handle *h, int variant);
 
 /* Tuning knobs of task mode (variant 4); none of them changes a bit of the result.  A panel task takes up to

@@ -590,9 +590,16 @@ cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws
     // One CTA per candidate (bit-identical) is kept where it measured faster: populations of two waves or more whose
     // last wave is full or nearly so -- C = 1024 at n = 1024: 12.3 against 12.9 ms -- and tiny matrices (n <= 256),
     // where a task is too short to pay for its ticket.
-    // Populations (from 64 candidates, matrices of four block columns or more): the INT8-tensor-core kernel
-    // (pk_chol_i8.cu), one CTA per candidate -- a candidate's bits do not depend on the size of the call or of its shard.
-    if (v == 0 && planes && !s.with_inverse && Ceff >= 64 && s.np >= 256 && s.np <= 16384) v = 5;
+    // Populations: the INT8-tensor-core kernel (pk_chol_i8.cu), one CTA per candidate and SM -- a candidate's bits do
+    // not depend on the size of the call or of its shard (the rule looks at the hinted population only).  It runs whole
+    // waves of sm_count candidates at the latency of ONE factorisation, so it pays when the waves are reasonably full:
+    // profiles/i8_sweep_r02.jsonl -- per candidate of a full wave it needs 0.66 (n = 1024) / 0.58 (n = 2048) of task
+    // mode's time, at n = 512 the two are level (the FP64 side of a pass does not shrink with K) and task mode stays.
+    if (v == 0 && planes && !s.with_inverse && s.np >= 768 && s.np <= 16384) {
+        const int64_t waves = (Ceff + h->sm_count - 1) / h->sm_count;
+        const double fill = (double)Ceff / (double)(waves * h->sm_count);
+        if (fill >= (s.np >= 1536 ? 0.42 : 0.6)) v = 5;
+    }
     if (v == 0) {
         const long long slots = 2LL * h->sm_count;
         const bool whole = (C >= 2 * slots && (C % slots == 0 || C % slots >= slots / 3)) || (s.np <= 256 && C >= h->sm_count);
