@@ -50,7 +50,8 @@ constexpr int STAGES = 2;
 constexpr int A_SLICE = BM * BK, B_SLICE = BN * BK;
 constexpr int STAGE_BYTES = S * (A_SLICE + B_SLICE);  // 84 KB
 constexpr int WTHREADS = 256;        // warps 0-7: FP64 workers
-constexpr int THREADS = 320;         // + warp 8 (TMA) + warp 9 (MMA, TMEM allocation)
+constexpr int THREADS = 384;         // + warp 8 (TMA) + warp 9 (MMA, TMEM allocation) + two idle warps: the third warpgroup hands
+                                     // its registers to the FP64 warpgroups (setmaxnreg)
 constexpr int STG_LD = 80;           // bytes per row of a warp's digit staging (16 rows x 64 bytes; 80: conflict-free 2-byte stores)
 constexpr int STG_BYTES = 16 * STG_LD;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (PK_TILE * TS + D_DOUBLES + PK_TILE) * 8 + 8 * STG_BYTES;
@@ -145,42 +146,29 @@ __device__ __forceinline__ void solve(double (&acc)[2][8][2], const double* Tl, 
 #pragma unroll
     for (int cb = 0; cb < 8; ++cb) {
         const double d0 = Dsm[(cb * 8 + fr) * DLD + q], d1 = Dsm[(cb * 8 + fr) * DLD + 4 + q];
-        double ax[NMI][2], x[NMI][2];
-        // the two row tiles are independent chains: their steps alternate so that a DMMA never waits for its neighbour
+        double ax[NMI][2];
 #pragma unroll
         for (int mi = 0; mi < NMI; ++mi) {
-            cta::acc_to_afrag(acc[mi][cb][0], acc[mi][cb][1], lane, ax[mi][0], ax[mi][1]);
-            x[mi][0] = x[mi][1] = 0.0;
-        }
-#pragma unroll
-        for (int mi = 0; mi < NMI; ++mi) dmma884(x[mi][0], x[mi][1], ax[mi][0], d0);
-#pragma unroll
-        for (int mi = 0; mi < NMI; ++mi) dmma884(x[mi][0], x[mi][1], ax[mi][1], d1);
-#pragma unroll
-        for (int mi = 0; mi < NMI; ++mi) {
-            acc[mi][cb][0] = x[mi][0];
-            acc[mi][cb][1] = x[mi][1];
             double a0, a1;
-            cta::acc_to_afrag(x[mi][0], x[mi][1], lane, a0, a1);
+            cta::acc_to_afrag(acc[mi][cb][0], acc[mi][cb][1], lane, a0, a1);
+            double x0 = 0.0, x1 = 0.0;
+            dmma884(x0, x1, a0, d0);
+            dmma884(x0, x1, a1, d1);
+            acc[mi][cb][0] = x0;
+            acc[mi][cb][1] = x1;
+            cta::acc_to_afrag(x0, x1, lane, a0, a1);
             ax[mi][0] = cta::negd(a0);
             ax[mi][1] = cta::negd(a1);
         }
-        if (cb < 7) {
-            double b0[7], b1[7];
 #pragma unroll
-            for (int gb = cb + 1; gb < 8; ++gb) {
-                b0[gb - 1] = Tl[(gb * 8 + fr) * TS + cb * 8 + q];
-                b1[gb - 1] = Tl[(gb * 8 + fr) * TS + cb * 8 + 4 + q];
+        for (int gb = cb + 1; gb < 8; ++gb) {
+            const double b0 = Tl[(gb * 8 + fr) * TS + cb * 8 + q];
+            const double b1 = Tl[(gb * 8 + fr) * TS + cb * 8 + 4 + q];
+#pragma unroll
+            for (int mi = 0; mi < NMI; ++mi) {
+                dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][0], b0);
+                dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][1], b1);
             }
-            // first k-step of every block, then the second: the two DMMAs of an accumulator are 2 (8 - cb) instructions apart
-#pragma unroll
-            for (int gb = cb + 1; gb < 8; ++gb)
-#pragma unroll
-                for (int mi = 0; mi < NMI; ++mi) dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][0], b0[gb - 1]);
-#pragma unroll
-            for (int gb = cb + 1; gb < 8; ++gb)
-#pragma unroll
-                for (int mi = 0; mi < NMI; ++mi) dmma884(acc[mi][gb][0], acc[mi][gb][1], ax[mi][1], b1[gb - 1]);
         }
     }
 }
@@ -310,17 +298,28 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     unsigned it = 0;    // K chunks issued / consumed so far (TMA and MMA threads)
     unsigned mp = 0;    // passes with MMAs so far (MMA thread and FP64 warps)
     unsigned ccol = 0;  // block columns finished before this candidate (TMA thread)
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            ctl_s[0] = (int)atomicAdd(queue, 1u);
-            ctl_s[2] = 0;
-            ctl_s[3] = ctl_s[4] = AUG_NONE;
+    // next candidate of this CTA (every thread of the CTA calls it: two CTA barriers), -1 = the queue is empty
+    auto next_candidate = [&]() -> int {
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) {
+                ctl_s[0] = (int)atomicAdd(queue, 1u);
+                ctl_s[2] = 0;
+                ctl_s[3] = ctl_s[4] = AUG_NONE;
+            }
+            __syncthreads();
+            const int c = ctl_s[0];
+            if (c >= C) return -1;
+            if (info[c] == 0) return c;  // candidates that failed before (NaN hyper-parameters) are skipped
         }
-        __syncthreads();
-        const int cand = ctl_s[0];
-        if (cand >= C) break;
-        if (info[cand] != 0) continue;
+    };
+    // 12 warps at 168 registers fill the register file, and the FP64 warps spill at 168: the producer warpgroup (TMA, MMA and
+    // two idle warps) hands its registers over.  Each side runs its own candidate loop behind its setmaxnreg.
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+      for (;;) {
+        const int cand = next_candidate();
+        if (cand < 0) break;
         if (warp == 8) {
             // ---------------- TMA producer ----------------
             if (lane == 0) {
@@ -390,7 +389,14 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-        } else {
+        }
+      }
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+      for (;;) {
+        const int cand = next_candidate();
+        if (cand < 0) break;
+        {
             // ---------------- FP64 warps ----------------
             const int quarter = warp & 3, half = warp >> 2;
             const int wrow = quarter * 32 + half * 16;  // this warp's 16 rows of a pass = its 16 TMEM lanes
@@ -490,6 +496,7 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 PK_TM(5)
             }
         }
+      }
     }
 #undef PK_TM
     if (tmw) {
