@@ -1,4 +1,6 @@
 // C ABI of libpykriging_b200.so (see include/pykriging_b200.h for the contract of every entry point).
+#include <cuda.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -164,6 +166,8 @@ int pk_create(pk_handle** out, int device) {
     if (const char* v = getenv("PK_CHOL_CTAS_PER_SM")) h->env_ctas_per_sm = (atoi(v) == 1) ? 1 : 2;
     h->env_cta_timing = getenv("PK_CTA_TIMING") != nullptr;
     h->env_cta_alias = getenv("PK_CTA_ALIAS") != nullptr;
+    if (const char* v = getenv("PK_RAGGED_FIRST")) h->ragged_first = atoi(v) != 0;
+    if (const char* v = getenv("PK_I8_L2")) h->i8_l2_mode = atoi(v) & 3;
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);
@@ -369,13 +373,16 @@ static int ensure_workspace(pk_handle* h, size_t per_matrix_bytes, int C, int* c
     return 0;
 }
 
-// Split a resident chunk of `cc` candidates into pipeline parts.  The persistent Cholesky kernel keeps
-// 2 CTAs per SM busy ("slots"); a population that is not a multiple of the slot count leaves a ragged
-// last wave.  The ragged part goes FIRST, so that the Psi construction of the remaining (whole-wave)
-// part fills the SMs its tail frees, and the last factorisation ends on a wave boundary.
-static void plan_parts(pk_handle* h, int cc, std::vector<int>& parts) {
+// Split a resident chunk of `cc` candidates into pipeline parts: Psi of part i+1 is built on stream2 while part i is
+// factorised on the main stream.
+//  * INT8-tensor-core Cholesky (one CTA per candidate and SM, a wave of sm_count candidates costs the latency of ONE
+//    factorisation): a short ragged wave goes FIRST -- its few CTAs factorise while the Psi kernel of the whole waves
+//    has the other SMs, so the population pays for its whole waves only (default population 300 = 4 + 2 x 148).  A
+//    candidate's bits do not depend on the part it is in (same kernel for every part: h->call_C).
+//  * DMMA kernels: the two-part pipeline of round 1 (pk_set_overlap; measured slower -- both kernels are bound by the
+//    FP64 pipe -- and off).
+static void plan_parts(pk_handle* h, const pk::TiledShape& s, int cc, std::vector<int>& parts) {
     parts.clear();
-    const int slots = 2 * h->sm_count;
     if (!h->env_split.empty()) {  // experiment knob (PK_SPLIT): comma-separated part sizes
         int left = cc;
         const char* q = h->env_split.c_str();
@@ -391,13 +398,51 @@ static void plan_parts(pk_handle* h, int cc, std::vector<int>& parts) {
         if (left > 0) parts.push_back(left);
         return;
     }
-    if (!h->overlap || h->profiling || h->chol_variant == 1 || cc <= slots) {
+    if (h->profiling || h->chol_variant == 1) {
+        parts.push_back(cc);
+        return;
+    }
+    const int variant = pk::cholesky_pick_variant(h, s, cc, true);
+    if (variant == 5) {
+        const int slots = h->sm_count;
+        const int rem = cc % slots;
+        // the short wave's SM time comes out of the Psi kernel's, so what is won is wave latency x (1 - rem / slots): take it
+        // up to half a wave (profiles/i8_knobs_r02_b.jsonl: 300 = 4 + 296: 5.30 -> 4.40 ms, 333 = 37 + 296: 5.52 -> 4.81)
+        if (h->ragged_first && cc > slots && rem > 0 && rem * 2 <= slots) {
+            parts.push_back(rem);
+            parts.push_back(cc - rem);
+        } else {
+            parts.push_back(cc);
+        }
+        return;
+    }
+    const int slots = 2 * h->sm_count;
+    if (!h->overlap || cc <= slots) {
         parts.push_back(cc);
         return;
     }
     const int rem = cc % slots;
     if (rem > 0) parts.push_back(rem);
     parts.push_back(cc - rem);
+}
+
+// stream memory operation: work queued on `stream` after this call waits until *addr >= value (cuStreamWaitValue32 through
+// the runtime's driver entry point).  stream == nullptr only asks whether the operation is available.
+static cudaError_t stream_wait_geq(cudaStream_t stream, unsigned int* addr, unsigned value) {
+    typedef CUresult (*wait_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static wait_fn fn = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (wait_fn)f;
+    }
+    if (!fn) return cudaErrorNotSupported;
+    if (!stream) return cudaSuccess;
+    return fn((CUstream)stream, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS ? cudaSuccess : cudaErrorUnknown;
 }
 
 int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, const double* lambda, int mode,
@@ -426,11 +471,16 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
         const size_t plane_bytes = pk::cholesky_i8_plane_bytes(s);
         if (ensure_workspace(h, s.elems() * sizeof(double) + plane_bytes, C, &chunk)) return 1;
         int8_t* planes0 = reinterpret_cast<int8_t*>(h->d_ws + (size_t)chunk * s.elems());  // behind the chunk's FP64 matrices
+        struct CallScope {  // every chunk and part of this call picks the kernel the whole population picks
+            pk_handle* h;
+            CallScope(pk_handle* h_, int C_) : h(h_) { h->call_C = C_; }
+            ~CallScope() { h->call_C = 0; }
+        } call_scope(h, C);
         for (int c0 = 0; c0 < C; c0 += chunk) {
             const int cc = (C - c0 < chunk) ? (C - c0) : chunk;
             // Parts of the resident chunk: Psi of part i+1 (stream2) runs while part i is factorised (stream).
             std::vector<int> parts;
-            plan_parts(h, cc, parts);
+            plan_parts(h, s, cc, parts);
             if (parts.size() > 1) {
                 while (h->ev_pipe.size() < parts.size() + 1) {
                     cudaEvent_t ev;
@@ -442,6 +492,10 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
                 PK_CUDA(h, cudaEventRecord(h->ev_pipe[0], h->stream));
                 PK_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_pipe[0], 0));
             }
+            // [short last wave, whole waves] of the INT8 kernel (plan_parts)
+            const bool ragged = parts.size() == 2 && h->env_split.empty() && pk::cholesky_pick_variant(h, s, cc, true) == 5;
+            unsigned int* started = h->d_queue + (PK_QUEUE_SLOTS - 1);
+            if (ragged) PK_CUDA(h, cudaMemsetAsync(started, 0, sizeof(unsigned int), h->stream2));
             int o = 0;
             for (size_t pi = 0; pi < parts.size(); ++pi) {
                 const int pc = parts[pi], a0 = c0 + o;
@@ -458,10 +512,18 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
                     PK_CUDA(h, cudaEventRecord(h->ev_pipe[pi + 1], h->stream2));
                     PK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_pipe[pi + 1], 0));
                 }
-                h->queue_slot = (int)(pi % PK_QUEUE_SLOTS);
+                h->queue_slot = (int)(pi % (PK_QUEUE_SLOTS - 1));
+                // ragged first: the few CTAs of the short wave need an SM each to themselves (219 KB of shared memory).  Were
+                // the Psi kernel of the whole waves released right away, its CTAs would take every SM first and keep refilling
+                // them, and the short wave would start when that grid runs dry -- so the Psi stream waits (device side, stream
+                // memory operation) until the short wave's CTAs have counted themselves in.
+                const bool gate = ragged && pi == 0 && stream_wait_geq(nullptr, nullptr, 0) == cudaSuccess;
+                if (gate) h->i8_started = started;
                 pk::phase_begin(h, 1);
                 PK_CUDA(h, pk::launch_cholesky(h, s, pc, wsp, h->d_info + a0, planes0 + (size_t)o * plane_bytes));
                 pk::phase_end(h);
+                h->i8_started = nullptr;
+                if (gate) PK_CUDA(h, stream_wait_geq(h->stream2, started, (unsigned)((pc < h->sm_count) ? pc : h->sm_count)));
                 pk::phase_begin(h, 2);
                 PK_CUDA(h, pk::launch_nll_epilogue(h, s, pc, wsp, h->d_out + a0, h->cap_C, h->d_info + a0));
                 pk::phase_end(h);

@@ -255,7 +255,7 @@ template <bool TIMING>
 __global__ void __launch_bounds__(THREADS, 1)
 chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int C, int nt, int ld,
                size_t elems, size_t plane_stride, size_t cand_stride, double piv_tol, double* __restrict__ ws,
-               int8_t* __restrict__ planes, int32_t* __restrict__ info, unsigned int* __restrict__ queue, long long* __restrict__ dbg) {
+               int8_t* __restrict__ planes, int32_t* __restrict__ info, unsigned int* __restrict__ queue, long long* __restrict__ dbg, int l2_mode, unsigned int* __restrict__ started) {
     long long tmv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
     const bool tmw = TIMING && threadIdx.x == 96;
 #define PK_TM(i)                          \
@@ -277,6 +277,9 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int np = nt * PK_TILE;
     if (tid == 0) {
+        // ragged-first pipeline (pk_nll_batch): the Psi kernel of the whole waves is released by a stream wait on this
+        // counter, i.e. once every CTA of this short wave holds its SM
+        if (started) atomicAdd(started, 1u);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
@@ -323,6 +326,9 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (warp == 8) {
             // ---------------- TMA producer ----------------
             if (lane == 0) {
+                // L2 policy of the digit tiles: row block j (B) is read again by every pass of the block column and should
+                // stay, the rows of a pass (A) come back only a whole block column later and should go first
+                const unsigned long long polA = l2_policy_evict_first(), polB = l2_policy_evict_last();
                 for (int j = 1; j < nt; ++j) {
                     const int npass = (np + PK_AUG_ROWS - j * PK_TILE + BM - 1) / BM;
                     bool waited = false;
@@ -344,8 +350,10 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                             unsigned char* sa = smem + st * STAGE_BYTES;
                             mbar_arrive_expect_tx(full + st, (unsigned)STAGE_BYTES);
-                            tma_load_4d(sa, &tmA, c * BK, r0, 0, cand, full + st);
-                            tma_load_4d(sa + S * A_SLICE, &tmB, c * BK, j * PK_TILE, 0, cand, full + st);
+                            if (l2_mode & 1) tma_load_4d_hint(sa, &tmA, c * BK, r0, 0, cand, full + st, polA);
+                            else tma_load_4d(sa, &tmA, c * BK, r0, 0, cand, full + st);
+                            if (l2_mode & 2) tma_load_4d_hint(sa + S * A_SLICE, &tmB, c * BK, j * PK_TILE, 0, cand, full + st, polB);
+                            else tma_load_4d(sa + S * A_SLICE, &tmB, c * BK, j * PK_TILE, 0, cand, full + st);
                         }
                     }
                 }
@@ -560,12 +568,14 @@ cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double*
     e = cudaMemsetAsync(queue, 0, sizeof(unsigned int), h->stream);
     if (e != cudaSuccess) return e;
     const int grid = (C < h->sm_count) ? C : h->sm_count;
+    unsigned int* started = h->i8_started;
+    h->i8_started = nullptr;
     if (h->env_cta_timing) {  // diagnostic (PK_CTA_TIMING): per-phase cycle counts of one FP64 warp, printed to stderr
         long long* dbg = nullptr;
         cudaMalloc((void**)&dbg, sizeof(long long) * 8 * grid);
         cudaMemset(dbg, 0, sizeof(long long) * 8 * grid);
         ci8::chol_i8_kernel<true><<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride, cand_stride,
-                                                                        h->pivot_tol, ws, planes, info, queue, dbg);
+                                                                        h->pivot_tol, ws, planes, info, queue, dbg, h->i8_l2_mode, nullptr);
         cudaStreamSynchronize(h->stream);
         std::vector<long long> host(8 * (size_t)grid);
         cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
@@ -580,7 +590,7 @@ cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double*
                 grid, sum[6], sum[0] / nc, sum[1] / nc, sum[2] / nc, sum[3] / nc, sum[4] / nc, sum[5] / nc);
     } else {
         ci8::chol_i8_kernel<false><<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride,
-                                                                         cand_stride, h->pivot_tol, ws, planes, info, queue, nullptr);
+                                                                         cand_stride, h->pivot_tol, ws, planes, info, queue, nullptr, h->i8_l2_mode, started);
     }
     h->launches++;
     return cudaGetLastError();

@@ -149,6 +149,25 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, in
         "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"((unsigned)__cvta_generic_to_shared(bar))
         : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): tiles that are re-read soon stay, streamed ones go first
+__device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, unsigned long long* bar,
+                                                 unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"((unsigned)__cvta_generic_to_shared(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, unsigned long long* bar) {
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(

@@ -9,7 +9,7 @@
 #include "../../include/pykriging_b200.h"
 #include "pk_common.cuh"
 
-constexpr int PK_QUEUE_SLOTS = 64;
+constexpr int PK_QUEUE_SLOTS = 64;  // the last counter is the "CTAs resident" word of the ragged-first pipeline (pk_nll_batch)
 constexpr int PK_MAX_DEVICES = 64;  // per-device "function attributes set" flags (cudaFuncSetAttribute is per device)
 
 struct pk_handle {
@@ -28,6 +28,7 @@ struct pk_handle {
     // this handle's calls are slices of a population / query set of these sizes (pk_set_shard_hint; 0 = no hint):
     // automatic kernel selection uses them, so a shard computes bit for bit what the unsharded call would
     int64_t hint_C = 0, hint_m = 0;
+    int64_t call_C = 0;                    // population of the pk_nll_batch call in flight: its chunks and pipeline parts pick the kernel the whole call picks
     size_t gang_bytes = 0;
     void* d_gang = nullptr;                // gang barrier counters + partial-sum scratch of the persistent Cholesky (gang mode)
     unsigned int* d_queue = nullptr;       // candidate queues of the persistent Cholesky kernel (PK_QUEUE_SLOTS counters)
@@ -48,12 +49,15 @@ struct pk_handle {
     std::vector<cudaEvent_t> ev_pipe;
     std::vector<cudaEvent_t> ev_pred;       // upload / compute / download events of the chunked host path of pk_predict_batch
     int overlap = 0;                       // 1: two-part pipeline on two streams (pk_set_overlap; measured slower, off)
+    int ragged_first = 1;                  // INT8 Cholesky: a short last wave is factorised first, under the Psi kernel of the whole waves (PK_RAGGED_FIRST=0: off)
     // experiment knobs, read from the environment ONCE in pk_create (never on the per-generation path)
     std::string env_split;                 // PK_SPLIT: comma-separated part sizes of a resident chunk
     int env_gang = 0;                      // PK_CHOL_GANG: forced gang size (0 = automatic)
     int env_ctas_per_sm = 2;               // PK_CHOL_CTAS_PER_SM
     bool env_cta_timing = false;           // PK_CTA_TIMING: per-phase cycle counts of the persistent kernel on stderr
     bool env_cta_alias = false;            // PK_CTA_ALIAS: timing experiment (results are garbage)
+    unsigned int* i8_started = nullptr;    // when set, every CTA of the next INT8 Cholesky launch counts itself in here as it starts (and the pointer is cleared)
+    int i8_l2_mode = 0;                    // INT8 Cholesky, L2 policy of the digit tiles: bit 0 rows of a pass evict-first, bit 1 row block j evict-last (PK_I8_L2)
     int* d_fault = nullptr;                // sticky device flag: some candidate came back with info < 0 (a spin-wait timed out)
 
     // model data (pk_set_data)
@@ -155,6 +159,9 @@ cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const dou
                              const double* lambda, int mode, double* ws, int32_t* info);
 // planes: digit planes of the INT8-tensor-core Cholesky (cholesky_i8_plane_bytes per candidate) or null (DMMA kernels only)
 cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info, int8_t* planes = nullptr);
+// the Cholesky kernel launch_cholesky runs for a call of C candidates (1 per-block-column launches, 2 one CTA per candidate,
+// 3 gangs, 4 task mode, 5 INT8 tensor cores); looks at the hinted / whole-call population, never at the size of a part
+int cholesky_pick_variant(pk_handle* h, const TiledShape& s, int C, bool have_planes);
 size_t cholesky_i8_plane_bytes(const TiledShape& s);
 cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double* ws, int8_t* planes, int32_t* info);
 cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);

@@ -578,10 +578,12 @@ cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, doub
     return cudaGetLastError();
 }
 
-cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info, int8_t* planes) {
+int cholesky_pick_variant(pk_handle* h, const TiledShape& s, int C, bool have_planes) {
+    const bool planes = have_planes;
     int v = h->chol_variant;
     if (v == 5 && (!planes || s.with_inverse || s.np > 16384)) v = 0;  // INT32 level sums: 7 x 2^14 x K < 2^31  // the INT8 kernel factorises populations only (pk_fit: gangs)
-    const int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;  // the population this call is a slice of
+    int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;  // the population this call is a slice of
+    if (h->call_C > Ceff) Ceff = h->call_C;                   // ... or a chunk / pipeline part of
     // Automatic: task mode (pk_chol_cta.cu).  Its tiles are produced by the arithmetic of the one-CTA-per-candidate kernel,
     // so a candidate's result does not depend on how many candidates it is evaluated with -- a single SLSQP evaluation,
     // a stencil of 21, a shard of 128 and a population of 1024 agree bit for bit -- and its task granularity follows the
@@ -608,6 +610,11 @@ cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws
     // pk_fit (one matrix + L^-T rows): the gang kernel, the inverse rows being further panel passes (per-block-column
     // kernels when pinned to variant 1 or when the matrix has fewer than three block columns)
     if (s.with_inverse) v = (h->chol_variant != 1 && cholesky_gang_size(h, s, Ceff, true) > 1) ? 3 : 1;
+    return v;
+}
+
+cudaError_t launch_cholesky(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info, int8_t* planes) {
+    const int v = cholesky_pick_variant(h, s, C, planes != nullptr);
     if (v == 5) return launch_cholesky_i8(h, s, C, ws, planes, info);
     if (v == 4) return launch_cholesky_task(h, s, C, ws, info);
     return (v >= 2) ? launch_cholesky_cta(h, s, C, ws, info) : launch_cholesky_steps(h, s, C, ws, info);
