@@ -212,6 +212,13 @@ int pk_set_predict_contraction(pk_handle *h, int mode);
  * shard computes bit for bit what the unsharded call computes.  0 = no hint. */
 int pk_set_shard_hint(pk_handle *h, int64_t population, int64_t query_points);
 
+/* ... and where the slice starts: the next pk_nll_batch calls evaluate candidates `first_candidate`, `first_candidate` + 1,
+ * ... of the hinted population (reset to 0 by pk_set_shard_hint).  The kernel a candidate is factorised by can depend on
+ * its position in the population -- the few candidates of a short last wave of the INT8 kernel ("stragglers") go through
+ * the DMMA task kernel when the matrices are large -- and with the offset a shard makes the same choice per candidate as
+ * the unsharded call (reference loop: krige.py:436-451, evaluated in order). */
+int pk_set_shard_offset(pk_handle *h, int64_t first_candidate);
+
 /* pk_nll_batch pipelining experiment (the candidate loop of krige.py:429-452 has no such notion: it is
  * strictly sequential).  0 (default): Psi -> Cholesky -> epilogue per resident chunk on one stream.
  * 1: a population larger than the number of resident Cholesky CTAs is split in two parts and the Psi

@@ -21,7 +21,7 @@ EXPORTS = [
     "pk_predict_batch", "pk_append_point", "pk_get_psi", "pk_get_U", "pk_psi_batch", "pk_synchronize", "pk_stream",
     "pk_launch_count", "pk_set_workspace_limit", "pk_set_pivot_tolerance", "pk_set_profiling", "pk_phase_times",
     "pk_fp64_peak", "pk_debug_math", "pk_set_cholesky_variant", "pk_set_predict_variant", "pk_set_overlap",
-    "pk_set_shard_hint", "pk_set_task_options", "pk_task_schedule", "pk_opt_set", "pk_opt_get", "pk_opt_evaluate",
+    "pk_set_shard_hint", "pk_set_shard_offset", "pk_set_task_options", "pk_task_schedule", "pk_opt_set", "pk_opt_get", "pk_opt_evaluate",
     "pk_ga_step", "pk_pso_step", "pk_set_predict_contraction",
 ]
 
@@ -81,6 +81,8 @@ def load():
     lib.pk_set_predict_variant.restype = ctypes.c_int
     lib.pk_set_shard_hint.argtypes = [hp, ctypes.c_int64, ctypes.c_int64]
     lib.pk_set_shard_hint.restype = ctypes.c_int
+    lib.pk_set_shard_offset.argtypes = [hp, ctypes.c_int64]
+    lib.pk_set_shard_offset.restype = ctypes.c_int
     lib.pk_set_overlap.argtypes = [hp, ctypes.c_int]
     lib.pk_set_overlap.restype = ctypes.c_int
     lib.pk_set_predict_contraction.argtypes = [hp, ctypes.c_int]
@@ -352,6 +354,11 @@ class Handle(object):
         """The next calls evaluate a slice of a population / query set of these sizes (0 = no hint): kernel
         selection follows the whole, so a shard reproduces the unsharded result bit for bit."""
         self._check(self.lib.pk_set_shard_hint(self._h, int(population), int(query_points)), "pk_set_shard_hint")
+
+    def set_shard_offset(self, first_candidate=0):
+        """The next pk_nll_batch calls evaluate candidates first_candidate, first_candidate + 1, ... of the hinted
+        population (the kernel a candidate takes can depend on its position: stragglers of a short last wave)."""
+        self._check(self.lib.pk_set_shard_offset(self._h, int(first_candidate)), "pk_set_shard_offset")
 
     def set_workspace_limit(self, nbytes):
         self._check(self.lib.pk_set_workspace_limit(self._h, int(nbytes)), "pk_set_workspace_limit")

@@ -168,6 +168,7 @@ int pk_create(pk_handle** out, int device) {
     h->env_cta_alias = getenv("PK_CTA_ALIAS") != nullptr;
     if (const char* v = getenv("PK_RAGGED_FIRST")) h->ragged_first = atoi(v) != 0;
     if (const char* v = getenv("PK_I8_L2")) h->i8_l2_mode = atoi(v) & 3;
+    if (const char* v = getenv("PK_STRAGGLERS")) h->stragglers = atoi(v) != 0;
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);
@@ -246,6 +247,13 @@ int pk_set_shard_hint(pk_handle* h, int64_t population, int64_t query_points) {
     if (!h || population < 0 || query_points < 0) return 1;
     h->hint_C = population;
     h->hint_m = query_points;
+    h->hint_first = 0;
+    return 0;
+}
+
+int pk_set_shard_offset(pk_handle* h, int64_t first_candidate) {
+    if (!h || first_candidate < 0) return 1;
+    h->hint_first = first_candidate;
     return 0;
 }
 
@@ -373,6 +381,21 @@ static int ensure_workspace(pk_handle* h, size_t per_matrix_bytes, int C, int* c
     return 0;
 }
 
+// Stragglers.  The INT8 kernel runs whole waves of sm_count candidates at the latency of ONE factorisation, so the few
+// candidates of a short last wave cost a whole wave (150 particles at n = 4096: 2 x 43 ms for 148 + 2).  When the matrices
+// are small relative to the population the ragged-first pipeline below hides that wave under the Psi kernel; when they are
+// large (the Psi kernel of the whole waves is shorter than a wave) the stragglers are factorised by the DMMA task kernel,
+// which spreads a handful of candidates over every SM.  Which candidates are stragglers is a property of the POPULATION
+// (hinted size, global index), never of the call: a shard, a chunk and the whole population agree on every candidate's kernel
+// and therefore on its bits.  Returns the global index of the first straggler (= Ceff: none).
+static int64_t first_straggler(pk_handle* h, const pk::TiledShape& s, int64_t Ceff) {
+    if (!h->stragglers || h->chol_variant != 0) return Ceff;
+    const int64_t slots = h->sm_count, rem = Ceff % slots, whole = Ceff - rem;
+    if (whole == 0 || rem == 0 || rem * 16 > slots * 7) return Ceff;  // <= 64 of 148: beyond that the short wave is worth its latency
+    if (whole * (h->k + 1) * 2 >= (int64_t)3 * s.n) return Ceff;      // Psi of the whole waves outlasts a wave: ragged first hides it
+    return whole;
+}
+
 // Split a resident chunk of `cc` candidates into pipeline parts: Psi of part i+1 is built on stream2 while part i is
 // factorised on the main stream.
 //  * INT8-tensor-core Cholesky (one CTA per candidate and SM, a wave of sm_count candidates costs the latency of ONE
@@ -478,6 +501,38 @@ int pk_nll_batch(pk_handle* h, int C, const double* theta, const double* p, cons
         } call_scope(h, C);
         for (int c0 = 0; c0 < C; c0 += chunk) {
             const int cc = (C - c0 < chunk) ? (C - c0) : chunk;
+            {
+                // stragglers of the population in this chunk: one Psi launch, the whole waves on the INT8 tensor cores, the
+                // stragglers in task mode
+                int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;
+                const int64_t g0 = (h->hint_C > 0 ? h->hint_first : 0) + c0;
+                const int64_t B = (pk::cholesky_pick_variant(h, s, cc, true) == 5) ? first_straggler(h, s, Ceff) : Ceff;
+                if (B < g0 + cc) {
+                    const int n_main = (B > g0) ? (int)(B - g0) : 0, n_strag = cc - n_main;
+                    pk::phase_begin(h, 0);
+                    cudaError_t pe = pk::launch_psi_build(h, s, cc, d_theta + (size_t)c0 * k, d_p + (size_t)c0 * k,
+                                                          d_lambda ? d_lambda + c0 : nullptr, mode, h->d_ws, h->d_info + c0);
+                    pk::phase_end(h);
+                    PK_CUDA(h, pe);
+                    pk::phase_begin(h, 1);
+                    h->queue_slot = 0;
+                    h->part_variant = 4;
+                    pe = pk::launch_cholesky(h, s, n_strag, h->d_ws + (size_t)n_main * s.elems(), h->d_info + c0 + n_main, nullptr);
+                    if (pe == cudaSuccess && n_main > 0) {
+                        h->queue_slot = 1;
+                        h->part_variant = 5;
+                        pe = pk::launch_cholesky(h, s, n_main, h->d_ws, h->d_info + c0, planes0);
+                    }
+                    h->part_variant = 0;
+                    h->queue_slot = 0;
+                    pk::phase_end(h);
+                    PK_CUDA(h, pe);
+                    pk::phase_begin(h, 2);
+                    PK_CUDA(h, pk::launch_nll_epilogue(h, s, cc, h->d_ws, h->d_out + c0, h->cap_C, h->d_info + c0));
+                    pk::phase_end(h);
+                    continue;
+                }
+            }
             // Parts of the resident chunk: Psi of part i+1 (stream2) runs while part i is factorised (stream).
             std::vector<int> parts;
             plan_parts(h, s, cc, parts);

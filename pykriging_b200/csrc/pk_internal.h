@@ -28,6 +28,9 @@ struct pk_handle {
     // this handle's calls are slices of a population / query set of these sizes (pk_set_shard_hint; 0 = no hint):
     // automatic kernel selection uses them, so a shard computes bit for bit what the unsharded call would
     int64_t hint_C = 0, hint_m = 0;
+    int64_t hint_first = 0;                // ... and where the slice starts in that population (pk_set_shard_offset)
+    int part_variant = 0;                  // transient: the Cholesky kernel of the next launch_cholesky (pk_nll_batch runs the stragglers of a population in task mode)
+    int stragglers = 1;                    // PK_STRAGGLERS=0: never peel the candidates of a short last wave off the INT8 kernel
     int64_t call_C = 0;                    // population of the pk_nll_batch call in flight: its chunks and pipeline parts pick the kernel the whole call picks
     size_t gang_bytes = 0;
     void* d_gang = nullptr;                // gang barrier counters + partial-sum scratch of the persistent Cholesky (gang mode)

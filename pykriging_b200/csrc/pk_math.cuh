@@ -151,7 +151,9 @@ __device__ __forceinline__ double exp2_lean4k(double pd, double lh, double ll, u
     double q = fma(r, c_e2q[2], c_e2q[1]);
     q = fma(r, q, c_e2q[0]);
     double T;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_saddr | (unsigned)(k8 & 0x7ff8)));
+    // base + offset (the base is 32 KB aligned, so this is the OR): the uniform base rides in the load's address mode
+    // (LDS [R + UR]) instead of being copied into a vector register for a LOP3 per call
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_saddr + (unsigned)(k8 & 0x7ff8)));
     const double v = fma(T * r, q, T);
     int hi;
     asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(hi) : "r"(k8 >> 15), "r"(__double2hiint(v)));
@@ -169,7 +171,7 @@ __device__ __forceinline__ double expneg_4k(double S, unsigned tab_saddr) {
     double q = fma(r, 1.6666666666666666e-01, 0.5);
     q = fma(r, q, 1.0);                         // (e^r - 1) / r up to r^2/6
     double T;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_saddr | (unsigned)((ki & 4095) << 3)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_saddr + (unsigned)((ki & 4095) << 3)));
     const double v = fma(T * r, q, T);
     if (!(S < 1.0e5)) return (S != S) ? S : 0.0;  // NaN propagates, huge S underflows
     return scale_pow2(v, ki >> 12);

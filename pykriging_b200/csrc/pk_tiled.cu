@@ -580,6 +580,7 @@ cudaError_t launch_cholesky_steps(pk_handle* h, const TiledShape& s, int C, doub
 
 int cholesky_pick_variant(pk_handle* h, const TiledShape& s, int C, bool have_planes) {
     const bool planes = have_planes;
+    if (h->part_variant && !s.with_inverse) return h->part_variant;
     int v = h->chol_variant;
     if (v == 5 && (!planes || s.with_inverse || s.np > 16384)) v = 0;  // INT32 level sums: 7 x 2^14 x K < 2^31  // the INT8 kernel factorises populations only (pk_fit: gangs)
     int64_t Ceff = (h->hint_C > C) ? h->hint_C : (int64_t)C;  // the population this call is a slice of

@@ -69,6 +69,7 @@ class matrixops(object):
             return h.nll_batch(theta, p, lam, mode)
 
         def eval_slice(lo, hi):
+            h.set_shard_offset(lo)
             o = h.nll_batch(theta[lo:hi], p[lo:hi], None if lam is None else lam[lo:hi], mode)
             return np.stack([o["nll"], o["mu"], o["sigma2"], o["lndet"], o["info"].astype(np.float64)], axis=1)
 

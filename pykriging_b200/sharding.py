@@ -171,6 +171,7 @@ def sharded_nll_device(handle, theta, p, lam, mode, group=None):
         if hi > lo:
             try:
                 r = buf["rows"]
+                handle.set_shard_offset(lo)   # this slice starts at candidate lo of the hinted population
                 handle.nll_batch_raw(hi - lo, np.ascontiguousarray(theta[lo:hi]), np.ascontiguousarray(p[lo:hi]),
                                      None if lam is None else np.ascontiguousarray(lam[lo:hi]), mode,
                                      r[0], r[1], r[2], r[3], buf["info"])

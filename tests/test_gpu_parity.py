@@ -466,6 +466,59 @@ def test_shard_hint_makes_slices_bit_identical(handle):
         assert np.array_equal(np.concatenate([q[name] for q in parts]), whole[name]), name
 
 
+def test_stragglers_of_a_population_take_task_mode_wherever_they_are_evaluated(handle):
+    """180 candidates at n = 1024, k = 2: the INT8 kernel runs waves of one candidate per SM, the 32 candidates of the
+    short second wave would cost a whole wave and are factorised by the DMMA task kernel instead (large matrices, short
+    Psi kernel: pk_api.cu first_straggler).  Which kernel a candidate takes is a property of its position in the
+    POPULATION: slices evaluated with pk_set_shard_hint + pk_set_shard_offset reproduce the unsharded call bit for
+    bit, the candidates of the whole waves carry the bits of the INT8 kernel and the stragglers those of task mode;
+    profiling (serialised phases) does not change a bit either."""
+    import torch
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    rng = np.random.default_rng(17)
+    n, k = 1024, 2
+    X = onp.rlh(n, k, 23)
+    y = onp.f_branin(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    handle.set_data(Xn, yn)
+    C = sms + 32
+    theta = 10.0 ** rng.uniform(-1, 1.5, (C, k))
+    p = rng.uniform(1.2, 2, (C, k))
+    names = ("nll", "mu", "sigma2", "lndet", "info")
+    full = handle.nll_batch(theta, p)
+    assert np.all(full["info"] == 0)
+    handle.set_cholesky_variant(5)
+    i8 = handle.nll_batch(theta, p)
+    handle.set_cholesky_variant(4)
+    task = handle.nll_batch(theta, p)
+    handle.set_cholesky_variant(0)
+    for nm in names:
+        assert np.array_equal(full[nm][:sms], i8[nm][:sms]), nm
+        assert np.array_equal(full[nm][sms:], task[nm][sms:]), nm
+    # the two kernels agree to rounding, but not bit for bit (otherwise this test would prove nothing)
+    assert not np.array_equal(i8["nll"], task["nll"])
+    assert np.max(np.abs(i8["nll"] - task["nll"]) / np.abs(task["nll"])) < 1e-10
+    # slices, in any order
+    handle.set_shard_hint(population=C)
+    try:
+        parts = {}
+        for lo in (120, 0, 60):
+            handle.set_shard_offset(lo)
+            parts[lo] = handle.nll_batch(theta[lo:lo + 60], p[lo:lo + 60])
+    finally:
+        handle.set_shard_hint()
+    for nm in names:
+        assert np.array_equal(np.concatenate([parts[lo][nm] for lo in (0, 60, 120)]), full[nm]), nm
+    handle.set_profiling(True)
+    try:
+        prof = handle.nll_batch(theta, p)
+    finally:
+        handle.set_profiling(False)
+    for nm in names:
+        assert np.array_equal(prof[nm], full[nm]), nm
+
+
 def test_full_size_c3_population_properties(handle):
     """BASELINE config C3 at full size (n = 1024, k = 10, population 1024 = 8.3 GiB of Psi matrices): the oracle
     checks a sample of the candidates; the size-independent properties cover all of them -- a candidate's result

@@ -143,6 +143,9 @@ def test_sharded_paths_bracket_their_slice_with_the_shard_hint():
         def set_shard_hint(self, population=0, query_points=0):
             self.log.append(("hint", int(population), int(query_points)))
 
+        def set_shard_offset(self, first_candidate=0):
+            self.log.append(("offset", int(first_candidate)))
+
         def nll_batch(self, theta, p, lam, mode):
             self.log.append(("nll", theta.shape[0]))
             z = np.zeros(theta.shape[0])
@@ -161,7 +164,7 @@ def test_sharded_paths_bracket_their_slice_with_the_shard_hint():
     m.__dict__.update(_has_U=True, _pending_factor=None, mu=0.5, SigmaSqr=1.0, theta=np.ones(2), pl=np.ones(2) * 2, k=2)
     out = m._pk_nll_population(np.ones((13, 2)), np.ones((13, 2)), None, 0)
     assert out["nll"].shape == (13,)
-    assert fake.log == [("hint", 13, 0), ("nll", 13), ("hint", 0, 0)]
+    assert fake.log == [("hint", 13, 0), ("offset", 0), ("nll", 13), ("hint", 0, 0)]
     fake.log.clear()
     batched = m._pk_predict
     batched(np.zeros((11, 2)), ("yhat",))
