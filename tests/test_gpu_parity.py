@@ -466,6 +466,43 @@ def test_shard_hint_makes_slices_bit_identical(handle):
         assert np.array_equal(np.concatenate([q[name] for q in parts]), whole[name]), name
 
 
+def test_int8_cholesky_layouts_agree_bit_for_bit():
+    """The INT8 Cholesky stores the digit planes with the rows of every group of 8 permuted (pk_chol_i8.cu PERM), so that
+    accumulators leave the TMEM as A fragments and the triangular solve needs no warp shuffles.  The first layout is kept
+    behind PK_I8_PERM=0: both perform the same arithmetic on every element -- same bits, also for a failing candidate, for
+    augmented rows whose exponent grows (right-hand side of wide range) and for a matrix order that is not a multiple of
+    the tile."""
+    import os
+
+    from pykriging_b200._lib import Handle
+
+    n, k, C = 770, 3, 40
+    X = onp.rlh(n, k, 31)
+    y = onp.f_squared(X) * np.exp(6.0 * X[:, 0])   # values over several orders of magnitude
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    rng = np.random.default_rng(5)
+    theta = 10.0 ** rng.uniform(-2, 1.5, (C, k))
+    p = rng.uniform(1.1, 2, (C, k))
+    theta[7] = 1e-9   # numerically singular
+    p[7] = 2.0
+    outs = []
+    for perm in ("0", "1"):
+        os.environ["PK_I8_PERM"] = perm
+        try:
+            h = Handle(0)
+        finally:
+            del os.environ["PK_I8_PERM"]
+        try:
+            h.set_data(Xn, yn)
+            h.set_cholesky_variant(5)
+            outs.append(h.nll_batch(theta, p))
+        finally:
+            h.close()
+    assert np.sum(outs[0]["info"] != 0) >= 1 and np.sum(outs[0]["info"] == 0) >= C - 4
+    for nm in ("nll", "mu", "sigma2", "lndet", "info"):
+        assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
+
+
 def test_stragglers_of_a_population_take_task_mode_wherever_they_are_evaluated(handle):
     """180 candidates at n = 1024, k = 2: the INT8 kernel runs waves of one candidate per SM, the 32 candidates of the
     short second wave would cost a whole wave and are factorised by the DMMA task kernel instead (large matrices, short
