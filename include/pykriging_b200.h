@@ -169,7 +169,10 @@ int pk_set_pivot_tolerance(pk_handle *h, double tol);
  * candidate, so a candidate's bits do not depend on the size or order of the call.
  * Automatic: the INT8 kernel for populations that fill their waves of one candidate per SM to 60 % or more (42 % from
  * n = 1473 on; counted on the whole population when the call is a shard, pk_set_shard_hint) at n > 704, task mode
- * otherwise, gangs for pk_fit. */
+ * otherwise, gangs for pk_fit.  A short last wave of the INT8 kernel (population mod SM count) is either factorised
+ * first, under the Psi kernel of the whole waves (small matrices: default population 300 = 4 + 2 x 148), or -- large
+ * matrices, at most 64 candidates -- handed to the task kernel ("stragglers": 150 particles at n = 4096); the choice
+ * follows from the population size and the candidate's index in it (pk_set_shard_offset), never from the call. */
 int pk_set_cholesky_variant(pk_handle *h, int variant);
 
 /* Tuning knobs of task mode (variant 4); none of them changes a bit of the result.  A panel task takes up to
