@@ -170,6 +170,7 @@ int pk_create(pk_handle** out, int device) {
     if (const char* v = getenv("PK_I8_L2")) h->i8_l2_mode = atoi(v) & 3;
     if (const char* v = getenv("PK_STRAGGLERS")) h->stragglers = atoi(v) != 0;
     if (const char* v = getenv("PK_I8_PERM")) h->i8_perm = atoi(v) != 0;
+    if (const char* v = getenv("PK_I8_QUIET")) h->i8_quiet = atoi(v) != 0;
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);

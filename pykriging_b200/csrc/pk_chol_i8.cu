@@ -80,6 +80,7 @@ __device__ __forceinline__ unsigned long long digit_bytes(double xs) {
 }
 
 // 64 x 64 factorisation of T (shared memory, stride TS) by the eight FP64 warps; see cta::diag_tile (pk_chol_cta.cu)
+template <bool QUIET>
 __device__ __forceinline__ int factor_tile(double* T, double* Dsm, const double* diag0, volatile int* ctl, double piv_tol,
                                            int warp, int lane) {
     if (warp == 0) {
@@ -98,7 +99,8 @@ __device__ __forceinline__ int factor_tile(double* T, double* Dsm, const double*
                 const int bad = cta::diag_block_factor(T, Dsm, diag0, kb + 1, piv_tol, lane);
                 if (bad && lane == 0) ctl[1] = bad;
             } else {
-                cta::trailing_update_rest<8>(T, kb, warp, lane);
+                if (QUIET) cta::trailing_update_rest_quiet<8>(T, kb, warp, lane);
+                else cta::trailing_update_rest<8>(T, kb, warp, lane);
             }
             wbar();
             if (ctl[1]) return ctl[1];
@@ -308,6 +310,7 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     volatile int* ctl = ctl_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int np = nt * PK_TILE;
+    const bool quiet = (l2_mode & 4) != 0;  // warp 4 leaves the scheduler to warp 0's pivot chain (factor_tile)
     if (tid == 0) {
         // ragged-first pipeline (pk_nll_batch): the Psi kernel of the whole waves is released by a stream wait on this
         // counter, i.e. once every CTA of this short wave holds its SM
@@ -522,7 +525,7 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         if (tid == 0) ctl[1] = 0;
                         wbar();
-                        const int bad = factor_tile(T, Dsm, diag0, ctl, piv_tol, warp, lane);
+                        const int bad = quiet ? factor_tile<true>(T, Dsm, diag0, ctl, piv_tol, warp, lane) : factor_tile<false>(T, Dsm, diag0, ctl, piv_tol, warp, lane);
                         if (bad) {
                             if (tid == 0) {
                                 info[cand] = row0 + bad;  // dpotrf convention: order of the failing minor
@@ -627,7 +630,7 @@ cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double*
         cudaMemset(dbg, 0, sizeof(long long) * 8 * grid);
         auto kfn = perm ? ci8::chol_i8_kernel<true, true> : ci8::chol_i8_kernel<true, false>;
         kfn<<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride, cand_stride, h->pivot_tol, ws, planes,
-                                                     info, queue, dbg, h->i8_l2_mode, nullptr);
+                                                     info, queue, dbg, h->i8_l2_mode | (h->i8_quiet ? 4 : 0), nullptr);
         cudaStreamSynchronize(h->stream);
         std::vector<long long> host(8 * (size_t)grid);
         cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
@@ -643,7 +646,7 @@ cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double*
     } else {
         auto kfn = perm ? ci8::chol_i8_kernel<false, true> : ci8::chol_i8_kernel<false, false>;
         kfn<<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride, cand_stride, h->pivot_tol, ws, planes,
-                                                     info, queue, nullptr, h->i8_l2_mode, started);
+                                                     info, queue, nullptr, h->i8_l2_mode | (h->i8_quiet ? 4 : 0), started);
     }
     h->launches++;
     return cudaGetLastError();

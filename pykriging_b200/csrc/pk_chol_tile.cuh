@@ -128,5 +128,22 @@ __device__ __forceinline__ void trailing_update_rest(double* T, int kb, int warp
     }
 }
 
+// The same for a CTA whose warps 0 and 4 share a scheduler (eight FP64 warps, one CTA per SM: the INT8 kernel): warp 4 stays
+// out, so that the sequential pivot chain of warp 0 -- the critical path of the tile -- has its scheduler's FP64 pipe to
+// itself instead of queueing behind warp 4's DMMAs (16 cycles each); the six other warps share the blocks.
+template <int NBR = 8>
+__device__ __forceinline__ void trailing_update_rest_quiet(double* T, int kb, int warp, int lane) {
+    if (warp == 4) return;
+    const int slot = (warp < 4) ? warp - 1 : warp - 2;  // warps 1 2 3 5 6 7 -> 0 .. 5
+    int cnt = 0;
+    for (int bi = kb + 1; bi < NBR; ++bi) {
+        for (int bl = kb + 1; bl <= min(bi, 7); ++bl) {
+            if (bi == kb + 1) continue;  // (kb+1, kb+1)
+            if (cnt++ % 6 != slot) continue;
+            trailing_block(T, kb, bi, bl, lane);
+        }
+    }
+}
+
 }  // namespace cta
 }  // namespace pk
