@@ -79,33 +79,53 @@ __device__ __forceinline__ unsigned long long digit_bytes(double xs) {
     return ((unsigned long long)__double2ll_rn(xs) + B) ^ B;
 }
 
-// 64 x 64 factorisation of T (shared memory, stride TS) by the eight FP64 warps; see cta::diag_tile (pk_chol_cta.cu)
-template <bool QUIET>
+// 64 x 64 factorisation of T (shared memory, stride TS) by the eight FP64 warps; see cta::diag_tile (pk_chol_cta.cu).
+// TM (PK_CTA_TIMING builds), ft != nullptr in thread 0 only: cycles of {first diagonal block + barrier, panel scale + barrier,
+// block (kb+1, kb+1), pivot chains, barrier after the chain} as warp 0 sees them (the warp is re-converged around every
+// reading: a diverged warp takes the slow path of the shuffles)
+template <bool QUIET, bool TM>
 __device__ __forceinline__ int factor_tile(double* T, double* Dsm, const double* diag0, volatile int* ctl, double piv_tol,
-                                           int warp, int lane) {
+                                           int warp, int lane, long long* ft = nullptr) {
+    long long tp = (TM && ft) ? clock64() : 0;
+#define PK_FT(i)                             \
+    if (TM) {                                \
+        __syncwarp();                        \
+        if (ft) {                            \
+            const long long tn_ = clock64(); \
+            ft[i] += tn_ - tp;               \
+            tp = tn_;                        \
+        }                                    \
+        __syncwarp();                        \
+    }
     if (warp == 0) {
         const int bad = cta::diag_block_factor(T, Dsm, diag0, 0, piv_tol, lane);
         if (bad && lane == 0) ctl[1] = bad;
     }
     wbar();
+    PK_FT(0)
     if (ctl[1]) return ctl[1];
     for (int kb = 0; kb < 8; ++kb) {
         cta::panel_scale_blocks<8>(T, Dsm, kb, warp, lane);
         wbar();
+        PK_FT(1)
         if (kb < 7) {
             if (warp == 0) {
                 cta::trailing_block(T, kb, kb + 1, kb + 1, lane);
                 __syncwarp();
+                PK_FT(2)
                 const int bad = cta::diag_block_factor(T, Dsm, diag0, kb + 1, piv_tol, lane);
                 if (bad && lane == 0) ctl[1] = bad;
+                PK_FT(3)
             } else {
                 if (QUIET) cta::trailing_update_rest_quiet<8>(T, kb, warp, lane);
                 else cta::trailing_update_rest<8>(T, kb, warp, lane);
             }
             wbar();
+            PK_FT(4)
             if (ctl[1]) return ctl[1];
         }
     }
+#undef PK_FT
     return 0;
 }
 
@@ -292,6 +312,9 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int8_t* __restrict__ planes, int32_t* __restrict__ info, unsigned int* __restrict__ queue, long long* __restrict__ dbg, int l2_mode, unsigned int* __restrict__ started) {
     long long tmv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
     const bool tmw = TIMING && threadIdx.x == 96;
+    long long ftv[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // TIMING: thread 0's view of the tile factorisation (factor_tile)
+    const bool tm0 = TIMING && threadIdx.x == 0;
+    long long tjv[24] = {};                       // TIMING: tile factorisation per block column (thread 96)
 #define PK_TM(i)                          \
     if (tmw) {                            \
         const long long tn_ = clock64();  \
@@ -525,7 +548,8 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         if (tid == 0) ctl[1] = 0;
                         wbar();
-                        const int bad = quiet ? factor_tile<true>(T, Dsm, diag0, ctl, piv_tol, warp, lane) : factor_tile<false>(T, Dsm, diag0, ctl, piv_tol, warp, lane);
+                        const int bad = quiet ? factor_tile<true, TIMING>(T, Dsm, diag0, ctl, piv_tol, warp, lane, tm0 ? ftv : nullptr)
+                                              : factor_tile<false, TIMING>(T, Dsm, diag0, ctl, piv_tol, warp, lane, tm0 ? ftv : nullptr);
                         if (bad) {
                             if (tid == 0) {
                                 info[cand] = row0 + bad;  // dpotrf convention: order of the failing minor
@@ -535,6 +559,7 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             continue;
                         }
                         if (tid < PK_TILE) M[(size_t)(row0 + tid) * ld + row0 + tid] = T[tid * TS + tid];  // L_ii: ln|Psi| (nll_epilogue_kernel)
+                        if (tmw && j < 24) tjv[j] += clock64() - tprev;
                         PK_TM(2)
                     }
                     if (in_tile || nmi == 0) continue;
@@ -559,7 +584,11 @@ chol_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 #undef PK_TM
     if (tmw) {
-        for (int i = 0; i < 8; ++i) dbg[8 * blockIdx.x + i] = tmv[i];
+        for (int i = 0; i < 8; ++i) dbg[40 * blockIdx.x + i] = tmv[i];
+        for (int i = 0; i < 24; ++i) dbg[40 * blockIdx.x + 16 + i] = tjv[i];
+    }
+    if (tm0) {
+        for (int i = 0; i < 8; ++i) dbg[40 * blockIdx.x + 8 + i] = ftv[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -626,23 +655,30 @@ cudaError_t launch_cholesky_i8(pk_handle* h, const TiledShape& s, int C, double*
     const bool perm = h->i8_perm != 0;  // permuted digit-plane layout (shuffle-free solve); 0 = the first layout (PK_I8_PERM)
     if (h->env_cta_timing) {  // diagnostic (PK_CTA_TIMING): per-phase cycle counts of one FP64 warp, printed to stderr
         long long* dbg = nullptr;
-        cudaMalloc((void**)&dbg, sizeof(long long) * 8 * grid);
-        cudaMemset(dbg, 0, sizeof(long long) * 8 * grid);
+        cudaMalloc((void**)&dbg, sizeof(long long) * 40 * grid);
+        cudaMemset(dbg, 0, sizeof(long long) * 40 * grid);
         auto kfn = perm ? ci8::chol_i8_kernel<true, true> : ci8::chol_i8_kernel<true, false>;
         kfn<<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride, cand_stride, h->pivot_tol, ws, planes,
                                                      info, queue, dbg, h->i8_l2_mode | (h->i8_quiet ? 4 : 0), nullptr);
         cudaStreamSynchronize(h->stream);
-        std::vector<long long> host(8 * (size_t)grid);
+        std::vector<long long> host(40 * (size_t)grid);
         cudaMemcpy(host.data(), dbg, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost);
         cudaFree(dbg);
-        double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double sum[40] = {};
         for (int b = 0; b < grid; ++b)
-            for (int i = 0; i < 8; ++i) sum[i] += (double)host[8 * b + i];
+            for (int i = 0; i < 40; ++i) sum[i] += (double)host[40 * b + i];
         const double nc = sum[6] > 0 ? sum[6] : 1;
         fprintf(stderr,
                 "[pk i8 timing] perm %d, grid %d, candidates %.0f; cycles per candidate (warp 3): wait for MMAs %.0f, drain %.0f, tile "
                 "factorisation %.0f, solve %.0f, digits %.0f, end of column %.0f\n",
                 (int)perm, grid, sum[6], sum[0] / nc, sum[1] / nc, sum[2] / nc, sum[3] / nc, sum[4] / nc, sum[5] / nc);
+        fprintf(stderr,
+                "[pk i8 timing] tile factorisation seen by warp 0: first diagonal block %.0f, panel scale + barrier %.0f, block (kb+1, kb+1) "
+                "%.0f, pivot chains %.0f, barrier after the chain %.0f\n",
+                sum[8] / nc, sum[9] / nc, sum[10] / nc, sum[11] / nc, sum[12] / nc);
+        fprintf(stderr, "[pk i8 timing] tile factorisation per block column (its MMAs of pass 1 run meanwhile):");
+        for (int j = 0; j < nt && j < 24; ++j) fprintf(stderr, " %.0f", sum[16 + j] / nc);
+        fprintf(stderr, "\n");
     } else {
         auto kfn = perm ? ci8::chol_i8_kernel<false, true> : ci8::chol_i8_kernel<false, false>;
         kfn<<<grid, ci8::THREADS, smem, h->stream>>>(tmA, tmB, C, nt, s.ld, s.elems(), plane_stride, cand_stride, h->pivot_tol, ws, planes,
