@@ -236,6 +236,10 @@ __device__ __forceinline__ void slice_store(double (&acc)[2][8][2], double down,
             }
     const int srow = lane >> 1, shalf = lane & 1;
     int8_t* gdst = P + (size_t)(row_first + srow) * np + col0 + shalf * 32;
+    // The staging round trip of plane t (2-byte stores, warp barrier, 16-byte loads) is latency bound -- the INT8 MMAs of the
+    // next pass keep the shared memory busy meanwhile -- so the global stores of plane t wait until the pieces of plane t+1
+    // are on their way: the loads have a whole plane's PRMT / STS work to come back.
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
 #pragma unroll
     for (int t = 0; t < S; ++t) {
         // digit t+1 = byte 6 - t of Y: bytes 4..6 in the high word
@@ -250,12 +254,16 @@ __device__ __forceinline__ void slice_store(double (&acc)[2][8][2], double down,
                 *reinterpret_cast<unsigned short*>(stg + (mi * 8 + fr) * STG_LD + ni * 8 + 2 * q) = (unsigned short)pr;
             }
         __syncwarp();
-        const uint4 v0 = *reinterpret_cast<const uint4*>(stg + srow * STG_LD + shalf * 32);
-        const uint4 v1 = *reinterpret_cast<const uint4*>(stg + srow * STG_LD + shalf * 32 + 16);
-        *reinterpret_cast<uint4*>(gdst + (size_t)t * plane_stride) = v0;
-        *reinterpret_cast<uint4*>(gdst + (size_t)t * plane_stride + 16) = v1;
+        if (t > 0) {
+            *reinterpret_cast<uint4*>(gdst + (size_t)(t - 1) * plane_stride) = v0;
+            *reinterpret_cast<uint4*>(gdst + (size_t)(t - 1) * plane_stride + 16) = v1;
+        }
+        v0 = *reinterpret_cast<const uint4*>(stg + srow * STG_LD + shalf * 32);
+        v1 = *reinterpret_cast<const uint4*>(stg + srow * STG_LD + shalf * 32 + 16);
         __syncwarp();
     }
+    *reinterpret_cast<uint4*>(gdst + (size_t)(S - 1) * plane_stride) = v0;
+    *reinterpret_cast<uint4*>(gdst + (size_t)(S - 1) * plane_stride + 16) = v1;
 }
 
 // Augmented rows (1^T -> a, y^T -> d) after their block of column j has been solved (values in acc[0][..], logical rows 0, 1

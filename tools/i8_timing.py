@@ -20,7 +20,7 @@ Xn, yn, _, _ = onp.normalize_data(X, y)
 for C in [int(a) for a in sys.argv[1:]] or [1024]:
     c = np.concatenate([onp.candidates_uniform(C // 2, k, 10), onp.candidates_loguniform(C - C // 2, k, 20, lo=-2)])
     th, p = np.ascontiguousarray(c[:, :k]), np.ascontiguousarray(c[:, k:])
-    for env in ({"PK_CTA_TIMING": "1"}, {"PK_CTA_TIMING": "1", "PK_I8_TILE": "0"}):
+    for env in ({}, {"PK_CTA_TIMING": "1"}):
         os.environ.update(env)
         h = _lib.Handle()
         for kk in env:
