@@ -171,6 +171,7 @@ int pk_create(pk_handle** out, int device) {
     if (const char* v = getenv("PK_STRAGGLERS")) h->stragglers = atoi(v) != 0;
     if (const char* v = getenv("PK_I8_PERM")) h->i8_perm = atoi(v) != 0;
     if (const char* v = getenv("PK_I8_QUIET")) h->i8_quiet = atoi(v) != 0;
+    if (const char* v = getenv("PK_PSI_CONST")) h->psi_const = atoi(v) != 0;
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);
@@ -187,12 +188,19 @@ int pk_destroy(pk_handle* h) {
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->dX, h->dy, h->d_theta, h->d_p, h->d_lambda, h->d_out, h->d_info, h->d_ws, h->d_fit, h->d_try,
                     h->d_psi, h->d_linv, h->d_ad, h->d_w, h->d_q, h->d_qout, h->d_hp, h->d_queue, h->d_fit_hp, h->d_try_hp, h->d_pscratch, h->d_gang, h->d_gridinfo, h->d_tasks, h->d_taskws, h->d_fault, h->d_opt[0], h->d_opt[1], h->d_opt[2],
-                    h->d_opt[3], h->d_opt[4], h->d_opt_idx, h->d_opt_r, h->d_linv_i8, h->d_linv_scale, h->d_psi_i8};
+                    h->d_opt[3], h->d_opt[4], h->d_opt_idx, h->d_opt_r, h->d_linv_i8, h->d_linv_scale, h->d_psi_i8, h->d_thp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_pipe) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_pred) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i)
+        if (h->psi_stream[i]) {
+            cudaStreamSynchronize(h->psi_stream[i]);
+            cudaStreamDestroy(h->psi_stream[i]);
+        }
+    for (int i = 0; i < 3; ++i)
+        if (h->psi_event[i]) cudaEventDestroy(h->psi_event[i]);
     if (h->stream2) {
         cudaStreamSynchronize(h->stream2);
         cudaStreamDestroy(h->stream2);

@@ -60,6 +60,11 @@ struct pk_handle {
     bool env_cta_timing = false;           // PK_CTA_TIMING: per-phase cycle counts of the persistent kernel on stderr
     bool env_cta_alias = false;            // PK_CTA_ALIAS: timing experiment (results are garbage)
     unsigned int* i8_started = nullptr;    // when set, every CTA of the next INT8 Cholesky launch counts itself in here as it starts (and the pointer is cleared)
+    int psi_const = 1;                     // Psi kernel, 8 <= k <= 10: (theta, p) through constant memory, one launch per candidate group (PK_PSI_CONST=0: shared memory)
+    double* d_thp = nullptr;               // (theta_d, p_d) pairs of the population (source of the constant-memory copies)
+    size_t thp_cap = 0;
+    cudaStream_t psi_stream[2] = {nullptr, nullptr};  // side streams of the per-group Psi launches (forked from / joined to the caller's stream)
+    cudaEvent_t psi_event[3] = {nullptr, nullptr, nullptr};
     int i8_quiet = 1;                      // INT8 Cholesky, tile factorisation: warp 4 stays out of the trailing update (PK_I8_QUIET=0: all seven warps)
     int i8_perm = 1;                       // INT8 Cholesky: permuted digit-plane layout, shuffle-free triangular solve (PK_I8_PERM=0: first layout)
     int i8_l2_mode = 0;                    // INT8 Cholesky, L2 policy of the digit tiles: bit 0 rows of a pass evict-first, bit 1 row block j evict-last (PK_I8_L2)

@@ -16,6 +16,8 @@
 //   * the sum over dimensions follows NumPy's reduction order (pk_common.cuh), the final exp(-S) is a
 //     Cody-Waite reduced table-driven exponential (< 1 ulp).
 #include "pk_internal.h"
+#include <mutex>
+
 #include "pk_math.cuh"
 
 namespace pk {
@@ -26,6 +28,14 @@ constexpr int PSI_GROUP = 128;  // candidates per CTA (amortises the log2 split 
 // PPT pairs per thread: large K keeps ONE pair per thread so that the per-pair log2 tables (3 registers per
 // dimension) leave room for three resident CTAs per SM -- the per-candidate 2^x chain is latency bound and
 // needs the extra warps more than it needs wider stores.
+// (theta_d, p_d) of one candidate group in constant memory, two buffers (PSI_CONST_MIN_K <= k <= PSI_CONST_MAX_K): the candidate loop reads them
+// through the uniform datapath (LDCU: one register copy per warp) instead of a 16-byte shared-memory broadcast per lane,
+// which costs four cycles of the shared-memory pipe per (candidate, dimension) -- 37 of the kernel's 85 wavefronts per warp
+// and entry (profiles/ncu_psi_pop_r02_u.txt: that pipe is 92 % busy)
+constexpr int PSI_CONST_MIN_K = 8;   // k = 7 (the short summation loop) measured 8 % slower this way, 8 <= k <= 10 8 % faster (profiles/psi_const_r02.jsonl)
+constexpr int PSI_CONST_MAX_K = 10;
+__constant__ double2 c_thp[2][PSI_GROUP * PSI_CONST_MAX_K];
+
 // bytes of the per-CTA arrays in front of the 2^x table
 template <int K, int PPT>
 __host__ __device__ constexpr unsigned psi_small_bytes() {
@@ -33,11 +43,12 @@ __host__ __device__ constexpr unsigned psi_small_bytes() {
                       sizeof(int) * PSI_GROUP);
 }
 
-template <int K, int PPT>
+// CB >= 0: the launch covers ONE candidate group (blockIdx.y = 0, candidates g0 ...), whose (theta, p) lie in c_thp[CB]
+template <int K, int PPT, int CB = -1>
 __global__ void __launch_bounds__(PSI_THREADS, (PPT == 1) ? (K <= 12 ? 3 : 2) : 1)
 psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restrict__ X,
                const double* __restrict__ theta, const double* __restrict__ p,
-               const double* __restrict__ lambda, int mode, double* __restrict__ ws) {
+               const double* __restrict__ lambda, int mode, double* __restrict__ ws, int group0 = 0) {
     constexpr int RB = PSI_THREADS * PPT / PK_TILE;  // rows of the pair block
     constexpr int SPT = PK_TILE / RB;                // row blocks per tile
     extern __shared__ __align__(16) double psi_smem[];
@@ -60,7 +71,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
     while (ti * (ti + 1) / 2 > t) --ti;
     const int tj = t - ti * (ti + 1) / 2;
     const int r0 = ti * PK_TILE + sb * RB, c0 = tj * PK_TILE;
-    const int g0 = blockIdx.y * PSI_GROUP;
+    const int g0 = (group0 + blockIdx.y) * PSI_GROUP;
     const int gn = min(PSI_GROUP, C - g0);
 
     fill_exp2_4096(tab4k, tid, PSI_THREADS);
@@ -123,7 +134,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                 // generic exponents: k table-driven 2^x, theta folded in with an FMA, NumPy's summation tree
                 // term(d) = theta_d * |d|^p_d
                 auto tw = [&](int d, double& th_d) {
-                    const double2 tp = tpg[d];
+                    const double2 tp = (CB >= 0 && K >= PSI_CONST_MIN_K && K <= PSI_CONST_MAX_K) ? c_thp[CB < 0 ? 0 : CB][g * K + d] : tpg[d];
                     th_d = tp.x;
                     return exp2_lean4k(tp.y, lh[q][d], ll[q][d], tab_saddr);
                 };
@@ -264,13 +275,20 @@ cudaError_t launch_psi_build_generic(pk_handle* h, const TiledShape& s, int C, c
                                      const double* lambda, int mode, double* ws);
 cudaError_t launch_aug_init(pk_handle* h, const TiledShape& s, int C, double* ws, int32_t* info);
 
+// interleaves theta and p of a population into (theta_d, p_d) pairs: the source of the constant-memory copies
+__global__ void pack_thp_kernel(size_t m, const double* __restrict__ theta, const double* __restrict__ p, double2* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_double2(theta[i], p[i]);
+}
+
 template <int K>
 static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
                                   const double* lambda, int mode, double* ws) {
     constexpr int PPT = (K > 6) ? 1 : 4;
     constexpr int RB = PSI_THREADS * PPT / PK_TILE;
     const int nt = s.np / PK_TILE;
-    dim3 grid(nt * (nt + 1) / 2 * (PK_TILE / RB), (C + PSI_GROUP - 1) / PSI_GROUP);
+    const int groups = (C + PSI_GROUP - 1) / PSI_GROUP;
+    dim3 grid(nt * (nt + 1) / 2 * (PK_TILE / RB), groups);
     // dynamic shared memory starts 1 KB into the CTA's window (the first KB is reserved by the system): room for
     // the table at the next 32 KB boundary wherever the base actually lies
     constexpr size_t smem = ((psi_small_bytes<K, PPT>() + 0x400 + 0x7fff) & ~(size_t)0x7fff) + 0x8000;
@@ -278,8 +296,77 @@ static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, cons
     bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(psi_pop_kernel<K, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if constexpr (K >= PSI_CONST_MIN_K && K <= PSI_CONST_MAX_K) {
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(psi_pop_kernel<K, PPT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(psi_pop_kernel<K, PPT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
         if (e != cudaSuccess) return e;
         attr_done = true;
+    }
+    if constexpr (K >= PSI_CONST_MIN_K && K <= PSI_CONST_MAX_K) if (h->psi_const) {
+        // One launch per candidate group, (theta, p) of the group in constant memory.  The two buffers belong to the DEVICE
+        // (every handle of the process shares them): g_thp_used[b] is recorded behind the last kernel that read buffer b and
+        // waited for by the next copy into it, under a lock that keeps wait / copy / launch / record of one group together.
+        // Several groups: they alternate between two side streams forked from the caller's stream, so that the next group's
+        // CTAs fill the tail of the previous launch (one stream: 5.66 instead of 5.26 ms per 1024 candidates at n = 1024, k = 10;
+        // shared-memory loads: 5.71 ms).
+        const size_t m = (size_t)C * K;
+        if (h->thp_cap < m) {
+            if (h->d_thp) cudaFree(h->d_thp);
+            h->d_thp = nullptr;
+            h->thp_cap = 0;
+            cudaError_t e = cudaMalloc((void**)&h->d_thp, sizeof(double2) * m);
+            if (e != cudaSuccess) return e;
+            h->thp_cap = m;
+        }
+        static std::mutex g_thp_lock;
+        static cudaEvent_t g_thp_used[PK_MAX_DEVICES][2] = {};
+        cudaEvent_t* used = g_thp_used[h->device & (PK_MAX_DEVICES - 1)];
+        cudaError_t e = cudaSuccess;
+        const bool fan = groups > 1;
+        if (fan && !h->psi_stream[0]) {
+            for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&h->psi_stream[i], cudaStreamNonBlocking);
+            for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->psi_event[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        double2* thp = reinterpret_cast<double2*>(h->d_thp);
+        const size_t pb = (m + 255) / 256;
+        pack_thp_kernel<<<(unsigned)(pb < 296 ? pb : 296), 256, 0, h->stream>>>(m, theta, p, thp);
+        h->launches++;
+        if (fan) {
+            e = cudaEventRecord(h->psi_event[2], h->stream);
+            for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(h->psi_stream[i], h->psi_event[2], 0);
+            if (e != cudaSuccess) return e;
+        }
+        grid.y = 1;
+        {
+            std::lock_guard<std::mutex> lock(g_thp_lock);
+            for (int b = 0; b < 2 && e == cudaSuccess; ++b)
+                if (!used[b]) e = cudaEventCreateWithFlags(&used[b], cudaEventDisableTiming);
+            for (int g = 0; g < groups && e == cudaSuccess; ++g) {
+                const int gn = (C - g * PSI_GROUP < PSI_GROUP) ? C - g * PSI_GROUP : PSI_GROUP;
+                const int b = g & 1;
+                cudaStream_t st = fan ? h->psi_stream[b] : h->stream;
+                e = cudaStreamWaitEvent(st, used[b], 0);  // never recorded: no wait
+                if (e == cudaSuccess)
+                    e = cudaMemcpyToSymbolAsync(c_thp, thp + (size_t)g * PSI_GROUP * K, sizeof(double2) * (size_t)gn * K,
+                                                sizeof(double2) * (size_t)b * PSI_GROUP * PSI_CONST_MAX_K, cudaMemcpyDeviceToDevice, st);
+                if (e != cudaSuccess) break;
+                if (b == 0)
+                    psi_pop_kernel<K, PPT, 0><<<grid, PSI_THREADS, smem, st>>>(s.n, s.np, s.ld, s.elems(), C, h->dX, theta, p, lambda, mode, ws, g);
+                else
+                    psi_pop_kernel<K, PPT, 1><<<grid, PSI_THREADS, smem, st>>>(s.n, s.np, s.ld, s.elems(), C, h->dX, theta, p, lambda, mode, ws, g);
+                h->launches++;
+                e = cudaEventRecord(used[b], st);
+            }
+        }
+        if (fan) {
+            for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+                e = cudaEventRecord(h->psi_event[i], h->psi_stream[i]);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->psi_event[i], 0);
+            }
+        }
+        return (e != cudaSuccess) ? e : cudaGetLastError();
     }
     psi_pop_kernel<K, PPT><<<grid, PSI_THREADS, smem, h->stream>>>(s.n, s.np, s.ld, s.elems(), C, h->dX, theta, p,
                                                                     lambda, mode, ws);

@@ -503,6 +503,80 @@ def test_int8_cholesky_layouts_agree_bit_for_bit():
         assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
 
 
+def test_psi_constant_memory_path_same_bits_and_handles_share_the_buffers():
+    """8 <= k <= 10: (theta, p) reach the population Psi kernel through constant memory (uniform loads instead of a
+    16-byte shared-memory broadcast per lane), one launch per group of 128 candidates on two side streams, the device's
+    two constant buffers in turn (pk_psi.cu launch_psi_pop).  PK_PSI_CONST=0 keeps the shared-memory loads: same bits, for
+    ragged groups, exact exponents, a failing candidate.  Two handles with different data whose asynchronous calls (device
+    outputs) are queued back to back share the two buffers of the device and must not see each other's hyper-parameters."""
+    import os
+
+    import torch
+
+    from pykriging_b200._lib import Handle
+
+    n, k, C = 700, 10, 300   # 3 groups: 128 + 128 + 44
+    X = onp.rlh(n, k, 41)
+    y = onp.f_stybtang_norm(X)
+    Xn, yn, _, _ = onp.normalize_data(X, y)
+    rng = np.random.default_rng(9)
+    theta = 10.0 ** rng.uniform(-2, 1.5, (C, k))
+    p = rng.uniform(1.0, 2.0, (C, k))
+    p[3] = 2.0
+    p[130, 4] = 1.0
+    theta[7] = 1e-9
+    p[7] = 2.0
+    outs = []
+    for const in ("0", "1"):
+        os.environ["PK_PSI_CONST"] = const
+        try:
+            h = Handle(0)
+        finally:
+            del os.environ["PK_PSI_CONST"]
+        try:
+            h.set_data(Xn, yn)
+            outs.append(h.nll_batch(theta, p))
+        finally:
+            h.close()
+    assert np.sum(outs[0]["info"] == 0) >= C - 4
+    for nm in ("nll", "mu", "sigma2", "lndet", "info"):
+        assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
+    # two handles, different samples and candidates, calls queued without a synchronisation in between
+    X2 = onp.rlh(n, k, 43)
+    y2 = onp.f_stybtang_norm(X2)
+    X2n, y2n, _, _ = onp.normalize_data(X2, y2)
+    theta2 = 10.0 ** rng.uniform(-1, 1, (C, k))
+    p2 = rng.uniform(1.2, 1.9, (C, k))
+    ha, hb = Handle(0), Handle(0)
+    try:
+        ha.set_data(Xn, yn)
+        hb.set_data(X2n, y2n)
+        want_b = hb.nll_batch(theta2, p2)
+        dev = torch.device("cuda:0")
+        ta, pa = torch.from_numpy(theta).to(dev), torch.from_numpy(p).to(dev)
+        tb, pb = torch.from_numpy(theta2).to(dev), torch.from_numpy(p2).to(dev)
+        res = []
+        for rep in range(3):
+            oa = torch.empty((4, C), dtype=torch.float64, device=dev)
+            ob = torch.empty((4, C), dtype=torch.float64, device=dev)
+            ia = torch.empty(C, dtype=torch.int32, device=dev)
+            ib = torch.empty(C, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            ha.nll_batch_raw(C, ta, pa, None, 0, oa[0], oa[1], oa[2], oa[3], ia)
+            hb.nll_batch_raw(C, tb, pb, None, 0, ob[0], ob[1], ob[2], ob[3], ib)
+            res.append((oa, ob, ia, ib))
+        ha.synchronize()
+        hb.synchronize()
+        for oa, ob, ia, ib in res:
+            assert np.array_equal(oa[0].cpu().numpy(), outs[0]["nll"], equal_nan=True)
+            assert np.array_equal(ob[0].cpu().numpy(), want_b["nll"], equal_nan=True)
+            assert np.array_equal(ia.cpu().numpy(), outs[0]["info"])
+            assert np.array_equal(ib.cpu().numpy(), want_b["info"])
+    finally:
+        ha.close()
+        hb.close()
+
+
 def test_stragglers_of_a_population_take_task_mode_wherever_they_are_evaluated(handle):
     """180 candidates at n = 1024, k = 2: the INT8 kernel runs waves of one candidate per SM, the 32 candidates of the
     short second wave would cost a whole wave and are factorised by the DMMA task kernel instead (large matrices, short
