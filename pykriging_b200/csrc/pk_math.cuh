@@ -123,7 +123,10 @@ __device__ __forceinline__ void fill_exp2_4096(double* tab, int tid, int nthread
 // kl of kd holds 32768 (x + 1/8192): bits 3..14 are the table index -- as a byte offset they are OR-ed into
 // the address by the same LOP3 that masks them -- bits 15.. are the binary exponent, and kd with the low
 // three bits cleared is x rounded to the nearest 1/4096: kf.
-__device__ __forceinline__ double exp2_lean4k(double pd, double lh, double ll, unsigned tab_saddr) {
+// `magic` = MAGIC4K; the population Psi kernel passes it in a REGISTER (made opaque to the compiler once per thread): as an
+// immediate it takes the one special-operand slot of the DFMA, and a pd that arrives in a uniform register (constant-memory
+// hyper-parameters, pk_psi.cu) would be copied into vector registers first -- two moves per call.
+__device__ __forceinline__ double exp2_lean4k(double pd, double lh, double ll, unsigned tab_saddr, double magic = MAGIC4K) {
 #ifdef PK_EXP2_4K_MASKED
     // first version: x rounded to 2^-15, low three bits masked off (one LOP3 + one register move more per call)
     const double kd = fma(pd, lh, MAGIC32K + HALF_STEP_4096);
@@ -143,9 +146,9 @@ __device__ __forceinline__ double exp2_lean4k(double pd, double lh, double ll, u
     // x = pd * lh rounded to the nearest multiple of 2^-12 by the magic add: the low word of kd is 4096 x in two's
     // complement -- bits 0..11 the table index, bits 12.. the binary exponent -- and kd - MAGIC4K is the rounded x
     // itself.  8 FP64 + 4 integer instructions + 1 shared load.
-    const double kd = fma(pd, lh, MAGIC4K);
+    const double kd = fma(pd, lh, magic);
     const int k8 = __double2loint(kd) << 3;      // index as a byte offset in bits 3..14, exponent in bits 15..
-    const double kf = kd - MAGIC4K;
+    const double kf = kd - magic;
     double r = fma(pd, lh, -kf);
     r = fma(pd, ll, r);                          // |r| <= 2^-13
     double q = fma(r, c_e2q[2], c_e2q[1]);

@@ -123,6 +123,9 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
 #pragma unroll
     for (int q = 0; q < PPT; ++q) any_live |= live[q];
 
+    // MAGIC4K = 1.5 * 2^40 in a REGISTER (n >> 30 is zero, which neither the compiler nor ptxas can know): as an immediate it
+    // takes the DFMA's one special-operand slot, and the uniform p_d would be copied into vector registers for every 2^x
+    const double magic4k = (CB >= 0) ? __hiloint2double(0x42780000 | (n >> 30), 0) : MAGIC4K;
     auto one_candidate = [&](int g) {
         double out[PPT];
         const double2* tpg = thp + g * K;
@@ -136,7 +139,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                 auto tw = [&](int d, double& th_d) {
                     const double2 tp = (CB >= 0 && K >= PSI_CONST_MIN_K && K <= PSI_CONST_MAX_K) ? c_thp[CB < 0 ? 0 : CB][g * K + d] : tpg[d];
                     th_d = tp.x;
-                    return exp2_lean4k(tp.y, lh[q][d], ll[q][d], tab_saddr);
+                    return exp2_lean4k(tp.y, lh[q][d], ll[q][d], tab_saddr, magic4k);
                 };
                 double S;
                 if (K < 8) {
