@@ -143,7 +143,9 @@ int pk_pso_step(pk_handle *h, const double *r, const int32_t *nbest, const int32
 /* Block until all work queued on the handle's stream has finished. */
 int pk_synchronize(pk_handle *h);
 
-/* The handle's CUDA stream (a cudaStream_t) so callers can time with events on the launching stream. */
+/* The handle's CUDA stream (a cudaStream_t) so callers can time with events on the launching stream.  The library may fan
+ * part of a call out to side streams of the handle (the per-group Psi launches of a population, the ragged-first pipeline);
+ * they are forked from and joined back to this stream inside the call, so events recorded on it still bracket the work. */
 void *pk_stream(pk_handle *h);
 
 /* Number of kernel launches issued by the handle since creation (bench.py's gpu_launches). */
