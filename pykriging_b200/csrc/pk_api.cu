@@ -172,6 +172,8 @@ int pk_create(pk_handle** out, int device) {
     if (const char* v = getenv("PK_I8_PERM")) h->i8_perm = atoi(v) != 0;
     if (const char* v = getenv("PK_I8_QUIET")) h->i8_quiet = atoi(v) != 0;
     if (const char* v = getenv("PK_PSI_CONST")) h->psi_const = atoi(v) != 0;
+    if (const char* v = getenv("PK_PSI_PPT_SMALL")) h->psi_ppt_small = (atoi(v) == 4) ? 4 : 1;
+    if (const char* v = getenv("PK_PSI_CONST_MINK")) h->psi_const_min_k = atoi(v);
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);

@@ -60,7 +60,9 @@ struct pk_handle {
     bool env_cta_timing = false;           // PK_CTA_TIMING: per-phase cycle counts of the persistent kernel on stderr
     bool env_cta_alias = false;            // PK_CTA_ALIAS: timing experiment (results are garbage)
     unsigned int* i8_started = nullptr;    // when set, every CTA of the next INT8 Cholesky launch counts itself in here as it starts (and the pointer is cleared)
-    int psi_const = 1;                     // Psi kernel, 8 <= k <= 10: (theta, p) through constant memory, one launch per candidate group (PK_PSI_CONST=0: shared memory)
+    int psi_ppt_small = 1;                 // Psi kernel, k <= 6: sample pairs per thread; 4 was round 1's choice (175 registers, one CTA per SM), 1 is 7 - 38 % faster (PK_PSI_PPT_SMALL=4 pins the old one; same bits)
+    int psi_const_min_k = 5;               // smallest k that takes the constant-memory path (PK_PSI_CONST_MINK; k <= 4 measured 5 - 10 % slower that way)
+    int psi_const = 1;                     // Psi kernel, psi_const_min_k <= k <= 10: (theta, p) through constant memory, one launch per candidate group (PK_PSI_CONST=0: shared memory)
     double* d_thp = nullptr;               // (theta_d, p_d) pairs of the population (source of the constant-memory copies)
     size_t thp_cap = 0;
     cudaStream_t psi_stream[2] = {nullptr, nullptr};  // side streams of the per-group Psi launches (forked from / joined to the caller's stream)

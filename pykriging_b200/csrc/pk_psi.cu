@@ -28,11 +28,10 @@ constexpr int PSI_GROUP = 128;  // candidates per CTA (amortises the log2 split 
 // PPT pairs per thread: large K keeps ONE pair per thread so that the per-pair log2 tables (3 registers per
 // dimension) leave room for three resident CTAs per SM -- the per-candidate 2^x chain is latency bound and
 // needs the extra warps more than it needs wider stores.
-// (theta_d, p_d) of one candidate group in constant memory, two buffers (PSI_CONST_MIN_K <= k <= PSI_CONST_MAX_K): the candidate loop reads them
+// (theta_d, p_d) of one candidate group in constant memory, two buffers (pk_handle::psi_const_min_k = 5 <= k <= PSI_CONST_MAX_K; k <= 4: 5 - 10 % slower this way, profiles/psi_const_r02.jsonl): the candidate loop reads them
 // through the uniform datapath (LDCU: one register copy per warp) instead of a 16-byte shared-memory broadcast per lane,
 // which costs four cycles of the shared-memory pipe per (candidate, dimension) -- 37 of the kernel's 85 wavefronts per warp
 // and entry (profiles/ncu_psi_pop_r02_u.txt: that pipe is 92 % busy)
-constexpr int PSI_CONST_MIN_K = 8;   // k = 7 (the short summation loop) measured 8 % slower this way, 8 <= k <= 10 8 % faster (profiles/psi_const_r02.jsonl)
 constexpr int PSI_CONST_MAX_K = 10;
 __constant__ double2 c_thp[2][PSI_GROUP * PSI_CONST_MAX_K];
 
@@ -137,7 +136,7 @@ psi_pop_kernel(int n, int np, int ld, size_t elems, int C, const double* __restr
                 // generic exponents: k table-driven 2^x, theta folded in with an FMA, NumPy's summation tree
                 // term(d) = theta_d * |d|^p_d
                 auto tw = [&](int d, double& th_d) {
-                    const double2 tp = (CB >= 0 && K >= PSI_CONST_MIN_K && K <= PSI_CONST_MAX_K) ? c_thp[CB < 0 ? 0 : CB][g * K + d] : tpg[d];
+                    const double2 tp = (CB >= 0 && K <= PSI_CONST_MAX_K) ? c_thp[CB < 0 ? 0 : CB][g * K + d] : tpg[d];
                     th_d = tp.x;
                     return exp2_lean4k(tp.y, lh[q][d], ll[q][d], tab_saddr, magic4k);
                 };
@@ -284,10 +283,9 @@ __global__ void pack_thp_kernel(size_t m, const double* __restrict__ theta, cons
         out[i] = make_double2(theta[i], p[i]);
 }
 
-template <int K>
-static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
-                                  const double* lambda, int mode, double* ws) {
-    constexpr int PPT = (K > 6) ? 1 : 4;
+template <int K, int PPT>
+static cudaError_t launch_psi_pop_ppt(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
+                                      const double* lambda, int mode, double* ws) {
     constexpr int RB = PSI_THREADS * PPT / PK_TILE;
     const int nt = s.np / PK_TILE;
     const int groups = (C + PSI_GROUP - 1) / PSI_GROUP;
@@ -299,14 +297,14 @@ static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, cons
     bool& attr_done = attr_done_dev[h->device & (PK_MAX_DEVICES - 1)];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(psi_pop_kernel<K, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if constexpr (K >= PSI_CONST_MIN_K && K <= PSI_CONST_MAX_K) {
+        if constexpr (PPT == 1 && K <= PSI_CONST_MAX_K) {
             if (e == cudaSuccess) e = cudaFuncSetAttribute(psi_pop_kernel<K, PPT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(psi_pop_kernel<K, PPT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    if constexpr (K >= PSI_CONST_MIN_K && K <= PSI_CONST_MAX_K) if (h->psi_const) {
+    if constexpr (PPT == 1 && K <= PSI_CONST_MAX_K) if (h->psi_const && K >= h->psi_const_min_k) {
         // One launch per candidate group, (theta, p) of the group in constant memory.  The two buffers belong to the DEVICE
         // (every handle of the process shares them): g_thp_used[b] is recorded behind the last kernel that read buffer b and
         // waited for by the next copy into it, under a lock that keeps wait / copy / launch / record of one group together.
@@ -375,6 +373,17 @@ static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, cons
                                                                     lambda, mode, ws);
     h->launches++;
     return cudaGetLastError();
+}
+
+// sample pairs per thread: one; up to k = 6 round 1 took four (175 registers, one CTA per SM), which measures 7 - 38 % slower
+// (profiles/psi_const_r02.jsonl) and is kept behind PK_PSI_PPT_SMALL=4 (pk_handle::psi_ppt_small); same bits
+template <int K>
+static cudaError_t launch_psi_pop(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,
+                                  const double* lambda, int mode, double* ws) {
+    if constexpr (K <= 6) {
+        if (h->psi_ppt_small == 4) return launch_psi_pop_ppt<K, 4>(h, s, C, theta, p, lambda, mode, ws);
+    }
+    return launch_psi_pop_ppt<K, 1>(h, s, C, theta, p, lambda, mode, ws);
 }
 
 cudaError_t launch_psi_build(pk_handle* h, const TiledShape& s, int C, const double* theta, const double* p,

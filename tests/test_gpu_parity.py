@@ -504,7 +504,7 @@ def test_int8_cholesky_layouts_agree_bit_for_bit():
 
 
 def test_psi_constant_memory_path_same_bits_and_handles_share_the_buffers():
-    """8 <= k <= 10: (theta, p) reach the population Psi kernel through constant memory (uniform loads instead of a
+    """5 <= k <= 10: (theta, p) reach the population Psi kernel through constant memory (uniform loads instead of a
     16-byte shared-memory broadcast per lane), one launch per group of 128 candidates on two side streams, the device's
     two constant buffers in turn (pk_psi.cu launch_psi_pop).  PK_PSI_CONST=0 keeps the shared-memory loads: same bits, for
     ragged groups, exact exponents, a failing candidate.  Two handles with different data whose asynchronous calls (device
@@ -575,6 +575,42 @@ def test_psi_constant_memory_path_same_bits_and_handles_share_the_buffers():
     finally:
         ha.close()
         hb.close()
+
+
+def test_psi_kernel_variants_for_small_k_agree_bit_for_bit():
+    """k <= 6: one sample pair per thread (default) against round 1's four (PK_PSI_PPT_SMALL=4), with the hyper-parameters
+    through shared memory (default for k <= 4) and through constant memory (PK_PSI_CONST_MINK=1): the same arithmetic per
+    entry, the same bits -- k = 3 and k = 6, a matrix order that is not a multiple of the tile, two candidate groups."""
+    import os
+
+    from pykriging_b200._lib import Handle
+
+    for n, k, C in ((300, 3, 150), (330, 6, 140)):
+        X = onp.rlh(n, k, 51 + k)
+        y = onp.f_squared(X)
+        Xn, yn, _, _ = onp.normalize_data(X, y)
+        rng = np.random.default_rng(k)
+        theta = 10.0 ** rng.uniform(-2, 1.5, (C, k))
+        p = rng.uniform(1.0, 2.0, (C, k))
+        p[2] = 2.0
+        outs = []
+        for env in ({}, {"PK_PSI_PPT_SMALL": "4"}, {"PK_PSI_CONST_MINK": "1"}, {"PK_PSI_CONST": "0"}):
+            os.environ.update(env)
+            try:
+                h = Handle(0)
+            finally:
+                for kk in env:
+                    del os.environ[kk]
+            try:
+                h.set_data(Xn, yn)
+                h.set_cholesky_variant(2)   # the tiled path also for these small orders
+                outs.append(h.nll_batch(theta, p))
+            finally:
+                h.close()
+        assert np.sum(outs[0]["info"] == 0) >= C - 4
+        for other in outs[1:]:
+            for nm in ("nll", "mu", "sigma2", "lndet", "info"):
+                assert np.array_equal(outs[0][nm], other[nm], equal_nan=True), (n, k, nm)
 
 
 def test_stragglers_of_a_population_take_task_mode_wherever_they_are_evaluated(handle):

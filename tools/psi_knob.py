@@ -51,7 +51,7 @@ def run(env, n, k, C, reps=5):
 SHAPES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [(1024, 10, 1024), (1024, 10, 128), (1024, 10, 300), (770, 7, 200), (1024, 8, 300), (200, 9, 130), (4096, 6, 16)]
 for n, k, C in SHAPES:
     base = None
-    for env in ({KNOB: "0"}, {}):
+    for env in (({KNOB: "4"}, {KNOB: "1"}) if KNOB == "PK_PSI_PPT_SMALL" else ({KNOB: "99"}, {KNOB: "1"}) if KNOB == "PK_PSI_CONST_MINK" else ({KNOB: "0"}, {})):
         out, line = run(env, n, k, C)
         if base is None:
             base = out
