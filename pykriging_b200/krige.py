@@ -359,13 +359,13 @@ class kriging(matrixops):
     def fittingObjective(self, candidates, args):
         """NegLnLike of every candidate [theta_1..k, p_1..k]: ONE batched device call.
         Cholesky failure -> the reference's penalty, the Python int 10000 (krige.py:447-450)."""
-        cands = np.asarray(candidates, dtype=float)
-        if cands.size == 0:
+        if len(candidates) == 0:
             return []
+        cands, get_cand = self._pk_candidate_rows(candidates)
         k = self.k
         out = self._pk_nll_population(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
                                       None, _lib.MODE_INTERP)
-        return self._pk_fitness_poststate(out, lambda i: cands[i])
+        return self._pk_fitness_poststate(out, get_cand)
 
     def _pk_fitness_poststate(self, out, get_cand):
         """Fitness list + post-state of the reference's candidate loop from the per-candidate scalars of one batched

@@ -61,6 +61,25 @@ class matrixops(object):
         self.__dict__.pop("_pk_shard", None)
         sharding.release_buffers()
 
+    def _pk_candidate_rows(self, candidates):
+        """A population handed over as a list of lists -> (C x width float array, getter of row i).  With sharding enabled
+        only THIS rank's slice of the list is converted (the other rows of the array stay uninitialised: the sharded
+        evaluation reads nothing but its slice, sharding.shard_bounds) -- at 8 ranks the list -> array conversion of a
+        1024 x 20 population, 0.6 ms in CPython, would otherwise be a quarter of a 2.1 ms generation on every rank."""
+        shard = self.__dict__.get("_pk_shard")
+        if shard is not None and isinstance(candidates, (list, tuple)) and len(candidates) >= 64:
+            rank, world = sharding.rank_and_world(shard[0])
+            if world > 1:
+                C = len(candidates)
+                lo, hi = sharding.shard_bounds(C, rank, world)
+                mine = np.asarray(candidates[lo:hi], dtype=float)
+                if mine.ndim == 2:
+                    rows = np.empty((C, mine.shape[1]))
+                    rows[lo:hi] = mine
+                    return rows, (lambda i: rows[i] if lo <= i < hi else np.asarray(candidates[i], dtype=float))
+        rows = np.asarray(candidates, dtype=float)
+        return rows, (lambda i: rows[i])
+
     def _pk_nll_population(self, theta, p, lam, mode):
         """NegLnLike / mu / SigmaSqr / LnDetPsi / info of a population (dict of arrays), sharded if enabled."""
         h = self._pk_handle()

@@ -71,13 +71,13 @@ class regression_kriging(kriging):
     def fittingObjective(self, candidates, args):
         """NegLnLike of every candidate [theta, p, lambda] in ONE batched device call, followed by the
         host post-pass that reproduces the reference's stale-factor semantics."""
-        cands = np.asarray(candidates, dtype=float)
-        if cands.size == 0:
+        if len(candidates) == 0:
             return []
+        cands, get_cand = self._pk_candidate_rows(candidates)
         k = self.k
         out = self._pk_nll_population(np.ascontiguousarray(cands[:, :k]), np.ascontiguousarray(cands[:, k:2 * k]),
                                       np.ascontiguousarray(cands[:, -1]), _lib.MODE_REGRESSION)
-        return self._pk_fitness_poststate(out, lambda i: cands[i])
+        return self._pk_fitness_poststate(out, get_cand)
 
     def _pk_fitness_poststate(self, out, get_cand):
         """regressionkrige.py:163-172, 428-452: a failed factorisation is swallowed, so the candidate repeats the

@@ -74,6 +74,24 @@ def _worker(rank, world, port, count, q):
             assert np.array_equal(again, rows)
             calls[:] = calls[: len(calls) // 2]
         lo, hi = sharding.shard_bounds(count, rank, world)
+        if count >= 64:
+            # a population handed over as a list of lists: with sharding enabled only this rank's slice is converted
+            # (matrixops._pk_candidate_rows) -- the rows of the other ranks are poisoned here and must not be touched
+            from pykriging_b200.matrixops import matrixops
+
+            m = object.__new__(matrixops)
+            m.__dict__["_pk_shard"] = (None, 1)
+            full = np.hstack([theta, p]).tolist()
+            poisoned = [row if lo <= i < hi else ["poison"] * 8 for i, row in enumerate(full)]
+            arr, get = m._pk_candidate_rows(poisoned)
+            assert arr.shape == (count, 8) and np.array_equal(arr[lo:hi], np.hstack([theta, p])[lo:hi])
+            assert np.array_equal(get(lo), arr[lo])
+            arr2, get2 = m._pk_candidate_rows(full)
+            other = 0 if lo > 0 else count - 1
+            assert np.array_equal(get2(other), np.asarray(full[other])) and np.array_equal(get2(hi - 1), arr2[hi - 1])
+            m.__dict__.pop("_pk_shard")
+            arr3, get3 = m._pk_candidate_rows(full)   # not sharded: the whole list
+            assert np.array_equal(arr3, np.hstack([theta, p])) and np.array_equal(get3(other), arr3[other])
         vals = rows[lo:hi, 0]
         best = sharding.global_argmax(vals, lo)
         elite = sharding.broadcast_candidate(np.arange(9.0) + 100 * rank, src=world - 1)
